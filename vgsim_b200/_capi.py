@@ -1,0 +1,301 @@
+"""ctypes binding of libvgsim_b200.so (include/vgsim_b200.h).
+
+The library is the product: it is loaded at import time and a missing/unbuildable library is a hard
+error (no CPU fallback).  Creating a handle needs a CUDA device; everything host-side (parameter
+validation in ``_engine.py``) works without one.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvgsim_b200.so")
+
+NCOUNTERS = 12
+NSUMMARY = 24
+COUNTER_NAMES = ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus", "migNonPlus",
+                 "swapLockdown", "good_attempt", "events", "leaps", "globalInfectious")
+
+c_void_p, c_int, c_int64, c_uint64, c_float, c_char_p = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                         ctypes.c_uint64, ctypes.c_float, ctypes.c_char_p)
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        # in-tree build (nvcc cross-compiles sm_100a without a GPU); raises if nvcc is unavailable
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    P = c_void_p
+    sig = {
+        "vgsim_last_error": (c_char_p, []),
+        "vgsim_version": (c_int, []),
+        "vgsim_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_void_p)]),
+        "vgsim_destroy": (c_int, [P]),
+        "vgsim_set_stream": (c_int, [P, P]),
+        "vgsim_set_seeds": (c_int, [P, P]),
+        "vgsim_upload_params": (c_int, [P, c_int] + [P] * 17),
+        "vgsim_set_replicate_params": (c_int, [P, P]),
+        "vgsim_set_state": (c_int, [P, P, P]),
+        "vgsim_get_state": (c_int, [P, P, P, P, P]),
+        "vgsim_simulate_direct": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
+        "vgsim_simulate_tau": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
+        "vgsim_synchronize": (c_int, [P]),
+        "vgsim_prop_num": (c_int64, [P]),
+        "vgsim_propensities": (c_int, [P, c_int, P, P, P, P]),
+        "vgsim_rates": (c_int, [P, c_int] + [P] * 8),
+        "vgsim_get_counters": (c_int, [P, P, P]),
+        "vgsim_get_event_log": (c_int, [P, c_int, P, c_int64]),
+        "vgsim_get_multievents": (c_int, [P, c_int, c_int64] + [P] * 7),
+        "vgsim_get_tau_log": (c_int, [P, c_int, c_int64, P, P]),
+        "vgsim_set_event_log": (c_int, [P, c_int, P, c_int64, P]),
+        "vgsim_num_lockdowns": (c_int64, [P, c_int]),
+        "vgsim_get_lockdowns": (c_int, [P, c_int, P, P, P]),
+        "vgsim_genealogy": (c_int, [P, P, P, P, c_int]),
+        "vgsim_tree_size": (c_int64, [P, c_int]),
+        "vgsim_get_tree": (c_int, [P, c_int, P, P, P]),
+        "vgsim_num_mutations": (c_int64, [P, c_int]),
+        "vgsim_get_mutations": (c_int, [P, c_int, P, P, P, P, P]),
+        "vgsim_num_migrations": (c_int64, [P, c_int]),
+        "vgsim_get_migrations": (c_int, [P, c_int, P, P, P, P]),
+        "vgsim_summaries": (c_int, [P, P]),
+        "vgsim_summaries_dev": (c_int, [P, ctypes.POINTER(c_void_p)]),
+        "vgsim_launch_count": (c_int64, [P]),
+        "vgsim_test_poisson": (c_int, [P, c_int64, c_uint64, P]),
+        "vgsim_test_hypergeometric": (c_int, [P, P, P, c_int64, P, c_int64, P, P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError here = the library does not export the declared ABI
+        fn.restype = res
+        fn.argtypes = args
+    return lib, tuple(sig)
+
+
+lib, EXPORTS = _load()
+
+
+class VgsimError(RuntimeError):
+    pass
+
+
+def _ck(rc):
+    if rc != 0:
+        raise VgsimError(lib.vgsim_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class Handle:
+    """RAII wrapper of a vgsim_handle (R replicates of one model shape on one CUDA device)."""
+
+    def __init__(self, sites, K, S, replicates=1, param_points=1, device=None):
+        self.sites, self.K, self.S, self.R, self.n_pp = sites, K, S, replicates, param_points
+        self.H = 4 ** sites
+        self._h = c_void_p()
+        _ck(lib.vgsim_create(sites, K, S, replicates, param_points, -1 if device is None else int(device),
+                             ctypes.byref(self._h)))
+        self.P = int(lib.vgsim_prop_num(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib.vgsim_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup
+    def set_stream(self, cuda_stream_ptr):
+        _ck(lib.vgsim_set_stream(self._h, c_void_p(cuda_stream_ptr)))
+
+    def set_seeds(self, seeds):
+        seeds = _arr(seeds, np.uint64)
+        assert seeds.shape == (self.R,)
+        _ck(lib.vgsim_set_seeds(self._h, _p(seeds)))
+
+    def upload_params(self, pp, a, reset_contact_density=True, cd_mask=None):
+        f, i = np.float64, np.int64
+        arrs = [_arr(a.get(k), f) for k in ("b", "d", "s", "mRate", "hapMutType", "sigma")]
+        arrs.append(_arr(a.get("suscType"), i))
+        arrs += [_arr(a.get(k), f) for k in ("T", "m", "cd", "cdBefore", "cdAfter", "startLD", "endLD", "sm")]
+        arrs.append(_arr(a.get("sizes"), i))
+        if cd_mask is None:
+            cd_mask = np.full(self.K, 1 if reset_contact_density else 0, dtype=np.int32)
+        arrs.append(_arr(cd_mask, np.int32))
+        _ck(lib.vgsim_upload_params(self._h, pp, *[_p(x) for x in arrs]))
+
+    def set_replicate_params(self, mapping):
+        m = _arr(mapping, np.int32)
+        _ck(lib.vgsim_set_replicate_params(self._h, _p(m)))
+
+    def set_state(self, Sx, I):
+        Sx, I = _arr(Sx, np.int64), _arr(I, np.int64)
+        assert Sx is None or Sx.shape == (self.R, self.K, self.S)
+        assert I is None or I.shape == (self.R, self.K, self.H)
+        _ck(lib.vgsim_set_state(self._h, _p(Sx), _p(I)))
+
+    def get_state(self, full=False):
+        Sx = np.empty((self.R, self.K, self.S), np.int64)
+        I = np.empty((self.R, self.K, self.H), np.int64)
+        cd = np.empty((self.R, self.K), np.float64)
+        lock = np.empty((self.R, self.K), np.int64)
+        _ck(lib.vgsim_get_state(self._h, _p(Sx), _p(I), _p(cd), _p(lock)))
+        return (Sx, I, cd, lock) if full else (Sx, I)
+
+    # ---- hot path
+    def simulate_direct(self, iterations, sample_size=-1, time=-1.0, attempts=200, sync=True):
+        _ck(lib.vgsim_simulate_direct(self._h, iterations, sample_size, time, attempts))
+        if sync:
+            self.synchronize()
+
+    def simulate_tau(self, iterations, sample_size=-1, time=-1.0, attempts=200, sync=True):
+        _ck(lib.vgsim_simulate_tau(self._h, iterations, sample_size, time, attempts))
+        if sync:
+            self.synchronize()
+
+    def synchronize(self, strict=True):
+        rc = lib.vgsim_synchronize(self._h)
+        if rc != 0 and strict:
+            raise VgsimError(lib.vgsim_last_error().decode())
+        return rc
+
+    def genealogy(self, seed=None, uniform_stream=None, raw_words=False, sync=True):
+        seeds = None
+        if seed is not None:
+            seeds = (np.uint64(seed) + np.arange(self.R, dtype=np.uint64)) if np.isscalar(seed) else _arr(seed, np.uint64)
+            seeds = _arr(seeds, np.uint64)
+        us = offs = None
+        if uniform_stream is not None:
+            if isinstance(uniform_stream, np.ndarray) and uniform_stream.ndim == 1:
+                uniform_stream = [uniform_stream]
+            assert len(uniform_stream) == self.R
+            dt = np.uint64 if raw_words else np.float64
+            parts = [np.ascontiguousarray(u, dtype=dt) for u in uniform_stream]
+            offs = np.zeros(self.R + 1, np.int64)
+            offs[1:] = np.cumsum([len(x) for x in parts])
+            us = np.concatenate(parts) if offs[-1] else np.zeros(1, dt)
+        _ck(lib.vgsim_genealogy(self._h, _p(seeds), _p(us), _p(offs), 1 if raw_words else 0))
+        if sync:
+            self.synchronize()
+
+    # ---- taps and outputs
+    def propensities(self, replicate=0):
+        out = np.empty(self.P, np.float64)
+        dI = np.empty((self.K, self.H), np.float64)
+        dS = np.empty((self.K, self.S), np.float64)
+        tau = np.zeros(1, np.float64)
+        _ck(lib.vgsim_propensities(self._h, replicate, _p(out), _p(dI), _p(dS), _p(tau)))
+        return out, dI, dS, float(tau[0])
+
+    def rates(self, replicate=0):
+        K, H = self.K, self.H
+        r = dict(A=np.empty(K), eff=np.empty((K, K)), maxEBM=np.empty(K), ev=np.empty((K, H, 4)), hp=np.empty((K, H)),
+                 popRate=np.empty(K), migPop=np.empty(K), totals=np.empty(2))
+        _ck(lib.vgsim_rates(self._h, replicate, *[_p(r[k]) for k in ("A", "eff", "maxEBM", "ev", "hp", "popRate",
+                                                                     "migPop", "totals")]))
+        return r
+
+    def get_counters(self):
+        c = np.empty((self.R, NCOUNTERS), np.int64)
+        t = np.empty(self.R, np.float64)
+        _ck(lib.vgsim_get_counters(self._h, _p(c), _p(t)))
+        d = {name: c[:, i].copy() for i, name in enumerate(COUNTER_NAMES)}
+        d["time"] = t
+        return d
+
+    def get_event_log(self, replicate=0):
+        n = int(self.get_counters()["events"][replicate])
+        out = np.zeros((6, n), np.float64)
+        _ck(lib.vgsim_get_event_log(self._h, replicate, _p(out), n))
+        return out
+
+    def get_tau_log(self, replicate=0):
+        L = int(self.get_counters()["leaps"][replicate])
+        counts = np.zeros((L, self.P), np.int32)
+        tt = np.zeros((L, 2), np.float64)
+        _ck(lib.vgsim_get_tau_log(self._h, replicate, L, _p(counts), _p(tt)))
+        return counts, tt
+
+    def get_multievents(self, replicate=0):
+        L = int(self.get_counters()["leaps"][replicate])
+        n = L * self.P
+        i = np.int64
+        num, typ, hap, pop, nhap, npop = (np.zeros(n, i) for _ in range(6))
+        t = np.zeros(n, np.float64)
+        _ck(lib.vgsim_get_multievents(self._h, replicate, n, _p(num), _p(t), _p(typ), _p(hap), _p(pop), _p(nhap), _p(npop)))
+        return dict(num=num, time=t, type=typ, hap=hap, pop=pop, nhap=nhap, npop=npop)
+
+    def set_event_log(self, replicate, chain6xN, I_end):
+        chain = _arr(chain6xN, np.float64)
+        I_end = _arr(I_end, np.int64)
+        _ck(lib.vgsim_set_event_log(self._h, replicate, _p(chain), chain.shape[1], _p(I_end)))
+
+    def get_lockdowns(self, replicate=0):
+        n = int(lib.vgsim_num_lockdowns(self._h, replicate))
+        st, pop, t = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.float64)
+        _ck(lib.vgsim_get_lockdowns(self._h, replicate, _p(st), _p(pop), _p(t)))
+        return st, pop, t
+
+    def get_tree(self, replicate=0):
+        n = int(lib.vgsim_tree_size(self._h, replicate))
+        parent, pop, t = np.zeros(n, np.int64), np.zeros(n, np.int64), np.zeros(n, np.float64)
+        if n:
+            _ck(lib.vgsim_get_tree(self._h, replicate, _p(parent), _p(pop), _p(t)))
+        return parent, pop, t
+
+    def get_mutations(self, replicate=0):
+        n = int(lib.vgsim_num_mutations(self._h, replicate))
+        node, AS, DS, site = (np.zeros(n, np.int64) for _ in range(4))
+        t = np.zeros(n, np.float64)
+        if n:
+            _ck(lib.vgsim_get_mutations(self._h, replicate, _p(node), _p(AS), _p(DS), _p(site), _p(t)))
+        return node, AS, DS, site, t
+
+    def get_migrations(self, replicate=0):
+        n = int(lib.vgsim_num_migrations(self._h, replicate))
+        node, oldp, newp = (np.zeros(n, np.int64) for _ in range(3))
+        t = np.zeros(n, np.float64)
+        if n:
+            _ck(lib.vgsim_get_migrations(self._h, replicate, _p(node), _p(t), _p(oldp), _p(newp)))
+        return node, t, oldp, newp
+
+    def summaries(self):
+        out = np.zeros((self.R, NSUMMARY), np.float64)
+        _ck(lib.vgsim_summaries(self._h, _p(out)))
+        return out
+
+    def summaries_dev_ptr(self):
+        p = c_void_p()
+        _ck(lib.vgsim_summaries_dev(self._h, ctypes.byref(p)))
+        return p.value
+
+    def launch_count(self):
+        return int(lib.vgsim_launch_count(self._h))
+
+
+def test_poisson(lam, seed=1):
+    lam = np.ascontiguousarray(lam, np.float64)
+    out = np.zeros(lam.shape, np.int64)
+    if lib.vgsim_test_poisson(_p(lam), lam.size, seed, _p(out)) != 0:
+        raise VgsimError("vgsim_test_poisson failed")
+    return out
+
+
+def test_hypergeometric(good, bad, sample, raw_words):
+    good, bad, sample = (np.ascontiguousarray(x, np.int64) for x in (good, bad, sample))
+    raw = np.ascontiguousarray(raw_words, np.uint64)
+    out = np.zeros(good.shape, np.int64)
+    used = np.zeros(1, np.int64)
+    if lib.vgsim_test_hypergeometric(_p(good), _p(bad), _p(sample), good.size, _p(raw), raw.size, _p(out), _p(used)) != 0:
+        raise VgsimError("vgsim_test_hypergeometric failed")
+    return out, int(used[0])

@@ -1,0 +1,781 @@
+"""Host side of the engine: the object that sits behind ``Simulator.simulation``.
+
+This is the drop-in replacement for the reference's ``cdef class BirthDeathModel``
+(reference ``src/_BirthDeath.pyx:30-2649``) at the boundary SURVEY.md §8(b) describes:
+same constructor arguments, same ``set_*`` methods / read-only properties (live numpy views),
+same exception types and messages, same ``SimulatePopulation`` / ``SimulatePopulation_tau`` /
+``GetGenealogy`` entry points.  The parameter store and validation are plain Python + numpy; the
+hot path (forward simulation, genealogy) runs in hand-written sm_100a CUDA kernels reached through
+the C ABI of ``libvgsim_b200.so`` (``include/vgsim_b200.h``).  There is no CPU fallback: without the
+library or without a GPU the hot-path calls raise.
+
+Extension over the reference: ``replicates=R`` runs R independent replicates (replicate ``r`` uses
+seed ``seed + r``) in one batched launch; with the default ``R == 1`` the object behaves like the
+reference engine.  Outputs take a ``replicate=`` index.
+"""
+import sys
+
+import numpy as np
+
+from . import _capi
+
+BIRTH, DEATH, SAMPLING, MUTATION, SUSCCHANGE, MIGRATION, MULTITYPE = range(7)  # src/events.pxi:2-8
+
+
+class BirthDeathModel:
+    # ------------------------------------------------------------------ construction (src/_BirthDeath.pyx:70-229)
+    def __init__(self, number_of_sites, populations_number, number_of_susceptible_groups, seed,
+                 sampling_probability, memory_optimization, genome_length, recombination_probability,
+                 replicates=1, device=None):
+        self.check_amount(seed, 'seed', zero=False)
+        self.user_seed = seed
+        self.first_simulation = False
+        if sampling_probability != True and sampling_probability != False:
+            raise ValueError('Incorrect value of sampling probability. Value of sampling probability should be True or False.')
+        self._sampling_probability = sampling_probability
+        if memory_optimization != True and memory_optimization != False:
+            raise ValueError('Incorrect value of memory optimization. Value of memory optimization should be True or False.')
+        self._memory_optimization = memory_optimization
+
+        self.check_amount(number_of_sites, 'number of sites', zero=False)
+        self.sites = number_of_sites
+        self.hapNum = int(4 ** self.sites)
+        self.check_amount(number_of_susceptible_groups, 'number of susceptible groups')
+        self.susNum = number_of_susceptible_groups
+        self.check_amount(populations_number, 'populations number')
+        self.popNum = populations_number
+
+        self.check_value(recombination_probability, 'recombination probability', edge=1)
+        self.recombination = recombination_probability
+        self.check_amount(genome_length, 'genome length')
+        self._genome_length = genome_length
+        self.sitesPosition = np.zeros(self.sites, dtype=np.int64)
+        if self.sites > self._genome_length:
+            raise ValueError('Incorrect value of number of sites or genome length. Genome length should be more or equal number of sites.')
+        if self.sites > 1:
+            for s in range(self.sites):
+                self.sitesPosition[s] = int(s * self._genome_length / (self.sites - 1))
+
+        # memory optimisation (lazy haplotype slots) is a direct-method-only CPU memory
+        # trick; the device path keeps the dense K x H state.  The knobs are kept for API compatibility.
+        if self._memory_optimization:
+            if self.sites > 2:
+                self.maxHapNum = int(4 ** (self.sites - 2))
+                self.addMemoryNum = int(4 ** (self.sites - 2))
+            else:
+                self.maxHapNum = 4
+                self.addMemoryNum = 4
+        else:
+            self.maxHapNum = self.hapNum
+            self.addMemoryNum = 0
+
+        H, K, S, U = self.hapNum, self.popNum, self.susNum, self.sites
+        self.suscType = np.zeros(H, dtype=np.int64)
+        self.bRate = np.full(H, 2.0)
+        self.dRate = np.full(H, 1.0)
+        self.sRate = np.full(H, 0.01)
+        self.mRate = np.full((H, U), 0.01)
+        self._susceptibility = np.zeros((H, S), dtype=float)
+        self._susceptibility[:, 0] = 1.0
+        self.hapMutType = np.ones((H, U, 3), dtype=float)
+
+        self.sizes = np.full(K, 1000000, dtype=np.int64)
+        self._susceptible = np.zeros((K, S), dtype=np.int64)
+        self._susceptible[:, 0] = 1000000
+        self._infectious = np.zeros((K, H), dtype=np.int64)
+        self.contactDensity = np.ones(K, dtype=float)
+        self.contactDensityBeforeLockdown = np.ones(K, dtype=float)
+        self.contactDensityAfterLockdown = np.zeros(K, dtype=float)
+        self.startLD = np.ones(K, dtype=float)
+        self.endLD = np.ones(K, dtype=float)
+        self.samplingMultiplier = np.ones(K, dtype=float)
+        self.suscepTransition = np.zeros((S, S), dtype=float)
+        self.migrationRates = np.zeros((K, K), dtype=float)
+
+        self.check_amount(replicates, 'replicates')
+        self.replicates = replicates
+        self._device = device
+        self._handle = None
+        self._dirty = True  # parameters changed since last upload
+        self._genealogy_done = False
+        self.last_elapsed = None
+
+    # ------------------------------------------------------------------ haplotype index helpers (:1187-1267)
+    def calculate_indexes(self, indexes_list, edge):
+        if isinstance(indexes_list, list):
+            indexes = set()
+            for i in indexes_list:
+                indexes.update(self.calculate_index(i, edge))
+        else:
+            indexes = set(self.calculate_index(indexes_list, edge))
+        return indexes
+
+    def calculate_index(self, index, edge):
+        if isinstance(index, str):
+            out = ['']
+            for ch in index:
+                if ch == '*':
+                    out = [o + letter for o in out for letter in 'ATCG']
+                else:
+                    out = [o + ch for o in out]
+            return [self.calculate_haplotype_from_string(o) for o in out]
+        elif isinstance(index, int):
+            return [index]
+        else:
+            return range(edge)
+
+    def calculate_string_from_haplotype(self, hapNum):
+        letters = "ATCG"
+        string = ""
+        for _ in range(self.sites):
+            string = letters[hapNum % 4] + string
+            hapNum = hapNum // 4
+        return string
+
+    calculate_string = calculate_string_from_haplotype  # the name the reference's printing code expects (Q12)
+
+    def calculate_haplotype_from_string(self, string):
+        code = {'A': 0, 'T': 1, 'C': 2, 'G': 3}
+        haplotype = 0
+        for ch in string[:self.sites]:
+            haplotype = haplotype * 4 + code.get(ch, 0)
+        return haplotype
+
+    def calculate_allele(self, haplotype, site):
+        return (haplotype // 4 ** (self.sites - site - 1)) % 4
+
+    def create_list_for_cycles(self, index, edge):
+        return sorted(self.calculate_indexes(index, edge))
+
+    # ------------------------------------------------------------------ read-only scalars (:1269-1295)
+    @property
+    def seed(self):
+        return self.user_seed
+
+    @property
+    def sampling_probability(self):
+        return self._sampling_probability
+
+    @property
+    def memory_optimization(self):
+        return self._memory_optimization
+
+    @property
+    def number_of_sites(self):
+        return self.sites
+
+    @property
+    def haplotypes_number(self):
+        return self.hapNum
+
+    haplotype_number = haplotypes_number
+
+    @property
+    def populations_number(self):
+        return self.popNum
+
+    @property
+    def number_of_susceptible_groups(self):
+        return self.susNum
+
+    # ------------------------------------------------------------------ validation (:1298-1377), messages pinned by the reference tests
+    def check_amount(self, amount, smth, zero=True):
+        if isinstance(amount, int) == False:
+            raise TypeError('Incorrect type of ' + smth + '. Type should be int.')
+        elif amount <= 0 and zero:
+            raise ValueError('Incorrect value of ' + smth + '. Value should be more 0.')
+        elif amount < 0 and zero == False:
+            raise ValueError('Incorrect value of ' + smth + '. Value should be more or equal 0.')
+
+    def check_value(self, value, smth, edge=None, none=False):
+        if none:
+            if isinstance(value, (int, float)) == False and value is not None:
+                raise TypeError('Incorrect type of ' + smth + '. Type should be int or float or None.')
+        else:
+            if isinstance(value, (int, float)) == False:
+                raise TypeError('Incorrect type of ' + smth + '. Type should be int or float.')
+        if isinstance(value, (int, float)):
+            if edge is None:
+                if value < 0:
+                    raise ValueError('Incorrect value of ' + smth + '. Value should be more or equal 0.')
+            elif value < 0 or value > edge:
+                raise ValueError('Incorrect value of ' + smth + '. Value should be more or equal 0 and equal or less ' + str(edge) + '.')
+
+    def check_indexes(self, index, edge, smth, hap=False, none=True):
+        if isinstance(index, list):
+            for i in index:
+                self.check_index(i, edge, smth, hap=hap, none=none)
+        else:
+            self.check_index(index, edge, smth, hap=hap, none=none)
+
+    def check_index(self, index, edge, smth, hap=False, none=True):
+        if none == False and index is None:
+            raise TypeError('Incorrect type of ' + smth + '. Type should be int.')
+        elif isinstance(index, int):
+            if index < 0 or index >= edge:
+                raise IndexError('There are no such ' + smth + '!')
+        elif isinstance(index, str) and hap:
+            if sum(index.count(c) for c in "ATCG*") != self.sites:
+                raise ValueError('Incorrect haplotype. Haplotype should contain only \"A\", \"T\", \"C\", \"G\", \"*\" and length of haplotype should be equal number of mutations sites.')
+        elif index is not None:
+            if hap:
+                raise TypeError('Incorrect type of haplotype. Type should be int or str or None.')
+            else:
+                raise TypeError('Incorrect type of ' + smth + '. Type should be int or None.')
+
+    def check_list(self, data, smth, length):
+        if isinstance(data, list):
+            if len(data) != length:
+                raise ValueError('Incorrect length of ' + smth + '. Length should be equal ' + str(length) + '.')
+        else:
+            raise TypeError('Incorrect type of ' + smth + '. Type should be list.')
+
+    def check_amount_sus(self, amount, source_type, target_type, population):
+        if self._susceptible[population, source_type] - amount < 0:
+            raise ValueError('Number of susceptible minus amount should be more or equal 0.')
+        if self._susceptible[population, target_type] + amount > self.sizes[population]:
+            raise ValueError('Number of susceptible plus amount should be equal or less population size.')
+
+    def check_amount_inf(self, amount, source_type, target_haplotype, population):
+        if self._susceptible[population, source_type] - amount < 0:
+            raise ValueError('Number of susceptible minus amount should be more or equal 0.')
+        if self._infectious[population, target_haplotype] + amount > self.sizes[population]:
+            raise ValueError('Number of infectious plus amount should be equal or less population size.')
+
+    def check_mig_rate(self):
+        for pn1 in range(self.popNum):
+            summa = 0
+            self.migrationRates[pn1, pn1] = 1.0
+            for pn2 in range(self.popNum):
+                if pn1 != pn2:
+                    summa += self.migrationRates[pn1, pn2]
+                    self.migrationRates[pn1, pn1] -= self.migrationRates[pn1, pn2]
+            if summa > 1:
+                raise ValueError('Incorrect the sum of migration probabilities. The sum of migration probabilities from each population should be equal or less 1.')
+        for pn in range(self.popNum):
+            if self.migrationRates[pn, pn] <= 1e-15:
+                raise ValueError('Incorrect value of migration probability. Value of migration probability from source population to target population should be more 0.')
+
+    # ------------------------------------------------------------------ setters / properties (:1380-1702)
+    @property
+    def initial_haplotype(self):
+        return self.maxHapNum
+
+    def set_initial_haplotype(self, amount):
+        if self._memory_optimization == False:
+            raise ValueError('Incorrect value of memory optimization. Value should be equal \'True\' for work this function.')
+        self.check_amount(amount, 'amount of initial haplotype')
+        self.maxHapNum = self.hapNum if amount >= self.hapNum else amount
+
+    @property
+    def step_haplotype(self):
+        return self.addMemoryNum
+
+    def set_step_haplotype(self, amount):
+        if self._memory_optimization == False:
+            raise ValueError('Incorrect value of memory optimization. Value should be equal \'True\' for work this function.')
+        self.check_amount(amount, 'amount of step haplotype')
+        self.addMemoryNum = amount
+
+    @property
+    def genome_length(self):
+        return self._genome_length
+
+    def set_genome_length(self, genome_length):
+        self.check_amount(genome_length, 'genome length')
+        if self.sites > genome_length:
+            raise ValueError('Incorrect value of number of sites or genome length. Genome length should be more or equal number of sites.')
+        self._genome_length = genome_length
+        for s in range(self.sites):
+            self.sitesPosition[s] = int(s * self._genome_length / (self.sites - 1))
+
+    @property
+    def coinfection_parameters(self):
+        return self.recombination
+
+    def set_coinfection_parameters(self, recombination):
+        self.check_value(recombination, 'recombination probability', edge=1)
+        self.recombination = recombination
+
+    @property
+    def transmission_rate(self):
+        return self.bRate
+
+    def set_transmission_rate(self, rate, haplotype):
+        self.check_value(rate, 'transmission rate')
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        for hn in self.calculate_indexes(haplotype, self.hapNum):
+            self.bRate[hn] = rate
+        self._dirty = True
+
+    @property
+    def recovery_rate(self):
+        return self.dRate
+
+    def set_recovery_rate(self, rate, haplotype):
+        self.check_value(rate, 'recovery rate')
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        for hn in self.calculate_indexes(haplotype, self.hapNum):
+            self.dRate[hn] = rate
+        self._dirty = True
+
+    @property
+    def sampling_rate(self):
+        return self.sRate
+
+    def set_sampling_rate(self, rate, haplotype):
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
+        if self._sampling_probability == True:
+            self.check_value(rate, 'sampling probability', edge=1)
+            for hn in haplotypes:
+                deathRate = self.dRate[hn] + self.sRate[hn]
+                self.dRate[hn] = (1 - rate) * deathRate
+                self.sRate[hn] = rate * deathRate
+        elif self._sampling_probability == False:
+            self.check_value(rate, 'sampling rate')
+            for hn in haplotypes:
+                self.sRate[hn] = rate
+        self._dirty = True
+
+    @property
+    def mutation_rate(self):
+        return self.mRate
+
+    def set_mutation_rate(self, rate, haplotype, mutation):
+        self.check_value(rate, 'mutation rate')
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        self.check_indexes(mutation, self.sites, 'mutation site')
+        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
+        sites = self.calculate_indexes(mutation, self.sites)
+        for hn in haplotypes:
+            for s in sites:
+                self.mRate[hn, s] = rate
+        self._dirty = True
+
+    @property
+    def mutation_probabilities(self):
+        return self.hapMutType
+
+    def set_mutation_probabilities(self, probabilities, haplotype, mutation):
+        self.check_list(probabilities, 'probabilities list', 4)
+        for i in range(4):
+            self.check_value(probabilities[i], 'mutation probabilities')
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        self.check_indexes(mutation, self.sites, 'mutation site')
+        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
+        sites = self.calculate_indexes(mutation, self.sites)
+        for hn in haplotypes:
+            for s in sites:
+                others = list(probabilities)
+                del others[self.calculate_allele(hn, s)]
+                if sum(others) == 0:
+                    raise ValueError('Incorrect probabilities list. The sum of three elements without mutation allele should be more 0.')
+                self.hapMutType[hn, s, :] = others
+        self._dirty = True
+
+    @property
+    def mutation_position(self):
+        return self.sitesPosition
+
+    def set_mutation_position(self, mutation, position):
+        self.check_index(mutation, self.sites, 'number of site', none=False)
+        self.check_index(position, self._genome_length, 'mutation position', none=False)
+        for s in range(self.sites):
+            if self.sitesPosition[s] == position and s != mutation:
+                raise IndexError('Incorrect value of position. Two mutations can\'t have the same position.')
+        self.sitesPosition[mutation] = position
+
+    @property
+    def susceptibility_type(self):
+        return self.suscType
+
+    def set_susceptibility_type(self, susceptibility_type, haplotype):
+        if isinstance(susceptibility_type, int) == False:
+            raise TypeError('Incorrect type of susceptibility type. Type should be int.')
+        elif susceptibility_type < 0 or susceptibility_type >= self.susNum:
+            raise IndexError('There are no such susceptibility type!')
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        for hn in self.calculate_indexes(haplotype, self.hapNum):
+            self.suscType[hn] = susceptibility_type
+        self._dirty = True
+
+    @property
+    def susceptibility(self):
+        return self._susceptibility
+
+    def set_susceptibility(self, rate, haplotype, susceptibility_type):
+        self.check_value(rate, 'susceptibility rate')
+        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
+        self.check_indexes(susceptibility_type, self.susNum, 'susceptibility type')
+        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
+        sus_types = self.calculate_indexes(susceptibility_type, self.susNum)
+        for hn in haplotypes:
+            for sn in sus_types:
+                self._susceptibility[hn, sn] = rate
+        self._dirty = True
+
+    @property
+    def immunity_transition(self):
+        return self.suscepTransition
+
+    def set_immunity_transition(self, rate, source, target):
+        self.check_value(rate, 'immunity transition rate')
+        self.check_indexes(source, self.susNum, 'susceptibility type')
+        self.check_indexes(target, self.susNum, 'susceptibility type')
+        for sn1 in self.calculate_indexes(source, self.susNum):
+            for sn2 in self.calculate_indexes(target, self.susNum):
+                if sn1 != sn2:
+                    self.suscepTransition[sn1, sn2] = rate
+        self._dirty = True
+
+    @property
+    def population_size(self):
+        return self.sizes
+
+    def set_population_size(self, amount, population):
+        if self.first_simulation == True:
+            raise ValueError('Changing population size is available only before first simulation!')
+        self.check_amount(amount, 'population size')
+        self.check_index(population, self.popNum, 'population')
+        for pn in self.calculate_index(population, self.popNum):
+            self.sizes[pn] = amount
+            self._susceptible[pn, 0] = amount
+            self._susceptible[pn, 1:] = 0
+        self._dirty = True
+
+    @property
+    def susceptible(self):
+        return self._susceptible
+
+    def set_susceptible(self, amount, source_type, target_type, population):
+        # The reference raises TypeError here unconditionally (it calls check_amount(amount) without
+        # the `smth` argument, src/_BirthDeath.pyx:1596, quirk Q11).  The replacement implements the
+        # documented behaviour instead (move `amount` hosts between susceptibility groups).
+        if self.first_simulation:
+            raise ValueError('This function is available only before first simulation!')
+        self.check_amount(amount, 'amount')
+        self.check_index(source_type, self.susNum, 'susceptibility type')
+        self.check_index(target_type, self.susNum, 'susceptibility type')
+        if source_type == target_type:
+            raise ValueError('Source and target susceptibility type shouldn\'t be equal!')
+        self.check_indexes(population, self.popNum, 'population')
+        for pn in self.calculate_indexes(population, self.popNum):
+            self.check_amount_sus(amount, source_type, target_type, pn)
+            self._susceptible[pn, source_type] -= amount
+            self._susceptible[pn, target_type] += amount
+        self._dirty = True
+
+    @property
+    def infectious(self):
+        return self._infectious
+
+    def set_infectious(self, amount, source_type, target_haplotype, population):
+        # see set_susceptible: broken upstream (Q11); implemented as documented.
+        if self.first_simulation:
+            raise ValueError('This function is available only before first simulation!')
+        self.check_amount(amount, 'amount')
+        self.check_index(source_type, self.susNum, 'susceptibility type')
+        self.check_index(target_haplotype, self.hapNum, 'haplotype', hap=True)
+        self.check_indexes(population, self.popNum, 'population')
+        haplotypes = self.calculate_index(target_haplotype, self.hapNum)
+        for pn in self.calculate_indexes(population, self.popNum):
+            for hn in haplotypes:
+                self.check_amount_inf(amount, source_type, hn, pn)
+                self._susceptible[pn, source_type] -= amount
+                self._infectious[pn, hn] += amount
+        self._dirty = True
+
+    @property
+    def contact_density(self):
+        return self.contactDensity
+
+    def set_contact_density(self, value, population):
+        self.check_value(value, 'contact density')
+        self.check_indexes(population, self.popNum, 'population')
+        for pn in self.calculate_indexes(population, self.popNum):
+            self.contactDensity[pn] = value
+            self.contactDensityBeforeLockdown[pn] = value
+        self._dirty = True
+        self._cd_changed = True
+
+    @property
+    def npi(self):
+        return [self.contactDensityAfterLockdown, self.startLD, self.endLD]
+
+    def set_npi(self, parameters, population):
+        self.check_list(parameters, 'npi parameters', 3)
+        self.check_value(parameters[0], 'first npi parameter')
+        self.check_value(parameters[1], 'second npi parameter', edge=1)
+        self.check_value(parameters[2], 'third npi parameter', edge=1)
+        self.check_indexes(population, self.popNum, 'population')
+        for pn in self.calculate_indexes(population, self.popNum):
+            self.contactDensityAfterLockdown[pn] = parameters[0]
+            self.startLD[pn] = parameters[1]
+            self.endLD[pn] = parameters[2]
+        self._dirty = True
+
+    @property
+    def sampling_multiplier(self):
+        return self.samplingMultiplier
+
+    def set_sampling_multiplier(self, multiplier, population):
+        self.check_value(multiplier, 'sampling multiplier')
+        self.check_indexes(population, self.popNum, 'population')
+        for pn in self.calculate_indexes(population, self.popNum):
+            self.samplingMultiplier[pn] = multiplier
+        self._dirty = True
+
+    @property
+    def migration_probability(self):
+        return self.migrationRates
+
+    def set_migration_probability(self, probability, source, target):
+        self.check_value(probability, 'migration probability', edge=1)
+        self.check_indexes(source, self.popNum, 'population')
+        self.check_indexes(target, self.popNum, 'population')
+        for pn1 in self.calculate_indexes(source, self.popNum):
+            for pn2 in self.calculate_indexes(target, self.popNum):
+                if pn1 != pn2:
+                    self.migrationRates[pn1, pn2] = probability
+        self.check_mig_rate()
+        self._dirty = True
+
+    def set_total_migration_probability(self, total_probability):
+        self.check_value(total_probability, 'total migration probability', edge=1)
+        source_rate = 1.0 - total_probability
+        target_rate = total_probability / (self.popNum - 1)
+        self.migrationRates[:, :] = target_rate
+        np.fill_diagonal(self.migrationRates, source_rate)
+        self.check_mig_rate()
+        self._dirty = True
+
+    # ------------------------------------------------------------------ device plumbing
+    def param_arrays(self):
+        """The parameter block in the order the C ABI (and the test oracle) takes it."""
+        c = np.ascontiguousarray
+        return dict(b=c(self.bRate), d=c(self.dRate), s=c(self.sRate), mRate=c(self.mRate),
+                    hapMutType=c(self.hapMutType), sigma=c(self._susceptibility), suscType=c(self.suscType),
+                    T=c(self.suscepTransition), m=c(self.migrationRates), cd=c(self.contactDensity),
+                    cdBefore=c(self.contactDensityBeforeLockdown), cdAfter=c(self.contactDensityAfterLockdown),
+                    startLD=c(self.startLD), endLD=c(self.endLD), sm=c(self.samplingMultiplier), sizes=c(self.sizes))
+
+    def _ensure_handle(self):
+        if self._handle is None:
+            self._handle = _capi.Handle(self.sites, self.popNum, self.susNum, self.replicates, 1, self._device)
+            seeds = (np.uint64(self.user_seed) + np.arange(self.replicates, dtype=np.uint64)).astype(np.uint64)
+            self._handle.set_seeds(seeds)
+        return self._handle
+
+    def _sync_params(self):
+        h = self._ensure_handle()
+        if self._dirty:
+            h.upload_params(0, self.param_arrays(), reset_contact_density=getattr(self, '_cd_changed', True))
+            self._cd_changed = False
+            self._dirty = False
+        if not self.first_simulation:
+            R = self.replicates
+            h.set_state(np.ascontiguousarray(np.broadcast_to(self._susceptible, (R,) + self._susceptible.shape)),
+                        np.ascontiguousarray(np.broadcast_to(self._infectious, (R,) + self._infectious.shape)))
+        return h
+
+    def _refresh_host_state(self):
+        Sx, I = self._handle.get_state()
+        self._susceptible[...] = Sx[0]
+        self._infectious[...] = I[0]
+        c = self._handle.get_counters()
+        self._counters = c
+
+    # ------------------------------------------------------------------ hot path entry points
+    def SimulatePopulation(self, iterations, sample_size, time, attempts):
+        """Direct (Gillespie) method, reference src/_BirthDeath.pyx:396-429."""
+        h = self._sync_params()
+        h.simulate_direct(int(iterations), int(sample_size), float(time), int(attempts))
+        self.first_simulation = True
+        self._genealogy_done = False
+        self._refresh_host_state()
+        self._print_stop_reason(sample_size, time)
+
+    def SimulatePopulation_tau(self, iterations, sample_size, time, attempts):
+        """Tau-leaping, reference src/_BirthDeath.pyx:2293-2346."""
+        h = self._sync_params()
+        h.simulate_tau(int(iterations), int(sample_size), float(time), int(attempts))
+        self.first_simulation = True
+        self._genealogy_done = False
+        self._refresh_host_state()
+        self._print_stop_reason(sample_size, time)
+
+    def _print_stop_reason(self, sample_size, time):
+        if self.replicates != 1:
+            return
+        c = self._counters
+        if c['globalInfectious'][0] == 0:
+            print('Simulation finished because no infections individuals remain!')
+        if c['sCounter'][0] > sample_size and sample_size != -1:
+            print("Achieved sample size.")
+        if c['time'][0] > time and time != -1:
+            print("Achieved internal time limit.")
+        if c['sCounter'][0] <= 1:
+            print('\033[41m{}\033[0m'.format('WARNING!'), 'Simulated less 2 samples, so genealogy will not work!')
+
+    def GetGenealogy(self, seed, uniform_stream=None):
+        """Backward coalescent replay, reference src/_BirthDeath.pyx:743-1000.
+
+        ``uniform_stream`` (parity tap): per-replicate list of fp64 uniforms consumed in the
+        reference's order instead of the device Philox stream.
+        """
+        if self._handle is None or not self.first_simulation:
+            raise RuntimeError('Nothing was simulated. Use simulate() before genealogy().')
+        c = self._handle.get_counters()
+        if self.replicates == 1 and c['sCounter'][0] < 2:
+            print("Less than two cases were sampled...")
+            print("_________________________________")
+            raise RuntimeError('Less than two cases were sampled.')
+        self._handle.genealogy(seed, uniform_stream)
+        self._genealogy_done = True
+        # the replay rewinds the device infectious counts to the initial state (reference quirk Q9)
+        self._refresh_host_state()
+
+    def Stats(self, time_simulation):
+        """reference src/_BirthDeath.pyx:2048-2068 (replicate 0; batch runs print aggregate lines)."""
+        self.last_elapsed = time_simulation
+        c = self._counters
+        if self.replicates != 1:
+            ev = (c['bCounter'] + c['dCounter'] + c['sCounter'] + c['mCounter'] + c['iCounter'] + c['migPlus']).sum()
+            print("Replicates:", self.replicates, " total events:", int(ev), " simulation time:", time_simulation)
+            print('----------------------------------')
+            return
+        print("Number of samples:", int(c['sCounter'][0]))
+        print("Total number of iterations:", int(c['events'][0]))
+        print('Success number:', int(c['good_attempt'][0]))
+        print("Epidemic time:", float(c['time'][0]))
+        print('Simulation time:', time_simulation)
+        print('Number of infections:', int(c['bCounter'][0]))
+        print('Number of recoveries:', int(c['dCounter'][0]))
+        if self.sites >= 1:
+            print('Number of mutations:', int(c['mCounter'][0]))
+        if self.popNum >= 2:
+            print('Number of accepted migrations:', int(c['migPlus'][0]))
+            print('Number of rejected migrations:', int(c['migNonPlus'][0]))
+        if np.any(self.suscepTransition.sum(axis=1) != 0.0):
+            print('Number of immunity transitions:', int(c['iCounter'][0]))
+        print('----------------------------------')
+
+    # ------------------------------------------------------------------ outputs (reference :1725-1851, 1948-2045)
+    def counters(self):
+        """Per-replicate counters as a dict of int64 arrays (bCounter ... migNonPlus, events, time)."""
+        return self._handle.get_counters()
+
+    def get_chain_events(self, replicate=0):
+        """6 x N float64 array in the layout of export_chain_events (src/_BirthDeath.pyx:1849-1851)."""
+        return self._handle.get_event_log(replicate)
+
+    def export_chain_events(self, name_file, replicate=0):
+        np.save(name_file, self.get_chain_events(replicate))
+
+    def get_multievents(self, replicate=0):
+        return self._handle.get_multievents(replicate)
+
+    def _require_tree(self):
+        if not self._genealogy_done:
+            print('Genealogy was not simulated. Use VGsim.genealogy() method to simulate it.')
+            raise RuntimeError('Genealogy was not simulated.')
+
+    def get_tree(self, replicate=0):
+        self._require_tree()
+        tree, pop, times = self._handle.get_tree(replicate)
+        return tree, times
+
+    def get_tree_populations(self, replicate=0):
+        self._require_tree()
+        return self._handle.get_tree(replicate)[1]
+
+    def get_mutations(self, replicate=0):
+        """(nodeId, AS, DS, site, time) arrays, src/models.pxi:12-26."""
+        self._require_tree()
+        return self._handle.get_mutations(replicate)
+
+    def get_migrations(self, replicate=0):
+        """(nodeId, time, oldPop, newPop) arrays, src/models.pxi:42-46."""
+        self._require_tree()
+        return self._handle.get_migrations(replicate)
+
+    def output_tree_mutations(self, replicate=0):
+        self._require_tree()
+        tree, pop, times = self._handle.get_tree(replicate)
+        node, AS, DS, site, t = self._handle.get_mutations(replicate)
+        mut = [list(map(int, node)), list(map(int, AS)), list(map(int, site)), list(map(int, DS)), list(map(float, t))]
+        # The reference maps node -> deme through a {time: events.populations} dict, which is garbage
+        # for tau-phase nodes (quirk Q14); the replacement keys the same dict by node time but fills it
+        # from tree_pop, which is what the dict was meant to hold.
+        populations = {float(times[i]): int(pop[i]) for i in range(len(times))}
+        return tree, times, mut, populations
+
+    def export_migrations(self, name_file, file_path, replicate=0):
+        self._require_tree()
+        node, t, oldp, newp = self._handle.get_migrations(replicate)
+        fn = (file_path + '/' if file_path is not None else '') + name_file + '.tsv'
+        with open(fn, 'w') as f:
+            f.write("Node\tTime\tOld_population\tNew_population\n")
+            for i in range(len(node)):
+                f.write(str(int(node[i])) + '\t' + str(float(t[i])) + '\t' + str(int(oldp[i])) + '\t' + str(int(newp[i])) + "\n")
+
+    def output_sample_data(self, replicate=0):
+        ev = self.get_chain_events(replicate)
+        sel = ev[1] == SAMPLING
+        return list(ev[0][sel]), [int(x) for x in ev[3][sel]], [int(x) for x in ev[2][sel]]
+
+    def get_lockdowns(self, replicate=0):
+        return self._handle.get_lockdowns(replicate)
+
+    def PrintCounters(self):
+        c = self._counters
+        print("Birth counter(mutable): ", int(c['bCounter'][0]))
+        print("Death counter(mutable): ", int(c['dCounter'][0]))
+        print("Sampling counter(mutable): ", int(c['sCounter'][0]))
+        print("Mutation counter(mutable): ", int(c['mCounter'][0]))
+        print("Immunity transition counter(mutable):", int(c['iCounter'][0]))
+        print("Migration counter(mutable):", int(c['migPlus'][0]))
+
+    def get_proportion(self):
+        c = self._counters
+        return int(c['migNonPlus'][0]) / (int(c['events'][0]) - 1)
+
+    def propensities(self, replicate=0):
+        """Deterministic parity tap (PrintPropensities, src/_BirthDeath.pyx:2615-2649): the P tau-leap
+        propensities of the current state in positional channel order, plus drifts and tau."""
+        h = self._sync_params()
+        return h.propensities(replicate)
+
+    def PrintPropensities(self):
+        prop, dI, dS, tau = self.propensities()
+        K, H, S, U = self.popNum, self.hapNum, self.susNum, self.sites
+        k = 0
+        print("Migrations")
+        for s in range(K):
+            for r in range(K):
+                if s == r:
+                    continue
+                for i in range(S):
+                    for h in range(H):
+                        print(s, r, i, h, prop[k]); k += 1
+        for s in range(K):
+            print("Susceptibility transition")
+            for i in range(S):
+                for j in range(S):
+                    if i == j:
+                        continue
+                    print(s, i, j, prop[k]); k += 1
+            for h in range(H):
+                print("Recovery ", s, h, self.suscType[h], prop[k]); k += 1
+                print("Sampling ", s, h, self.suscType[h], prop[k]); k += 1
+                for site in range(U):
+                    for i in range(3):
+                        print("Mutation", s, h, site, i, prop[k]); k += 1
+                for i in range(S):
+                    print("Transmission", s, h, i, prop[k]); k += 1
+
+    def rates(self, replicate=0):
+        """Deterministic parity tap for the direct method (UpdateAllRates, src/_BirthDeath.pyx:279-351)."""
+        h = self._sync_params()
+        return h.rates(replicate)

@@ -1,0 +1,632 @@
+// C ABI of libvgsim_b200.so (include/vgsim_b200.h): host-side plumbing around the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/vgsim_b200.h"
+#include "common.cuh"
+#include "handle.h"
+
+using namespace vg;
+
+static thread_local std::string g_err;
+static int fail(const std::string &m) {
+    g_err = m;
+    return 1;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_));                       \
+    } while (0)
+
+struct vgsim_handle_s : public Handle {};
+
+template <class T>
+static int dalloc(Handle *h, T **p, size_t n) {
+    void *q = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+    if (e != cudaSuccess) return fail(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    e = cudaMemsetAsync(q, 0, n * sizeof(T), h->stream);
+    if (e != cudaSuccess) return fail(std::string("cudaMemset: ") + cudaGetErrorString(e));
+    h->allocs.push_back(q);
+    *p = (T *)q;
+    return 0;
+}
+static void dfree(Handle *h, void *p) {
+    if (!p) return;
+    auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+    if (it != h->allocs.end()) h->allocs.erase(it);
+    cudaFree(p);
+}
+
+extern "C" {
+
+const char *vgsim_last_error(void) { return g_err.c_str(); }
+int vgsim_version(void) { return 100; }
+
+int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, int device, vgsim_handle *out) {
+    if (sites < 0 || sites > 9) return fail("number of sites must be in [0, 9] (18-bit haplotype field of the packed event)");
+    if (K < 1 || K > 4096) return fail("populations number must be in [1, 4096]");
+    if (S < 1 || S > 64) return fail("number of susceptible groups must be in [1, 64]");
+    if (n_replicates < 1 || n_param_points < 1) return fail("replicates and parameter points must be >= 1");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("no CUDA device available (the vgsim_b200 hot path has no CPU fallback): ") +
+                    cudaGetErrorString(e));
+    if (device < 0) CK(cudaGetDevice(&device));
+    CK(cudaSetDevice(device));
+    vgsim_handle_s *h = new vgsim_handle_s();
+    h->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->num_sms = prop.multiProcessorCount;
+    h->D = make_dims(sites, K, S);
+    const Dims &D = h->D;
+    if ((long long)K * (K - 1) * S * D.H + (long long)K * D.PD > 2000000000LL) {
+        delete h;
+        return fail("too many reaction channels for 32-bit channel indices");
+    }
+    h->R = n_replicates;
+    h->n_pp = n_param_points;
+    h->hp.resize(n_param_points);
+    DevState &st = h->st;
+    memset(&st, 0, sizeof(st));
+    st.D = D;
+    st.R = n_replicates;
+    st.n_pp = n_param_points;
+    size_t R = n_replicates;
+    double *params;
+    int *rep_pp;
+    uint64_t *seeds;
+    if (dalloc(h, &params, (size_t)n_param_points * D.blob) || dalloc(h, &rep_pp, R) || dalloc(h, &seeds, R) ||
+        dalloc(h, &st.I, R * K * D.H) || dalloc(h, &st.Sx, R * K * S) || dalloc(h, &st.initI, R * K * D.H) ||
+        dalloc(h, &st.initSx, R * K * S) || dalloc(h, &st.cd, R * K) || dalloc(h, &st.lock, R * K) ||
+        dalloc(h, &st.eff, R * K * K) || dalloc(h, &st.ceff, R * K) || dalloc(h, &st.maxEBM, R * K) ||
+        dalloc(h, &st.time, R) || dalloc(h, &st.counters, R * NCOUNT) || dalloc(h, &st.epoch, R) ||
+        dalloc(h, &st.err, R) || dalloc(h, &st.loc_n, R)) {
+        vgsim_destroy(h);
+        return 1;
+    }
+    st.params = params;
+    st.rep_pp = rep_pp;
+    st.seeds = seeds;
+    st.loc_cap = 64;
+    if (dalloc(h, &st.loc_sp, R * st.loc_cap) || dalloc(h, &st.loc_t, R * st.loc_cap) ||
+        dalloc(h, &h->summaries, R * VGSIM_NSUMMARY)) {
+        vgsim_destroy(h);
+        return 1;
+    }
+    // default state: everyone susceptible in group 0, sizes 1e6 (reference :201-204)
+    std::vector<long long> Sx(R * K * S, 0);
+    for (size_t i = 0; i < R * K; i++) Sx[i * S] = 1000000;
+    CK(cudaMemcpyAsync(st.Sx, Sx.data(), Sx.size() * 8, cudaMemcpyHostToDevice, h->stream));
+    std::vector<uint64_t> sd(R);
+    for (size_t i = 0; i < R; i++) sd[i] = i;
+    CK(cudaMemcpyAsync(seeds, sd.data(), R * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return 0;
+}
+
+int vgsim_destroy(vgsim_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (void *p : h->allocs) cudaFree(p);
+    h->allocs.clear();
+    delete h;
+    return 0;
+}
+
+int vgsim_set_stream(vgsim_handle h, void *cuda_stream) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    h->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int vgsim_set_seeds(vgsim_handle h, const uint64_t *seeds) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync((void *)h->st.seeds, seeds, (size_t)h->R * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vgsim_set_replicate_params(vgsim_handle h, const int32_t *map) {
+    for (int r = 0; r < h->R; r++)
+        if (map[r] < 0 || map[r] >= h->n_pp) return fail("replicate_to_param entry out of range");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync((void *)h->st.rep_pp, map, (size_t)h->R * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+__global__ void set_cd_kernel(DevState st, int pp, const int *mask, const double *cdv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.R * st.D.K) return;
+    int r = i / st.D.K, p = i - r * st.D.K;
+    if (st.rep_pp[r] == pp && mask[p]) st.cd[i] = cdv[p];
+}
+
+int vgsim_upload_params(vgsim_handle h, int pp, const double *b, const double *d, const double *s,
+                        const double *mRate, const double *hapMutType, const double *sigma, const int64_t *suscType,
+                        const double *T, const double *m, const double *contact_density, const double *cd_before,
+                        const double *cd_after, const double *startLD, const double *endLD,
+                        const double *sampling_multiplier, const int64_t *sizes, const int32_t *cd_reset_mask) {
+    if (pp < 0 || pp >= h->n_pp) return fail("parameter point out of range");
+    CK(cudaSetDevice(h->device));
+    const Dims &D = h->D;
+    const int K = D.K, H = D.H, S = D.S, U = D.U;
+    HostParams &P = h->hp[pp];
+    auto cp = [](std::vector<double> &v, const double *src, size_t n, double dflt) {
+        if (src)
+            v.assign(src, src + n);
+        else if (v.size() != n)
+            v.assign(n, dflt);
+    };
+    cp(P.b, b, H, 2.0);
+    cp(P.d, d, H, 1.0);
+    cp(P.s, s, H, 0.01);
+    cp(P.mRate, mRate, (size_t)H * U, 0.01);
+    cp(P.hapMutType, hapMutType, (size_t)H * U * 3, 1.0);
+    if (sigma)
+        P.sigma.assign(sigma, sigma + (size_t)H * S);
+    else if (P.sigma.size() != (size_t)H * S) {
+        P.sigma.assign((size_t)H * S, 0.0);
+        for (int i = 0; i < H; i++) P.sigma[(size_t)i * S] = 1.0;
+    }
+    if (suscType)
+        P.suscType.assign(suscType, suscType + H);
+    else if (P.suscType.size() != (size_t)H)
+        P.suscType.assign(H, 0);
+    cp(P.T, T, (size_t)S * S, 0.0);
+    cp(P.m, m, (size_t)K * K, 0.0);
+    cp(P.cd, contact_density, K, 1.0);
+    cp(P.cdBefore, cd_before, K, 1.0);
+    cp(P.cdAfter, cd_after, K, 0.0);
+    cp(P.startLD, startLD, K, 1.0);
+    cp(P.endLD, endLD, K, 1.0);
+    cp(P.sm, sampling_multiplier, K, 1.0);
+    if (sizes)
+        P.sizes.assign(sizes, sizes + K);
+    else if (P.sizes.size() != (size_t)K)
+        P.sizes.assign(K, 1000000);
+    for (int i = 0; i < H; i++)
+        if (P.suscType[i] < 0 || P.suscType[i] >= S) return fail("susceptibility type out of range");
+    for (int p = 0; p < K; p++)
+        if (P.sizes[p] <= 0 || P.sizes[p] > 2147483647LL)
+            return fail("population sizes must be in [1, 2^31-1] (compartment counts are int32 on the device)");
+
+    // ---- derived constants of UpdateAllRates (reference :279-351), fp64, reference summation order
+    std::vector<double> blob(D.blob, 0.0);
+    for (int i = 0; i < H; i++) {
+        blob[D.o_b + i] = P.b[i];
+        blob[D.o_d + i] = P.d[i];
+        blob[D.o_sr + i] = P.s[i];
+        blob[D.o_g + i] = (double)P.suscType[i];
+        double tq = 0.0;
+        for (int u = 0; u < U; u++) {
+            const double *w = &P.hapMutType[((size_t)i * U + u) * 3];
+            blob[D.o_mu + i * U + u] = P.mRate[(size_t)i * U + u];
+            for (int k = 0; k < 3; k++) {
+                double q = P.mRate[(size_t)i * U + u] * w[k] / (w[0] + w[1] + w[2]);  // (:2400-2401)
+                blob[D.o_q + (i * U + u) * 3 + k] = q;
+                blob[D.o_w + (i * U + u) * 3 + k] = w[k];
+                tq += q;
+            }
+        }
+        blob[D.o_tmq + i] = tq;
+        for (int sn = 0; sn < S; sn++) blob[D.o_sigT + sn * H + i] = P.sigma[(size_t)i * S + sn];
+    }
+    for (int s1 = 0; s1 < S; s1++) {
+        double tc = 0;
+        for (int s2 = 0; s2 < S; s2++) {
+            blob[D.o_T + s1 * S + s2] = P.T[(size_t)s1 * S + s2];
+            tc += P.T[(size_t)s1 * S + s2];
+        }
+        blob[D.o_Tc + s1] = tc;
+    }
+    std::vector<double> mm(P.m);
+    std::vector<double> A(K, 0.0);
+    for (int p1 = 0; p1 < K; p1++) {
+        mm[(size_t)p1 * K + p1] = 1.0;
+        A[p1] = 0.0;
+        for (int p2 = 0; p2 < K; p2++) {
+            if (p1 == p2) continue;
+            mm[(size_t)p1 * K + p1] -= mm[(size_t)p1 * K + p2];
+            A[p1] += mm[(size_t)p2 * K + p1] * (double)P.sizes[p2];
+        }
+        A[p1] += mm[(size_t)p1 * K + p1] * (double)P.sizes[p1];
+    }
+    double maxB = 0.0;
+    for (int i = 0; i < H; i++)
+        for (int sn = 0; sn < S; sn++)
+            if (P.b[i] * P.sigma[(size_t)i * S + sn] > maxB) maxB = P.b[i] * P.sigma[(size_t)i * S + sn];
+    blob[D.o_maxB] = maxB;
+    for (int p = 0; p < K; p++) {
+        for (int q = 0; q < K; q++) blob[D.o_m + p * K + q] = mm[(size_t)p * K + q];
+        blob[D.o_A + p] = A[p];
+        blob[D.o_sm + p] = P.sm[p];
+        blob[D.o_cdB + p] = P.cdBefore[p];
+        blob[D.o_cdA + p] = P.cdAfter[p];
+        blob[D.o_startN + p] = P.startLD[p] * (double)P.sizes[p];
+        blob[D.o_endN + p] = P.endLD[p] * (double)P.sizes[p];
+        blob[D.o_size + p] = (double)P.sizes[p];
+    }
+    CK(cudaMemcpyAsync((void *)(h->st.params + (size_t)pp * D.blob), blob.data(), (size_t)D.blob * 8,
+                       cudaMemcpyHostToDevice, h->stream));
+    // live contact density: first upload sets every deme, later uploads only the masked ones
+    std::vector<int> mask(K, 1);
+    if (P.uploaded && cd_reset_mask)
+        for (int p = 0; p < K; p++) mask[p] = cd_reset_mask[p] != 0;
+    else if (P.uploaded && !contact_density)
+        std::fill(mask.begin(), mask.end(), 0);
+    int *dmask;
+    double *dcd;
+    CK(cudaMalloc(&dmask, K * 4));
+    CK(cudaMalloc(&dcd, K * 8));
+    CK(cudaMemcpyAsync(dmask, mask.data(), K * 4, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(dcd, P.cd.data(), K * 8, cudaMemcpyHostToDevice, h->stream));
+    int n = h->R * K;
+    set_cd_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->st, pp, dmask, dcd);
+    h->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(dmask);
+    cudaFree(dcd);
+    P.uploaded = true;
+    return 0;
+}
+
+int vgsim_set_state(vgsim_handle h, const int64_t *Sx, const int64_t *I) {
+    CK(cudaSetDevice(h->device));
+    const Dims &D = h->D;
+    if (Sx) CK(cudaMemcpyAsync(h->st.Sx, Sx, (size_t)h->R * D.K * D.S * 8, cudaMemcpyHostToDevice, h->stream));
+    if (I) CK(cudaMemcpyAsync(h->st.I, I, (size_t)h->R * D.K * D.H * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vgsim_get_state(vgsim_handle h, int64_t *Sx, int64_t *I, double *cd, int64_t *lock) {
+    CK(cudaSetDevice(h->device));
+    const Dims &D = h->D;
+    if (Sx) CK(cudaMemcpyAsync(Sx, h->st.Sx, (size_t)h->R * D.K * D.S * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (I) CK(cudaMemcpyAsync(I, h->st.I, (size_t)h->R * D.K * D.H * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (cd) CK(cudaMemcpyAsync(cd, h->st.cd, (size_t)h->R * D.K * 8, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<int> lk;
+    if (lock) {
+        lk.resize((size_t)h->R * D.K);
+        CK(cudaMemcpyAsync(lk.data(), h->st.lock, lk.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    if (lock)
+        for (size_t i = 0; i < lk.size(); i++) lock[i] = lk[i];
+    return 0;
+}
+
+}  // extern "C"
+
+// grow a per-replicate 2-D device buffer [R][old_cap*w] -> [R][new_cap*w], keeping the first `keep` rows
+template <class T>
+static int grow2d(Handle *h, T **buf, long long old_cap, long long new_cap, long long keep, size_t w) {
+    T *nb;
+    if (dalloc(h, &nb, (size_t)h->R * new_cap * w)) return 1;
+    if (*buf && keep > 0) {
+        cudaError_t e = cudaMemcpy2DAsync(nb, new_cap * w * sizeof(T), *buf, old_cap * w * sizeof(T),
+                                          keep * w * sizeof(T), h->R, cudaMemcpyDeviceToDevice, h->stream);
+        if (e != cudaSuccess) return fail(std::string("cudaMemcpy2D: ") + cudaGetErrorString(e));
+    }
+    if (*buf) {
+        cudaStreamSynchronize(h->stream);
+        dfree(h, *buf);
+    }
+    *buf = nb;
+    return 0;
+}
+
+static int ensure_ev_cap(Handle *h, long long need) {
+    DevState &st = h->st;
+    if (need <= st.ev_cap) return 0;
+    long long nc = need;
+    if (grow2d(h, &st.ev_time, st.ev_cap, nc, h->ev_bound, 1)) return 1;
+    if (grow2d(h, &st.ev_desc, st.ev_cap, nc, h->ev_bound, 1)) return 1;
+    st.ev_cap = nc;
+    return 0;
+}
+static int ensure_leap_cap(Handle *h, long long need) {
+    DevState &st = h->st;
+    if (need <= st.leap_cap) return 0;
+    long long nc = need;
+    if (grow2d(h, &st.tau_counts, st.leap_cap, nc, h->leap_bound, (size_t)st.D.Pp)) return 1;
+    if (grow2d(h, &st.tau_tt, st.leap_cap, nc, h->leap_bound, 2)) return 1;
+    st.leap_cap = nc;
+    return 0;
+}
+
+static int prepare(Handle *h, int tau_mode) {
+    if (!h->hp[0].uploaded) return fail("parameters were not uploaded (vgsim_upload_params)");
+    int first = h->st.first_simulation == 0;
+    cudaError_t e = launch_prepare(h->st, first, tau_mode, h->stream);
+    if (e != cudaSuccess) return fail(std::string("prepare kernel: ") + cudaGetErrorString(e));
+    e = launch_refresh(h->st, h->stream);
+    if (e != cudaSuccess) return fail(std::string("refresh kernel: ") + cudaGetErrorString(e));
+    h->launches += 2;
+    h->st.first_simulation = 1;
+    h->gen.valid = false;
+    return 0;
+}
+
+static SimArgs make_args(int64_t iterations, int64_t sample_size, float t, int64_t attempts) {
+    SimArgs a;
+    a.iterations = iterations;
+    a.sample_size = sample_size;
+    a.time = t;
+    a.has_time = !(t == -1.0f);
+    a.attempts = attempts < 1 ? 1 : attempts;
+    return a;
+}
+
+extern "C" {
+
+int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
+                       int64_t attempts) {
+    CK(cudaSetDevice(h->device));
+    if (iterations < 0) return fail("iterations must be >= 0");
+    if (ensure_ev_cap(h, h->ev_bound + iterations) || ensure_leap_cap(h, h->leap_bound + iterations)) return 1;
+    if (prepare(h, 1)) return 1;
+    SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
+    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms);
+    if (e != cudaSuccess) return fail(std::string("tau kernel: ") + cudaGetErrorString(e));
+    h->launches++;
+    h->ev_bound += iterations;
+    h->leap_bound += iterations;
+    return 0;
+}
+
+int vgsim_simulate_direct(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
+                          int64_t attempts) {
+    CK(cudaSetDevice(h->device));
+    if (iterations < 0) return fail("iterations must be >= 0");
+    if (ensure_ev_cap(h, h->ev_bound + iterations)) return 1;
+    if (prepare(h, 0)) return 1;
+    SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
+    cudaError_t e = launch_direct(h->st, a, h->stream, h->num_sms);
+    if (e != cudaSuccess) return fail(std::string("direct kernel: ") + cudaGetErrorString(e));
+    h->launches++;
+    h->ev_bound += iterations;
+    return 0;
+}
+
+int vgsim_synchronize(vgsim_handle h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<int> err(h->R);
+    CK(cudaMemcpy(err.data(), h->st.err, (size_t)h->R * 4, cudaMemcpyDeviceToHost));
+    int all = 0;
+    for (int v : err) all |= v;
+    if (all) {
+        g_err = "device error flags: " + std::to_string(all);
+        if (all & ERR_ZERO_WEIGHT) g_err += " [zero weight sampled]";
+        if (all & ERR_LOCKDOWN_OVERFLOW) g_err += " [lockdown record overflow]";
+        if (all & ERR_ARENA) g_err += " [lineage arena exhausted]";
+        if (all & ERR_STREAM) g_err += " [injected uniform stream exhausted]";
+        if (all & ERR_CLAMPED) g_err += " [tau-log coalescences clamped]";
+        if (all & ERR_COUNT_OVERFLOW) g_err += " [compartment count overflow]";
+        if (all & ERR_BADLOG) g_err += " [bad event log]";
+    }
+    return all;
+}
+
+int64_t vgsim_prop_num(vgsim_handle h) { return h->D.P; }
+
+int vgsim_propensities(vgsim_handle h, int replicate, double *out, double *dI, double *dS, double *tau) {
+    CK(cudaSetDevice(h->device));
+    if (replicate < 0 || replicate >= h->R) return fail("replicate out of range");
+    if (!h->hp[0].uploaded) return fail("parameters were not uploaded");
+    const Dims &D = h->D;
+    // like PrintPropensities: UpdateAllRates on the CURRENT state (no FirstInfection, no lockdown check)
+    cudaError_t e = launch_refresh(h->st, h->stream);
+    if (e != cudaSuccess) return fail(std::string("refresh kernel: ") + cudaGetErrorString(e));
+    double *buf;
+    size_t n = (size_t)D.P + (size_t)D.K * D.H + (size_t)D.K * D.S + 1;
+    CK(cudaMalloc(&buf, n * 8));
+    e = launch_propensities(h->st, replicate, buf, buf + D.P, buf + D.P + D.K * D.H, buf + n - 1, h->stream);
+    h->launches += 2;
+    if (e != cudaSuccess) {
+        cudaFree(buf);
+        return fail(std::string("propensity kernel: ") + cudaGetErrorString(e));
+    }
+    std::vector<double> hb(n);
+    CK(cudaMemcpyAsync(hb.data(), buf, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(buf);
+    if (out) memcpy(out, hb.data(), (size_t)D.P * 8);
+    if (dI) memcpy(dI, hb.data() + D.P, (size_t)D.K * D.H * 8);
+    if (dS) memcpy(dS, hb.data() + D.P + D.K * D.H, (size_t)D.K * D.S * 8);
+    if (tau) *tau = hb[n - 1];
+    return 0;
+}
+
+int vgsim_rates(vgsim_handle h, int replicate, double *A, double *eff, double *maxEBM, double *ev, double *hapPopRate,
+                double *popRate, double *migPopRate, double *totals) {
+    CK(cudaSetDevice(h->device));
+    if (replicate < 0 || replicate >= h->R) return fail("replicate out of range");
+    if (!h->hp[0].uploaded) return fail("parameters were not uploaded");
+    const Dims &D = h->D;
+    const int K = D.K, H = D.H;
+    cudaError_t e = launch_refresh(h->st, h->stream);
+    if (e != cudaSuccess) return fail(std::string("refresh kernel: ") + cudaGetErrorString(e));
+    size_t n = (size_t)K * H * 4 + (size_t)K * H + K + K + 2;
+    double *buf;
+    CK(cudaMalloc(&buf, n * 8));
+    e = launch_rates_tap(h->st, replicate, buf, buf + K * H * 4, buf + K * H * 5, buf + K * H * 5 + K,
+                         buf + K * H * 5 + 2 * K, h->stream);
+    h->launches += 2;
+    if (e != cudaSuccess) {
+        cudaFree(buf);
+        return fail(std::string("rates kernel: ") + cudaGetErrorString(e));
+    }
+    std::vector<double> hb(n);
+    CK(cudaMemcpyAsync(hb.data(), buf, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    int pp;
+    CK(cudaMemcpyAsync(&pp, h->st.rep_pp + replicate, 4, cudaMemcpyDeviceToHost, h->stream));
+    if (eff) CK(cudaMemcpyAsync(eff, h->st.eff + (size_t)replicate * K * K, (size_t)K * K * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (maxEBM) CK(cudaMemcpyAsync(maxEBM, h->st.maxEBM + (size_t)replicate * K, (size_t)K * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (A) CK(cudaMemcpy(A, h->st.params + (size_t)pp * D.blob + D.o_A, (size_t)K * 8, cudaMemcpyDeviceToHost));
+    cudaFree(buf);
+    if (ev) memcpy(ev, hb.data(), (size_t)K * H * 4 * 8);
+    if (hapPopRate) memcpy(hapPopRate, hb.data() + K * H * 4, (size_t)K * H * 8);
+    if (popRate) memcpy(popRate, hb.data() + K * H * 5, (size_t)K * 8);
+    if (migPopRate) memcpy(migPopRate, hb.data() + K * H * 5 + K, (size_t)K * 8);
+    if (totals) memcpy(totals, hb.data() + K * H * 5 + 2 * K, 16);
+    return 0;
+}
+
+int vgsim_get_counters(vgsim_handle h, int64_t *counters, double *current_time) {
+    CK(cudaSetDevice(h->device));
+    if (counters)
+        CK(cudaMemcpyAsync(counters, h->st.counters, (size_t)h->R * NCOUNT * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (current_time) CK(cudaMemcpyAsync(current_time, h->st.time, (size_t)h->R * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int fetch_counters(Handle *h, int r, long long *c) {
+    CK(cudaMemcpyAsync(c, h->st.counters + (size_t)r * NCOUNT, NCOUNT * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vgsim_get_event_log(vgsim_handle h, int r, double *out, int64_t n) {
+    CK(cudaSetDevice(h->device));
+    if (r < 0 || r >= h->R) return fail("replicate out of range");
+    long long c[NCOUNT];
+    if (fetch_counters(h, r, c)) return 1;
+    if (n != c[C_EVPTR]) return fail("event count mismatch (expected counters[9])");
+    if (n == 0) return 0;
+    std::vector<double> t(n);
+    std::vector<unsigned long long> d(n);
+    CK(cudaMemcpyAsync(t.data(), h->st.ev_time + (size_t)r * h->st.ev_cap, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(d.data(), h->st.ev_desc + (size_t)r * h->st.ev_cap, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const long long P = h->D.P;
+    for (int64_t i = 0; i < n; i++) {
+        int type, hap, pop, nhap, npop;
+        unpack_event(d[i], type, hap, pop, nhap, npop);
+        out[i] = t[i];
+        out[n + i] = type;
+        if (type == EV_MULTITYPE) {
+            long long leap = unpack_multi(d[i]);
+            out[2 * n + i] = (double)(leap * P);
+            out[3 * n + i] = (double)((leap + 1) * P);
+            out[4 * n + i] = 0;
+            out[5 * n + i] = 0;
+        } else {
+            out[2 * n + i] = hap;
+            out[3 * n + i] = pop;
+            out[4 * n + i] = nhap;
+            out[5 * n + i] = (type == EV_BIRTH) ? h->D.H : npop;  // BIRTH rows carry the hapNum sentinel (:600)
+        }
+    }
+    return 0;
+}
+
+int vgsim_get_tau_log(vgsim_handle h, int r, int64_t leaps, int32_t *counts, double *time_tau) {
+    CK(cudaSetDevice(h->device));
+    if (r < 0 || r >= h->R) return fail("replicate out of range");
+    long long c[NCOUNT];
+    if (fetch_counters(h, r, c)) return 1;
+    if (leaps != c[C_LEAPS]) return fail("leap count mismatch (expected counters[10])");
+    if (leaps == 0) return 0;
+    const Dims &D = h->D;
+    if (counts)
+        CK(cudaMemcpy2DAsync(counts, (size_t)D.P * 4, h->st.tau_counts + (size_t)r * h->st.leap_cap * D.Pp,
+                             (size_t)D.Pp * 4, (size_t)D.P * 4, leaps, cudaMemcpyDeviceToHost, h->stream));
+    if (time_tau)
+        CK(cudaMemcpyAsync(time_tau, h->st.tau_tt + (size_t)r * h->st.leap_cap * 2, leaps * 16, cudaMemcpyDeviceToHost,
+                           h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vgsim_get_multievents(vgsim_handle h, int r, int64_t n, int64_t *num, double *time, int64_t *type, int64_t *hap,
+                          int64_t *pop, int64_t *nhap, int64_t *npop) {
+    const Dims &D = h->D;
+    if (n % D.P != 0) return fail("n must be leaps * P");
+    int64_t L = n / D.P;
+    std::vector<int32_t> cnt((size_t)n);
+    std::vector<double> tt((size_t)L * 2);
+    if (vgsim_get_tau_log(h, r, L, cnt.data(), tt.data())) return 1;
+    const HostParams &P = h->hp[0];
+    const int K = D.K, H = D.H, S = D.S, U = D.U;
+    int64_t k = 0;
+    auto put = [&](int64_t nn, double t, int ty, int a, int b, int c, int d2) {
+        if (num) num[k] = nn;
+        if (time) time[k] = t;
+        if (type) type[k] = ty;
+        if (hap) hap[k] = a;
+        if (pop) pop[k] = b;
+        if (nhap) nhap[k] = c;
+        if (npop) npop[k] = d2;
+        k++;
+    };
+    for (int64_t l = 0; l < L; l++) {
+        double t = tt[l * 2];
+        const int32_t *c = cnt.data() + l * D.P;
+        int64_t j = 0;
+        for (int sp = 0; sp < K; sp++)
+            for (int tp = 0; tp < K; tp++) {
+                if (sp == tp) continue;
+                for (int sn = 0; sn < S; sn++)
+                    for (int hh = 0; hh < H; hh++) put(c[j++], t, EV_MIGRATION, hh, sp, sn, tp);
+            }
+        for (int p = 0; p < K; p++) {
+            for (int ss = 0; ss < S; ss++)
+                for (int ts = 0; ts < S; ts++)
+                    if (ss != ts) put(c[j++], t, EV_SUSCCHANGE, ss, p, ts, 0);
+            for (int hh = 0; hh < H; hh++) {
+                int g = (int)P.suscType[hh];
+                put(c[j++], t, EV_DEATH, hh, p, g, 0);
+                put(c[j++], t, EV_SAMPLING, hh, p, g, 0);
+                for (int u = 0; u < U; u++)
+                    for (int i = 0; i < 3; i++) put(c[j++], t, EV_MUTATION, hh, p, mutate_hap(hh, u, i, U), 0);
+                for (int sn = 0; sn < S; sn++) put(c[j++], t, EV_BIRTH, hh, p, sn, 0);
+            }
+        }
+    }
+    return 0;
+}
+
+int64_t vgsim_num_lockdowns(vgsim_handle h, int r) {
+    cudaSetDevice(h->device);
+    int n = 0;
+    cudaMemcpyAsync(&n, h->st.loc_n + r, 4, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    return n;
+}
+int vgsim_get_lockdowns(vgsim_handle h, int r, int64_t *state, int64_t *pop, double *time) {
+    CK(cudaSetDevice(h->device));
+    int n = (int)vgsim_num_lockdowns(h, r);
+    if (n == 0) return 0;
+    std::vector<int> sp(n);
+    CK(cudaMemcpyAsync(sp.data(), h->st.loc_sp + (size_t)r * h->st.loc_cap, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(time, h->st.loc_t + (size_t)r * h->st.loc_cap, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; i++) {
+        state[i] = sp[i] & 1;
+        pop[i] = sp[i] >> 1;
+    }
+    return 0;
+}
+
+int64_t vgsim_launch_count(vgsim_handle h) { return h->launches; }
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Host-side handle behind the C ABI (include/vgsim_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+#include "common.cuh"
+
+namespace vg {
+
+struct HostParams {  // host copy of one parameter point in the reference's layouts
+    std::vector<double> b, d, s, mRate, hapMutType, sigma, T, m, cd, cdBefore, cdAfter, startLD, endLD, sm;
+    std::vector<long long> suscType, sizes;
+    bool uploaded = false;
+};
+
+struct GenealogyBuffers {
+    // per replicate outputs; node capacity = 2*sC-1
+    long long *node_off = nullptr;     // [R+1] prefix offsets into the node arrays
+    int *parent = nullptr, *pop = nullptr;
+    double *time = nullptr;
+    long long total_nodes = 0;
+    // side tables
+    long long *mut_off = nullptr, *mig_off = nullptr;  // [R+1] capacity offsets
+    int *mut_n = nullptr, *mig_n = nullptr;            // [R] used
+    int *mut_node = nullptr, *mut_hap = nullptr;       // hap | nhap packed separately
+    int *mut_nhap = nullptr;
+    double *mut_time = nullptr;
+    int *mig_node = nullptr, *mig_old = nullptr, *mig_new = nullptr;
+    double *mig_time = nullptr;
+    // lineage arena
+    long long *arena_off = nullptr;  // [R+1]
+    int *arena = nullptr;
+    int *cell_hdr = nullptr;         // [R][K*H][3] (offset, size, cap)
+    int *n_nodes = nullptr;          // [R] nodes actually created
+    bool valid = false;
+    std::vector<long long> h_node_off, h_mut_off, h_mig_off;
+};
+
+struct Handle {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = 0;
+    Dims D;
+    int R = 0, n_pp = 0;
+    DevState st;
+    std::vector<HostParams> hp;
+    long long ev_bound = 0, leap_bound = 0;  // host upper bounds of log rows / leaps per replicate
+    long long launches = 0;
+    bool state_set = false;
+    GenealogyBuffers gen;
+    double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
+    std::vector<void *> allocs;
+};
+
+// kernels' host launchers (defined in the .cu files)
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms);
+cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
+                                cudaStream_t stream);
+cudaError_t launch_prepare(const DevState &st, int first, int tau_mode, cudaStream_t stream);
+cudaError_t launch_refresh(const DevState &st, cudaStream_t stream);
+cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms);
+cudaError_t launch_rates_tap(const DevState &st, int r, double *ev, double *hp, double *popRate, double *migPop,
+                             double *totals, cudaStream_t stream);
+
+}  // namespace vg

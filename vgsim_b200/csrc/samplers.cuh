@@ -1,0 +1,74 @@
+// Device samplers driven by counter-based Philox words.
+//
+// Poisson replaces numpy's random_poisson (reference src/_BirthDeath.pyx:2531-2532).  The reference
+// draws from a sequential PCG64 stream (multiplication method for lam < 10, Hoermann PTRS above);
+// here every draw is a pure function of (key, counter):
+//   * lam == 0            -> 0, no random words consumed (same as numpy)
+//   * 0 < lam < 10        -> exact inversion of one 53-bit uniform U (sequential search from 0).
+//                            Fast path: if the top 32 bits of U already prove U < 1-lam <= exp(-lam)
+//                            the draw is 0 without touching exp() or the low word.
+//   * lam >= 10           -> PTRS transformed rejection (Hoermann 1993), 2 uniforms per trial,
+//                            trial t uses Philox domain 2+t of the same channel counter.
+#pragma once
+#include "common.cuh"
+
+namespace vg {
+
+struct PhiloxCtx {
+    uint2 key;
+    uint32_t c0, c1, c2;  // counter words x,y,z ; w = domain
+    __device__ __forceinline__ uint4 draw(uint32_t domain) const {
+        return philox4x32_10(make_uint4(c0, c1, c2, domain), key);
+    }
+};
+
+// lane = which of the 4 words of a Philox block belongs to this draw
+__device__ __forceinline__ uint32_t pick_word(const uint4 &w, int lane) {
+    return lane == 0 ? w.x : lane == 1 ? w.y : lane == 2 ? w.z : w.w;
+}
+
+static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCtx &ctx, int lane) {
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    for (uint32_t t = 0; t < 64; t++) {
+        // trial t: domain 2 + 4*t + lane gives 4 words = two 53-bit uniforms private to this channel
+        uint4 w = ctx.draw(2u + 4u * t + (uint32_t)lane);
+        double U = u53(w.x, w.y) - 0.5;
+        double V = u53(w.z, w.w);
+        double us = 0.5 - fabs(U);
+        long long k = (long long)floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (k < 0 || (us < 0.013 && V > us)) continue;
+        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + (double)k * loglam - lgamma((double)k + 1.0)))
+            return k;
+    }
+    return (long long)floor(lam + 0.5);  // unreachable in practice (acceptance ~0.9 per trial)
+}
+
+static __device__ __noinline__ long long poisson_inversion(double lam, uint32_t hi, const PhiloxCtx &ctx, int lane) {
+    uint4 w = ctx.draw(1u);
+    double U = u53(hi, pick_word(w, lane));
+    double p = exp(-lam), cdf = p;
+    long long n = 0;
+    while (U >= cdf && n < 256) {
+        n++;
+        p *= lam / (double)n;
+        cdf += p;
+    }
+    return n;
+}
+
+// `hi`: this channel's word of the chunk's domain-0 Philox block.
+__device__ __forceinline__ long long poisson_draw(double lam, uint32_t hi, const PhiloxCtx &ctx, int lane) {
+    if (lam < 10.0) {
+        // U = (hi + f)/2^32 with f in [0,1).  (hi+1)/2^32 <= 1 - lam  =>  U < 1-lam <= exp(-lam)  =>  0
+        if ((double)hi + 1.0 <= (1.0 - lam) * 4294967296.0) return 0;
+        return poisson_inversion(lam, hi, ctx, lane);
+    }
+    return poisson_ptrs(lam, ctx, lane);
+}
+
+}  // namespace vg
