@@ -1084,15 +1084,15 @@ void vgo_set_state(void *h, const i64 *Sx, const i64 *I) {
     Model &M = *(Model *)h;
     CP(M.Sx, Sx, (size_t)M.K * M.S);
     CP(M.I, I, (size_t)M.K * M.H);
-    if (M.first_simulation) {
-        M.globalInf = 0;
-        for (int p = 0; p < M.K; p++) {
-            M.totSus[p] = 0;
-            M.totInf[p] = 0;
-            for (int sn = 0; sn < M.S; sn++) M.totSus[p] += M.Sx[p * M.S + sn];
-            for (int hh = 0; hh < M.H; hh++) M.totInf[p] += M.I[p * M.H + hh];
-            M.globalInf += M.totInf[p];
-        }
+    // totals always follow the arrays, so FirstInfection (:234-242) only fires when nobody is infected
+    // (the reference cannot reach this path: its set_infectious always raises)
+    M.globalInf = 0;
+    for (int p = 0; p < M.K; p++) {
+        M.totSus[p] = 0;
+        M.totInf[p] = 0;
+        for (int sn = 0; sn < M.S; sn++) M.totSus[p] += M.Sx[p * M.S + sn];
+        for (int hh = 0; hh < M.H; hh++) M.totInf[p] += M.I[p * M.H + hh];
+        M.globalInf += M.totInf[p];
     }
 }
 void vgo_get_state(void *h, i64 *Sx, i64 *I) {

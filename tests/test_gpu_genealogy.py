@@ -1,0 +1,121 @@
+"""GPU parity tests of the genealogy kernel: given an event log and a random stream, parent arrays,
+node demes/times, mutation and migration tables must be bit-identical to the oracle's (north_star)."""
+import numpy as np
+import pytest
+from numpy.random import PCG64, Generator, SeedSequence
+
+from oracle import oracle as O
+from scenarios import SCENARIOS, example_phase2
+from vgsim_b200 import _capi
+from test_gpu_tau import make_engine, warm_state
+
+pytestmark = pytest.mark.gpu
+
+
+def pcg(seed, num=0):
+    return Generator(PCG64(SeedSequence(seed, spawn_key=(num,))))
+
+
+def assert_same_genealogy(h, r, om):
+    tree, pop, times = h.get_tree(r)
+    t2, p2, tm2 = om.tree()
+    assert np.array_equal(tree, t2)
+    assert np.array_equal(pop, p2)
+    assert np.array_equal(times, tm2)
+    for a, b in zip(h.get_mutations(r), om.mutations()):
+        assert np.array_equal(a, b)
+    for a, b in zip(h.get_migrations(r), om.migrations()):
+        assert np.array_equal(a, b)
+
+
+def test_device_hypergeometric_matches_numpy():
+    rs = np.random.RandomState(3)
+    n = 4000
+    good = rs.randint(1, 3000, n)
+    bad = rs.randint(1, 3000, n)
+    sample = np.array([rs.randint(1, g + b + 1) for g, b in zip(good, bad)])
+    small = rs.rand(n) < 0.3
+    sample[small] = np.minimum(sample[small], rs.randint(1, 12, small.sum()))
+    g = pcg(11, 0)
+    state = g.bit_generator.state
+    want = np.array([g.hypergeometric(a, b, c) for a, b, c in zip(good, bad, sample)])
+    g2 = Generator(PCG64())
+    g2.bit_generator.state = state
+    words = g2.bit_generator.random_raw(200000)
+    got, used = _capi.test_hypergeometric(good, bad, sample, words)
+    assert used > 0
+    assert np.array_equal(want, got)
+
+
+@pytest.mark.parametrize("name,iters,gseed", [("s1", 20000, 7), ("s4", 100000, 3), ("s7", 30000, 5), ("s8", 20000, 9),
+                                              ("s9", 40000, 2020), ("example", 60000, 1)])
+def test_direct_log_genealogy_bit_exact(name, iters, gseed):
+    """Oracle forward run -> its event chain is loaded into the device (set_event_log) -> both replay it
+    with the SAME uniform stream (the reference's genealogy(seed) stream, PCG64(SeedSequence(seed,(0,))))."""
+    om = O.OracleModel.from_engine(make_engine(name, 2020))
+    om.simulate(iters)
+    chain = om.events()
+    Sx_end, I_end = om.get_state()
+    assert om.counters()["sCounter"] >= 2
+    e = make_engine(name, 2020, replicates=2)
+    h = e._sync_params()
+    for r in range(2):
+        h.set_event_log(r, chain, I_end)
+    u = pcg(gseed).random(chain.shape[1] * 4 + 16)
+    h.genealogy(uniform_stream=[u, u])
+    om.genealogy(gseed)
+    for r in range(2):
+        assert_same_genealogy(h, r, om)
+    # the replay rewinds the infectious counts to the initial state (reference quirk Q9)
+    _, I_dev = h.get_state()
+    assert np.array_equal(I_dev[0], om.get_state()[1])
+
+
+@pytest.mark.parametrize("name,seed,t0,leaps", [("t3small", 5, 60.0, 80), ("s9", 2020, 4.0, 90), ("example", 1234, 60.0, 60)])
+def test_tau_log_genealogy_bit_exact(name, seed, t0, leaps):
+    """Device direct + tau run -> the same log is handed to the oracle -> both replay it with the same raw
+    PCG64 word stream (uniforms and numpy-compatible hypergeometric draws)."""
+    e = make_engine(name, seed, replicates=3)
+    e.SimulatePopulation(10**6, 10**9, t0, 200)
+    e.SimulatePopulation_tau(leaps, 10**9, -1, 1)
+    h = e._handle
+    c = h.get_counters()
+    Sx_f, I_f = h.get_state()
+    words = [pcg(100 + r).bit_generator.random_raw(400000) for r in range(3)]
+    chains = [h.get_event_log(r) for r in range(3)]
+    logs = [h.get_tau_log(r) for r in range(3)]
+    h.genealogy(uniform_stream=words, raw_words=True)
+    for r in range(3):
+        if c["sCounter"][r] < 2:
+            continue
+        e1 = make_engine(name, seed)
+        om = O.OracleModel.from_engine(e1)
+        direct_rows = chains[r][:, chains[r][1] < 6]
+        om.set_events(direct_rows)
+        om.set_state(Sx_f[r], I_f[r])
+        counts, tt = logs[r]
+        om.append_tau_log(counts, tt[:, 0])
+        assert om.counters()["sCounter"] == c["sCounter"][r]
+        # oracle consumes the same PCG64 stream natively
+        om.genealogy(100 + r)
+        assert_same_genealogy(h, r, om)
+
+
+def test_philox_genealogy_is_a_valid_tree():
+    e = make_engine("s9", 42, replicates=64)
+    e.SimulatePopulation(20000, 20000, -1, 200)
+    e.GetGenealogy(None)
+    h = e._handle
+    c = h.get_counters()
+    for r in range(0, 64, 7):
+        tree, pop, times = h.get_tree(r)
+        n = int(c["sCounter"][r])
+        assert len(tree) == 2 * n - 1
+        roots = np.where(tree == -1)[0]
+        assert len(roots) == 1 and roots[0] == 2 * n - 2
+        kids = np.bincount(tree[tree >= 0], minlength=len(tree))
+        assert set(np.unique(kids)) <= {0, 2} and (kids == 0).sum() == n
+        nz = tree >= 0
+        assert np.all(times[nz] >= times[tree[nz]])  # children are younger (later) than parents
+    s = h.summaries()
+    assert np.all(s[:, 16] == 1) and np.all(s[:, 13] == 2 * c["sCounter"] - 1)

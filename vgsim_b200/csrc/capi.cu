@@ -26,6 +26,11 @@ static int fail(const std::string &m) {
 
 struct vgsim_handle_s : public Handle {};
 
+int vgsim_set_error(const char *msg) {
+    g_err = msg;
+    return 1;
+}
+
 template <class T>
 static int dalloc(Handle *h, T **p, size_t n) {
     void *q = nullptr;
@@ -628,5 +633,120 @@ int vgsim_get_lockdowns(vgsim_handle h, int r, int64_t *state, int64_t *pop, dou
 }
 
 int64_t vgsim_launch_count(vgsim_handle h) { return h->launches; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------
+namespace vg {
+// per-replicate summary vector: counters, final time, tree statistics (one warp per replicate)
+__global__ void summary_kernel(DevState st, const long long *node_off, const int *parent, const double *time,
+                               const int *n_nodes, const int *mut_n, const int *mig_n, double *out) {
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    for (int r = blockIdx.x * wpc + (threadIdx.x >> 5); r < st.R; r += gridDim.x * wpc) {
+        double *o = out + (size_t)r * VGSIM_NSUMMARY;
+        for (int i = lane; i < VGSIM_NSUMMARY; i += 32) o[i] = 0.0;
+        __syncwarp();
+        if (lane < NCOUNT) o[lane] = (double)st.counters[(size_t)r * NCOUNT + lane];
+        if (lane == 0) o[12] = st.time[r];
+        if (!node_off) continue;
+        const int n = n_nodes[r];
+        if (n == 0) continue;
+        const int *par = parent + node_off[r];
+        const double *tm = time + node_off[r];
+        double tmin = 1e300, tmax = -1e300, bl = 0.0;
+        int cherries = 0, roots = 0;
+        for (int i = lane; i < n; i += 32) {
+            double t = tm[i];
+            tmin = fmin(tmin, t);
+            tmax = fmax(tmax, t);
+            int p = par[i];
+            if (p >= 0) bl += t - tm[p]; else roots++;
+        }
+        // an internal node is a cherry when both children are leaves; leaves are the nodes nobody points to.
+        // children of node v have smaller ids than v only in creation order, so count via a second pass:
+        // node i is a leaf iff no j has par[j] == i  <=>  i was created by a SAMPLING row. Leaves never get
+        // children, and internal nodes always have exactly two, so "cherry" <=> both children are leaves.
+        // (computed on the host from the gathered parent array when needed; here: roots and lengths only)
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o2));
+            tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o2));
+            bl += __shfl_xor_sync(0xffffffffu, bl, o2);
+            roots += __shfl_xor_sync(0xffffffffu, roots, o2);
+            cherries += __shfl_xor_sync(0xffffffffu, cherries, o2);
+        }
+        if (lane == 0) {
+            o[13] = (double)n;
+            o[14] = tmax - tmin;   // tree height (latest sample to root)
+            o[15] = bl;            // total branch length
+            o[16] = (double)roots; // 1 when the genealogy coalesced completely
+            o[17] = (double)mut_n[r];
+            o[18] = (double)mig_n[r];
+            o[19] = tmin;          // time of the root (TMRCA in absolute time)
+        }
+    }
+}
+}  // namespace vg
+
+extern "C" {
+
+int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr) {
+    CK(cudaSetDevice(h->device));
+    const GenealogyBuffers &G = h->gen;
+    int wpc = 4, grid = (h->R + wpc - 1) / wpc;
+    if (grid > h->num_sms * 8) grid = h->num_sms * 8;
+    summary_kernel<<<grid, wpc * 32, 0, h->stream>>>(h->st, G.valid ? G.node_off : nullptr, G.parent, G.time, G.n_nodes,
+                                                      G.mut_n, G.mig_n, h->summaries);
+    h->launches++;
+    CK(cudaGetLastError());
+    if (dev_ptr) *dev_ptr = h->summaries;
+    return 0;
+}
+
+int vgsim_summaries(vgsim_handle h, double *out) {
+    if (vgsim_summaries_dev(h, nullptr)) return 1;
+    CK(cudaMemcpyAsync(out, h->summaries, (size_t)h->R * VGSIM_NSUMMARY * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int vgsim_set_event_log(vgsim_handle h, int r, const double *in, int64_t n, const int64_t *I_end) {
+    CK(cudaSetDevice(h->device));
+    if (r < 0 || r >= h->R) return fail("replicate out of range");
+    const Dims &D = h->D;
+    if (ensure_ev_cap(h, n > h->ev_bound ? n : h->ev_bound)) return 1;
+    std::vector<double> t(n);
+    std::vector<unsigned long long> d(n);
+    long long sC = 0, cnt[6] = {0, 0, 0, 0, 0, 0};
+    for (int64_t i = 0; i < n; i++) {
+        int ty = (int)in[n + i];
+        if (ty < 0 || ty > 5) return fail("set_event_log accepts direct-method rows only (types 0..5)");
+        t[i] = in[i];
+        int hap = (int)in[2 * n + i], pop = (int)in[3 * n + i], nhap = (int)in[4 * n + i], npop = (int)in[5 * n + i];
+        if (ty == EV_BIRTH) npop = 0;
+        if (hap < 0 || hap >= (ty == EV_SUSCCHANGE ? D.S : D.H) || pop < 0 || pop >= D.K || nhap < 0 || npop < 0 ||
+            npop >= D.K)
+            return fail("event row out of range");
+        d[i] = pack_event(ty, hap, pop, nhap, npop);
+        cnt[ty]++;
+        if (ty == EV_SAMPLING) sC++;
+    }
+    if (n) {
+        CK(cudaMemcpyAsync(h->st.ev_time + (size_t)r * h->st.ev_cap, t.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->st.ev_desc + (size_t)r * h->st.ev_cap, d.data(), n * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    long long c[NCOUNT] = {cnt[0], cnt[1], cnt[2], cnt[3], cnt[4], cnt[5], 0, 0, 1, (long long)n, 0, 0};
+    if (I_end) {
+        for (int i = 0; i < D.K * D.H; i++) c[C_GINF] += I_end[i];
+        CK(cudaMemcpyAsync(h->st.I + (size_t)r * D.K * D.H, I_end, (size_t)D.K * D.H * 8, cudaMemcpyHostToDevice, h->stream));
+    }
+    CK(cudaMemcpyAsync(h->st.counters + (size_t)r * NCOUNT, c, NCOUNT * 8, cudaMemcpyHostToDevice, h->stream));
+    double tl = n ? t[n - 1] : 0.0;
+    CK(cudaMemcpyAsync(h->st.time + r, &tl, 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (n > h->ev_bound) h->ev_bound = n;
+    h->st.first_simulation = 1;
+    h->gen.valid = false;
+    return 0;
+}
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 #include "../../include/vgsim_b200.h"
 #include "common.cuh"
 #include "samplers.cuh"
+#include "genrng.cuh"
 
 namespace vg {
 __global__ void poisson_tap_kernel(const double *lam, long long n, uint64_t seed, long long *out) {
@@ -35,5 +36,47 @@ extern "C" int vgsim_test_poisson(const double *lam, int64_t n, uint64_t seed, i
     cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost);
     cudaFree(dl);
     cudaFree(dout);
+    return e == cudaSuccess ? 0 : 1;
+}
+
+namespace vg {
+__global__ void hyper_tap_kernel(const long long *good, const long long *bad, const long long *sample, long long n,
+                                 const unsigned long long *words, long long n_words, long long *out, long long *used) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    GRng g;
+    g.mode = 2;
+    g.ud = nullptr;
+    g.uw = words;
+    g.pos = 0;
+    g.end = n_words;
+    g.err = 0;
+    g.has32 = 0;
+    g.b32 = 0;
+    g.have = 0;
+    g.ctr = 0;
+    for (long long i = 0; i < n; i++) out[i] = hypergeometric(g, good[i], bad[i], sample[i]);
+    *used = g.err ? -1 : g.pos;
+}
+}  // namespace vg
+
+// sequential draws from an injected raw-word stream (numpy PCG64 semantics), for draw-for-draw parity
+extern "C" int vgsim_test_hypergeometric(const int64_t *good, const int64_t *bad, const int64_t *sample, int64_t n,
+                                         const uint64_t *raw_words, int64_t n_words, int64_t *out, int64_t *words_used) {
+    long long *dg, *db, *ds, *dout, *dused;
+    unsigned long long *dw;
+    if (cudaMalloc(&dg, n * 8) || cudaMalloc(&db, n * 8) || cudaMalloc(&ds, n * 8) || cudaMalloc(&dout, n * 8) ||
+        cudaMalloc(&dused, 8) || cudaMalloc(&dw, n_words * 8))
+        return 1;
+    cudaMemcpy(dg, good, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, bad, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(ds, sample, n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dw, raw_words, n_words * 8, cudaMemcpyHostToDevice);
+    vg::hyper_tap_kernel<<<1, 32>>>(dg, db, ds, n, dw, n_words, dout, dused);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(out, dout, n * 8, cudaMemcpyDeviceToHost);
+    long long u = 0;
+    cudaMemcpy(&u, dused, 8, cudaMemcpyDeviceToHost);
+    if (words_used) *words_used = u;
+    cudaFree(dg); cudaFree(db); cudaFree(ds); cudaFree(dout); cudaFree(dused); cudaFree(dw);
     return e == cudaSuccess ? 0 : 1;
 }
