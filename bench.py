@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py — simulated events/sec of the replicate-batched tau-leap path (BASELINE.json metric).
+
+Workload ("T3"): 3 sites (64 haplotypes) x 10 demes x 3 susceptibility
+groups, 1e6 hosts per deme, R = 4096 replicates PER GPU (weak scaling: replicates shard over ranks with
+no data-path collective; one NCCL all-gather of the per-replicate summaries at the end).
+Phase A (setup, untimed): every replicate runs the direct method on the device to t = 60 (the
+reference's intended "direct warm-up, then tau" usage) and the resulting compartment
+states are snapshotted.  A STEP = one batch: vgsim_reset + state upload + vgsim_simulate_tau of
+L leaps for all R replicates (fresh seeds per step), i.e. R*L leaps, R*L*P Poisson channel draws and
+R*L*(4P+16) bytes of dense event log written to HBM (13.8 GB per step at the defaults >> 126 MB L2,
+so no L2 flush is needed between steps).
+
+  value  : events/s with the batch's input state already resident in HBM (device->device restore).
+  e2e    : the same step through the C ABI with HOST buffers: seeds + states are copied host->device
+           from pinned memory and counters + final states are read back device->host every step.
+           The event log stays in HBM, as it stays inside the engine object in the reference; it is
+           what vgsim_genealogy consumes.
+  roofline: dominant kernel = tau_kernel; achieved = leaps * (4P+16) B / its CUDA-event duration
+           (events recorded inside vgsim_simulate_tau on the launching stream).
+  cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref, Cython build of
+           /root/reference made by oracle/build_ref.py) on the host cores, one process per core,
+           each process running whole replicates of the same workload (direct warm-up to t = 60
+           untimed, then L tau leaps timed).  If oracle/_ref is absent the CPU oracle port is used.
+
+Launch: python bench.py [--gpus N --steps K --warmup W]   (N > 1: under torch.distributed.run)
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+T_WARM = 60.0
+SEED0 = 1000
+WORKLOAD = "T3 tau-leap: 3 sites (64 haplotypes) x 10 demes x 3 susceptibility groups, 1e6/deme"
+EVENT_KEYS = ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--replicates", type=int, default=4096, help="replicates per GPU")
+    ap.add_argument("--leaps", type=int, default=32, help="tau leaps per replicate per step")
+    ap.add_argument("--scenario", default="t3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=4.0, help="target timed CPU seconds per worker")
+    ap.add_argument("--cpu-worker", nargs=4, metavar=("SEED", "REPS", "LEAPS", "SCENARIO"), default=None)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the unmodified reference (oracle/_ref) or, failing that, the oracle port.  TEST/BASELINE
+# infrastructure: the only place bench.py touches oracle/.
+def _ref_counters(ref):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        ref.PrintCounters()
+    tot = 0
+    for line in buf.getvalue().splitlines():
+        if ":" in line:
+            tot += int(line.rsplit(":", 1)[1])
+    return tot
+
+
+def cpu_worker(seed, reps, leaps, scenario):
+    """One host core: `reps` replicates, each direct to T_WARM (untimed) then `leaps` tau leaps (timed)."""
+    import numpy as np  # noqa
+    from oracle import oracle as O
+    from scenarios import SCENARIOS
+    (U, K, S), setup = SCENARIOS[scenario]
+    H = 4 ** U
+    P = K * ((K - 1) * H * S + S * (S - 1) + H * (2 + 3 * U + S))
+    use_ref = O.reference_available()
+    t_tau = 0.0
+    events = 0
+    n_leaps = 0
+    for r in range(reps):
+        if use_ref:
+            def fresh():
+                m = O.make_reference(U, K, S, seed + r)
+                setup(m)
+                return m
+            with O.quiet():
+                # pass 1 learns the warm-up's row count; pass 2 repeats it with iterations == that count so the
+                # tau call's log allocation is exactly `leaps` rows (avoids reference quirk Q3)
+                m = fresh()
+                m.SimulatePopulation(2000000, 10 ** 9, T_WARM, 200)
+                import tempfile
+                with tempfile.TemporaryDirectory() as d:
+                    m.export_chain_events(os.path.join(d, "c"))
+                    n_direct = int(np.count_nonzero(np.load(os.path.join(d, "c.npy"))[0]))
+                del m
+                m = fresh()
+                m.SimulatePopulation(n_direct, 10 ** 9, T_WARM, 200)
+                c0 = _ref_counters(m)
+                t0 = time.perf_counter()
+                m.SimulatePopulation_tau(leaps, 10 ** 9, -1, 1)
+                t_tau += time.perf_counter() - t0
+                events += _ref_counters(m) - c0
+                n_leaps += leaps
+        else:
+            from vgsim_b200._engine import BirthDeathModel as Eng
+            e = Eng(U, K, S, seed + r, False, False, int(1e6), 0.0)
+            setup(e)
+            om = O.OracleModel.from_engine(e)
+            om.simulate(2000000, sample_size=10 ** 9, epidemic_time=T_WARM)
+            c0 = om.counters()
+            t0 = time.perf_counter()
+            om.simulate(leaps, sample_size=10 ** 9, epidemic_time=-1, method="tau", attempts=1)
+            t_tau += time.perf_counter() - t0
+            c1 = om.counters()
+            events += sum(c1[k] - c0[k] for k in EVENT_KEYS)
+            n_leaps += c1["events"] - c0["events"]
+    print(json.dumps({"events": int(events), "leaps": int(n_leaps), "seconds": t_tau, "P": P,
+                      "kind": "reference" if use_ref else "port"}))
+    sys.stdout.flush()
+    os._exit(0)  # the reference's destructor can abort on exit (free(): invalid pointer); results are out
+
+
+def run_cpu_sample(scenario, leaps, reps_per_worker, seed_base):
+    """All host cores at once, one process per core; returns aggregate events/s etc."""
+    cores = os.cpu_count() or 1
+    procs = []
+    t0 = time.perf_counter()
+    for c in range(cores):
+        cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(seed_base + c * reps_per_worker),
+               str(reps_per_worker), str(leaps), scenario]
+        procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    outs = []
+    for p in procs:
+        out, _ = p.communicate()
+        for line in out.splitlines():
+            if line.startswith("{"):
+                outs.append(json.loads(line))
+    wall = time.perf_counter() - t0
+    if not outs:
+        raise RuntimeError("CPU baseline workers produced no output")
+    ev = sum(o["events"] for o in outs)
+    lp = sum(o["leaps"] for o in outs)
+    # workers run concurrently; aggregate rate = sum of per-worker rates over their timed (tau) sections
+    rate = sum(o["events"] / o["seconds"] for o in outs if o["seconds"] > 0)
+    lrate = sum(o["leaps"] / o["seconds"] for o in outs if o["seconds"] > 0)
+    return dict(events_per_s=rate, leaps_per_s=lrate, events=ev, leaps=lp, cores=len(outs), wall=wall,
+                kind=outs[0]["kind"], P=outs[0]["P"], timed_seconds=max(o["seconds"] for o in outs))
+
+
+def calibrate_cpu_reps(scenario, leaps, target_seconds):
+    """One replicate on one core to size the sample (reference T3: ~2 ms per leap on one core)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(SEED0), "1", str(leaps), scenario]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    o = [json.loads(l) for l in out.splitlines() if l.startswith("{")][0]
+    return max(1, int(round(target_seconds / max(o["seconds"], 1e-3))))
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    reps = calibrate_cpu_reps(args.scenario, args.leaps, args.cpu_seconds)
+    for _ in range(args.warmup):
+        run_cpu_sample(args.scenario, args.leaps, 1, SEED0 + 500000)
+    t_events = 0
+    t_rate = []
+    walls = []
+    res = None
+    for s in range(args.steps):
+        res = run_cpu_sample(args.scenario, args.leaps, reps, SEED0 + s * 100000)
+        t_events += res["events"]
+        t_rate.append(res["events_per_s"])
+        walls.append(res["timed_seconds"])
+    value = sum(t_rate) / len(t_rate)
+    sample = "%d cores x %d replicates x %d tau leaps per step (direct warm-up to t=%g untimed)" % (
+        res["cores"], reps, args.leaps, T_WARM)
+    line = {
+        "impl": "reference", "metric": "simulated events/sec (tau-leap, replicate-batched)", "value": value,
+        "unit": "events/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "scenario": args.scenario, "leaps_per_step": args.leaps, "channels_P": res["P"]},
+        "cpu_baseline": {"value": value, "unit": "events/s", "cores": res["cores"], "kind": res["kind"], "sample": sample,
+                         "leaps_per_s": res["leaps_per_s"]},
+        "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+class _DevArray:
+    """__cuda_array_interface__ view of a raw device pointer (so torch can address library buffers)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def gpu_arm(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from scenarios import SCENARIOS
+    from vgsim_b200 import _capi
+    from vgsim_b200._engine import BirthDeathModel as Eng
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the vgsim_b200 hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    R, L = args.replicates, args.leaps
+    (U, K, S), setup = SCENARIOS[args.scenario]
+    seed_base = SEED0 + rank * R
+    eng = Eng(U, K, S, seed_base, False, False, int(1e6), 0.0, replicates=R, device=local_rank)
+    setup(eng)
+    h = eng._sync_params()
+    P, H = h.P, h.H
+    stream = torch.cuda.Stream(device=dev)
+    h.set_stream(stream.cuda_stream)
+
+    # ---- Phase A (untimed): device direct method to T_WARM for every replicate; snapshot the states
+    h.simulate_direct(250000, -1, T_WARM, 200)
+    cA = h.get_counters()
+    Sx0, I0 = h.get_state()
+    hSx = torch.from_numpy(Sx0).pin_memory()
+    hI = torch.from_numpy(I0).pin_memory()
+    with torch.cuda.stream(stream):
+        dSx = hSx.to(dev, non_blocking=True)
+        dI = hI.to(dev, non_blocking=True)
+    stream.synchronize()
+    out_Sx = torch.empty_like(hSx).pin_memory()
+    out_I = torch.empty_like(hI).pin_memory()
+    out_cnt = torch.empty((R, _capi.NCOUNTERS), dtype=torch.int64).pin_memory()
+    out_time = torch.empty(R, dtype=torch.float64).pin_memory()
+    cptr, _tptr = h.counters_dev_ptrs()
+    dev_counters = torch.as_tensor(_DevArray(cptr, (R, _capi.NCOUNTERS), "<i8"), device=dev)
+    n_total = args.warmup + args.steps
+    acc = torch.zeros((2 * n_total + 2, R, _capi.NCOUNTERS), dtype=torch.int64, device=dev)
+    seeds_pinned = torch.empty(R, dtype=torch.int64).pin_memory()
+
+    def seeds_for(step):
+        # fresh Philox keys per step and per replicate, disjoint across ranks
+        s = np.uint64(SEED0) + np.uint64(1 << 32) * np.uint64(step + 1) + np.arange(R, dtype=np.uint64) + np.uint64(rank * R)
+        seeds_pinned.numpy()[:] = s.view(np.int64)
+        return seeds_pinned.numpy().view(np.uint64)
+
+    kernel_ms = []
+
+    def step_resident(i):
+        h.reset()
+        h.set_seeds(seeds_for(i))
+        h.set_state_dev(dSx.data_ptr(), dI.data_ptr())
+        h.simulate_tau(L, -1, -1.0, 1, sync=False)
+        with torch.cuda.stream(stream):
+            acc[i].copy_(dev_counters, non_blocking=True)
+
+    def step_e2e(i):
+        h.reset()
+        h.set_seeds(seeds_for(i))                                    # H2D  R*8
+        h.set_state(hSx.numpy(), hI.numpy())                          # H2D  R*K*(S+H)*8 from pinned memory
+        h.simulate_tau(L, -1, -1.0, 1, sync=False)
+        h.get_counters(out=(out_cnt.numpy(), out_time.numpy()))       # D2H  R*(12+1)*8
+        h.get_state(out=(out_Sx.numpy(), out_I.numpy()))              # D2H  R*K*(S+H)*8
+        return int(out_cnt[:, :6].sum())
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(args.warmup, n_total):
+        step_resident(i)
+        kernel_ms.append(h.last_kernel_ms())
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = h.launch_count() - launches0
+    err = h.synchronize(strict=False)
+    cnt = acc[args.warmup:n_total].cpu().numpy()
+    events = int(cnt[:, :, :6].sum())
+    leaps = int(cnt[:, :, 10].sum())
+
+    # ---- end-to-end timing (host buffers through the C ABI)
+    for i in range(args.warmup):
+        step_e2e(n_total + i)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    f0.record(stream)
+    ev_e2e = 0
+    for i in range(args.steps):
+        ev_e2e += step_e2e(2 * n_total + i)
+    f1.record(stream)
+    barrier()
+    # the host-blocking copies make the host clock the honest one here: take the larger of the two
+    ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - w0))
+    clk = clocks.stop() if rank == 0 else None
+
+    # ---- final all-gather of per-replicate summaries (the only collective of the path)
+    sptr = h.summaries_dev_ptr()
+    summ = torch.as_tensor(_DevArray(sptr, (R, _capi.NSUMMARY), "<f8"), device=dev)
+    stream.synchronize()
+    if world > 1:
+        gathered = torch.empty((world * R, _capi.NSUMMARY), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, summ.clone())
+        t = torch.tensor([ms, ms_e2e, float(events), float(leaps), float(ev_e2e), float(launches), float(err),
+                          sum(kernel_ms)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(tmax[0]), float(tmax[1])
+        events, leaps, ev_e2e, launches = int(tsum[2]), int(tsum[3]), int(tsum[4]), int(tsum[5])
+        err = int(tmax[6])
+        kms_sum = float(tmax[7])
+    else:
+        kms_sum = sum(kernel_ms)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        b_leap = 4 * P + 16
+        leaps_per_launch_rank = leaps / max(world, 1) / args.steps
+        k_ms = kms_sum / args.steps
+        achieved = leaps_per_launch_rank * b_leap / (k_ms * 1e-3) / 1e9
+        h2d = R * 8 + R * K * (S + H) * 8
+        d2h = R * (_capi.NCOUNTERS + 1) * 8 + R * K * (S + H) * 8
+        line = {
+            "metric": "simulated events/sec (tau-leap, replicate-batched)",
+            "value": events / (ms * 1e-3), "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "scenario": args.scenario, "replicates_per_gpu": R, "leaps_per_step": L,
+                       "channels_P": P, "phase_a": "device direct method to t=%g per replicate (untimed)" % T_WARM,
+                       "l2": "each step writes %.1f GB of event log per GPU (> 126 MB L2): no flush needed" % (R * L * b_leap / 1e9),
+                       "parallelism": "replicates sharded %dx%d, no data-path collective" % (world, R)},
+            "leaps_per_s": leaps / (ms * 1e-3), "channel_draws_per_s": leaps * P / (ms * 1e-3),
+            "events_per_leap": events / max(leaps, 1),
+            "roofline": {"bound": "hbm", "kernel": "tau_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_leap": b_leap, "kernel_ms": k_ms},
+            "e2e": {"value": ev_e2e / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d * world,
+                    "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clk, "device_error_flags": err,
+            "phase_a": {"mean_events": float(np.mean(cA["events"])), "mean_time": float(np.mean(cA["time"])),
+                        "mean_infectious": float(I0.sum() / R)},
+        }
+        prof = os.path.join(ROOT, "profiles", "tau_kernel_traffic.json")
+        if os.path.exists(prof):
+            try:
+                line["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                reps = calibrate_cpu_reps(args.scenario, L, args.cpu_seconds)
+                res = run_cpu_sample(args.scenario, L, reps, SEED0)
+                line["cpu_baseline"] = {
+                    "value": res["events_per_s"], "unit": "events/s", "cores": res["cores"], "kind": res["kind"],
+                    "sample": "%d cores x %d replicates x %d tau leaps (direct warm-up to t=%g untimed)" % (
+                        res["cores"], reps, L, T_WARM), "leaps_per_s": res["leaps_per_s"]}
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "events/s", "cores": 0, "kind": "unavailable",
+                                        "sample": "failed: %s" % ex}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.cpu_worker:
+        seed, reps, leaps, scenario = args.cpu_worker
+        cpu_worker(int(seed), int(reps), int(leaps), scenario)
+        return
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    gpu_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,6 +76,16 @@ int vgsim_set_state(vgsim_handle h, const int64_t *Sx /*[R][K][S]*/, const int64
 int vgsim_get_state(vgsim_handle h, int64_t *Sx, int64_t *I, double *contact_density /*[R][K]*/,
                     int64_t *lockdown_on /*[R][K]*/);
 
+/* Same as vgsim_set_state with DEVICE pointers (asynchronous on the handle's stream), and the device
+ * pointers of the live compartment arrays Sx[R][K][S], I[R][K][H] (int64) for zero-copy consumers. */
+int vgsim_set_state_dev(vgsim_handle h, const int64_t *dSx, const int64_t *dI);
+int vgsim_state_dev(vgsim_handle h, void **dSx, void **dI);
+/* Back to the state of a freshly constructed engine with the uploaded parameters kept: event logs,
+ * counters, clocks, lockdown flags and genealogy are dropped (log capacity is retained and reused), the
+ * next simulate call is a "first simulation" again (what re-running the reference's constructor +
+ * setters does; batch drivers call it between independent batches, followed by vgsim_set_state). */
+int vgsim_reset(vgsim_handle h);
+
 /* SimulatePopulation (src/_BirthDeath.pyx:396-429): batched direct Gillespie, one warp per
  * replicate.  `epidemic_time` is a C float like the reference's (quirk Q1); -1 = no limit;
  * sample_size -1 = no limit.  Appends up to `iterations` rows to each replicate's event log. */
@@ -154,6 +164,12 @@ int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr);
 
 /* Launch accounting: kernels launched by this handle since creation. */
 int64_t vgsim_launch_count(vgsim_handle h);
+/* Device time of the LAST forward kernel (tau / direct), bracketed by CUDA events on the handle's
+ * stream inside vgsim_simulate_* (replaces the reference's time.time() pair, src/_interface.py:821-827).
+ * Blocks until that kernel has finished. */
+int vgsim_last_kernel_ms(vgsim_handle h, float *ms);
+/* Device pointers of counters[R][VGSIM_NCOUNTERS] (int64) and current_time[R] (fp64). */
+int vgsim_counters_dev(vgsim_handle h, void **counters, void **current_time);
 
 /* Test taps for the device samplers (Poisson: multiplication-free inversion / PTRS;
  * hypergeometric: numpy-compatible HYP/HRUA): n draws each from Philox keyed by `seed`. */

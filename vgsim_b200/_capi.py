@@ -39,6 +39,9 @@ def _load():
         "vgsim_set_replicate_params": (c_int, [P, P]),
         "vgsim_set_state": (c_int, [P, P, P]),
         "vgsim_get_state": (c_int, [P, P, P, P, P]),
+        "vgsim_set_state_dev": (c_int, [P, P, P]),
+        "vgsim_state_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
+        "vgsim_reset": (c_int, [P]),
         "vgsim_simulate_direct": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
         "vgsim_simulate_tau": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
         "vgsim_synchronize": (c_int, [P]),
@@ -62,6 +65,8 @@ def _load():
         "vgsim_summaries": (c_int, [P, P]),
         "vgsim_summaries_dev": (c_int, [P, ctypes.POINTER(c_void_p)]),
         "vgsim_launch_count": (c_int64, [P]),
+        "vgsim_last_kernel_ms": (c_int, [P, ctypes.POINTER(c_float)]),
+        "vgsim_counters_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vgsim_test_poisson": (c_int, [P, c_int64, c_uint64, P]),
         "vgsim_test_hypergeometric": (c_int, [P, P, P, c_int64, P, c_int64, P, P]),
     }
@@ -144,7 +149,25 @@ class Handle:
         assert I is None or I.shape == (self.R, self.K, self.H)
         _ck(lib.vgsim_set_state(self._h, _p(Sx), _p(I)))
 
-    def get_state(self, full=False):
+    def set_state_dev(self, dSx_ptr, dI_ptr):
+        _ck(lib.vgsim_set_state_dev(self._h, c_void_p(dSx_ptr), c_void_p(dI_ptr)))
+
+    def state_dev_ptrs(self):
+        a, b = c_void_p(), c_void_p()
+        _ck(lib.vgsim_state_dev(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def reset(self):
+        _ck(lib.vgsim_reset(self._h))
+
+    def get_state(self, full=False, out=None):
+        """out=(Sx, I): caller-owned (e.g. pinned) int64 buffers of the right shape to fill instead."""
+        if out is not None:
+            Sx, I = out
+            assert Sx.shape == (self.R, self.K, self.S) and I.shape == (self.R, self.K, self.H)
+            assert Sx.dtype == np.int64 and I.dtype == np.int64 and Sx.flags.c_contiguous and I.flags.c_contiguous
+            _ck(lib.vgsim_get_state(self._h, _p(Sx), _p(I), None, None))
+            return Sx, I
         Sx = np.empty((self.R, self.K, self.S), np.int64)
         I = np.empty((self.R, self.K, self.H), np.int64)
         cd = np.empty((self.R, self.K), np.float64)
@@ -205,7 +228,12 @@ class Handle:
                                                                      "migPop", "totals")]))
         return r
 
-    def get_counters(self):
+    def get_counters(self, out=None):
+        if out is not None:
+            c, t = out
+            assert c.shape == (self.R, NCOUNTERS) and c.dtype == np.int64 and t.shape == (self.R,)
+            _ck(lib.vgsim_get_counters(self._h, _p(c), _p(t)))
+            return c, t
         c = np.empty((self.R, NCOUNTERS), np.int64)
         t = np.empty(self.R, np.float64)
         _ck(lib.vgsim_get_counters(self._h, _p(c), _p(t)))
@@ -278,6 +306,16 @@ class Handle:
         p = c_void_p()
         _ck(lib.vgsim_summaries_dev(self._h, ctypes.byref(p)))
         return p.value
+
+    def last_kernel_ms(self):
+        ms = c_float()
+        _ck(lib.vgsim_last_kernel_ms(self._h, ctypes.byref(ms)))
+        return float(ms.value)
+
+    def counters_dev_ptrs(self):
+        a, b = c_void_p(), c_void_p()
+        _ck(lib.vgsim_counters_dev(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
 
     def launch_count(self):
         return int(lib.vgsim_launch_count(self._h))

@@ -81,6 +81,9 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
     h->R = n_replicates;
     h->n_pp = n_param_points;
     h->hp.resize(n_param_points);
+    h->rep_pp_host.assign(n_replicates, 0);
+    CK(cudaEventCreate(&h->ev_k0));
+    CK(cudaEventCreate(&h->ev_k1));
     DevState &st = h->st;
     memset(&st, 0, sizeof(st));
     st.D = D;
@@ -126,6 +129,8 @@ int vgsim_destroy(vgsim_handle h) {
     cudaDeviceSynchronize();
     for (void *p : h->allocs) cudaFree(p);
     h->allocs.clear();
+    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
+    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
     delete h;
     return 0;
 }
@@ -150,6 +155,7 @@ int vgsim_set_replicate_params(vgsim_handle h, const int32_t *map) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync((void *)h->st.rep_pp, map, (size_t)h->R * 4, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    h->rep_pp_host.assign(map, map + h->R);
     return 0;
 }
 
@@ -299,6 +305,48 @@ int vgsim_set_state(vgsim_handle h, const int64_t *Sx, const int64_t *I) {
     return 0;
 }
 
+int vgsim_set_state_dev(vgsim_handle h, const int64_t *dSx, const int64_t *dI) {
+    CK(cudaSetDevice(h->device));
+    const Dims &D = h->D;
+    if (dSx) CK(cudaMemcpyAsync(h->st.Sx, dSx, (size_t)h->R * D.K * D.S * 8, cudaMemcpyDeviceToDevice, h->stream));
+    if (dI) CK(cudaMemcpyAsync(h->st.I, dI, (size_t)h->R * D.K * D.H * 8, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int vgsim_state_dev(vgsim_handle h, void **dSx, void **dI) {
+    if (dSx) *dSx = h->st.Sx;
+    if (dI) *dI = h->st.I;
+    return 0;
+}
+
+int vgsim_reset(vgsim_handle h) {
+    CK(cudaSetDevice(h->device));
+    DevState &st = h->st;
+    const size_t R = h->R;
+    CK(cudaMemsetAsync(st.counters, 0, R * NCOUNT * 8, h->stream));
+    CK(cudaMemsetAsync(st.time, 0, R * 8, h->stream));
+    CK(cudaMemsetAsync(st.epoch, 0, R * 4, h->stream));
+    CK(cudaMemsetAsync(st.err, 0, R * 4, h->stream));
+    CK(cudaMemsetAsync(st.loc_n, 0, R * 4, h->stream));
+    CK(cudaMemsetAsync(st.lock, 0, R * st.D.K * 4, h->stream));
+    // live contact density back to the uploaded value of each replicate's parameter point
+    {
+        const int K = st.D.K;
+        std::vector<double> cdv(R * K, 1.0);
+        for (size_t r = 0; r < R; r++) {
+            const HostParams &P = h->hp[h->rep_pp_host[r]];
+            if (P.uploaded) std::copy(P.cd.begin(), P.cd.end(), cdv.begin() + r * K);
+        }
+        CK(cudaMemcpyAsync(st.cd, cdv.data(), cdv.size() * 8, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));  // cdv is pageable and goes out of scope
+    }
+    h->ev_bound = 0;
+    h->leap_bound = 0;
+    st.first_simulation = 0;
+    h->gen.valid = false;
+    return 0;
+}
+
 int vgsim_get_state(vgsim_handle h, int64_t *Sx, int64_t *I, double *cd, int64_t *lock) {
     CK(cudaSetDevice(h->device));
     const Dims &D = h->D;
@@ -387,8 +435,11 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
     if (ensure_ev_cap(h, h->ev_bound + iterations) || ensure_leap_cap(h, h->leap_bound + iterations)) return 1;
     if (prepare(h, 1)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
+    CK(cudaEventRecord(h->ev_k0, h->stream));
     cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms);
     if (e != cudaSuccess) return fail(std::string("tau kernel: ") + cudaGetErrorString(e));
+    CK(cudaEventRecord(h->ev_k1, h->stream));
+    h->ev_valid = true;
     h->launches++;
     h->ev_bound += iterations;
     h->leap_bound += iterations;
@@ -402,8 +453,11 @@ int vgsim_simulate_direct(vgsim_handle h, int64_t iterations, int64_t sample_siz
     if (ensure_ev_cap(h, h->ev_bound + iterations)) return 1;
     if (prepare(h, 0)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
+    CK(cudaEventRecord(h->ev_k0, h->stream));
     cudaError_t e = launch_direct(h->st, a, h->stream, h->num_sms);
     if (e != cudaSuccess) return fail(std::string("direct kernel: ") + cudaGetErrorString(e));
+    CK(cudaEventRecord(h->ev_k1, h->stream));
+    h->ev_valid = true;
     h->launches++;
     h->ev_bound += iterations;
     return 0;
@@ -633,6 +687,20 @@ int vgsim_get_lockdowns(vgsim_handle h, int r, int64_t *state, int64_t *pop, dou
 }
 
 int64_t vgsim_launch_count(vgsim_handle h) { return h->launches; }
+
+int vgsim_last_kernel_ms(vgsim_handle h, float *ms) {
+    CK(cudaSetDevice(h->device));
+    if (!h->ev_valid) return fail("no hot kernel was launched yet");
+    CK(cudaEventSynchronize(h->ev_k1));
+    CK(cudaEventElapsedTime(ms, h->ev_k0, h->ev_k1));
+    return 0;
+}
+
+int vgsim_counters_dev(vgsim_handle h, void **counters, void **current_time) {
+    if (counters) *counters = h->st.counters;
+    if (current_time) *current_time = h->st.time;
+    return 0;
+}
 
 }  // extern "C"
 

@@ -49,6 +49,9 @@ struct Handle {
     bool state_set = false;
     GenealogyBuffers gen;
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
+    std::vector<int> rep_pp_host;  // host copy of the replicate -> parameter point map
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the last hot kernel on the handle's stream
+    bool ev_valid = false;
     std::vector<void *> allocs;
 };
 
