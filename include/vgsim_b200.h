@@ -162,6 +162,12 @@ int vgsim_get_migrations(vgsim_handle h, int replicate, int64_t *node, double *t
 int vgsim_summaries(vgsim_handle h, double *out);
 int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr);
 
+/* Parity tap: variant 1 makes vgsim_simulate_tau walk all P channels of every leap instead of the
+ * compact infectious-cell list (variant 0, the default).  Both address the Philox stream by
+ * (cell, channel-within-cell), so their logs are bit-identical; tests use it to prove that skipping
+ * zero-propensity channels changes nothing (numpy's random_poisson(0) consumes no randomness either). */
+int vgsim_set_tau_variant(vgsim_handle h, int variant);
+
 /* Launch accounting: kernels launched by this handle since creation. */
 int64_t vgsim_launch_count(vgsim_handle h);
 /* Device time of the LAST forward kernel (tau / direct), bracketed by CUDA events on the handle's

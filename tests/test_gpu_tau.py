@@ -201,3 +201,35 @@ def test_tau_distribution_matches_oracle(name, seed, t0, dt, R):
         ora["inf_deme0"].append(If[0].sum())
     bad = _ks_all(dev, ora, keys)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name,seed,t0,dt,leaps", [("t3small", 5, 60.0, 25.0, 60), ("s9", 2020, 4.0, 2.0, 80),
+                                                   ("t3", 11, 70.0, 8.0, 40), ("s7", 2020, 6.0, 3.0, 80)])
+def test_cell_list_walk_is_bit_identical_to_all_channel_walk(name, seed, t0, dt, leaps):
+    """The product kernel draws only for channels owned by infectious cells (I > 0); the parity variant walks
+    all P channels.  Both address Philox by (cell, channel-within-cell), so logs, times, states and counters
+    must be identical bit for bit: skipping Poisson(0) channels changes nothing (numpy's random_poisson(0)
+    consumes no randomness in the reference either, src/_BirthDeath.pyx:2531-2532)."""
+    Sx0, I0 = warm_state(name, seed, t0)
+    R = 6
+    out = []
+    for variant in (0, 1):
+        e = make_engine(name, seed, replicates=R)
+        e._susceptible[...] = Sx0
+        e._infectious[...] = I0
+        h = e._sync_params()
+        h.set_tau_variant(variant)
+        h.simulate_tau(leaps, -1, dt, 1)
+        c = h.get_counters()
+        Sx_f, I_f = h.get_state()
+        logs = [h.get_tau_log(r) for r in range(R)]
+        out.append((c, Sx_f, I_f, logs, [h.get_lockdowns(r) for r in range(R)]))
+    (c0, S0, I0f, L0, K0), (c1, S1, I1f, L1, K1) = out
+    assert c0["leaps"].min() > 3
+    for k in c0:
+        assert np.array_equal(c0[k], c1[k]), k
+    assert np.array_equal(S0, S1) and np.array_equal(I0f, I1f)
+    for r in range(R):
+        assert np.array_equal(L0[r][0], L1[r][0]) and np.array_equal(L0[r][1], L1[r][1])
+        for a, b in zip(K0[r], K1[r]):
+            assert np.array_equal(a, b)

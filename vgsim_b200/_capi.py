@@ -65,6 +65,7 @@ def _load():
         "vgsim_summaries": (c_int, [P, P]),
         "vgsim_summaries_dev": (c_int, [P, ctypes.POINTER(c_void_p)]),
         "vgsim_launch_count": (c_int64, [P]),
+        "vgsim_set_tau_variant": (c_int, [P, c_int]),
         "vgsim_last_kernel_ms": (c_int, [P, ctypes.POINTER(c_float)]),
         "vgsim_counters_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vgsim_test_poisson": (c_int, [P, c_int64, c_uint64, P]),
@@ -319,6 +320,10 @@ class Handle:
 
     def launch_count(self):
         return int(lib.vgsim_launch_count(self._h))
+
+    def set_tau_variant(self, variant):
+        """0 = infectious-cell list (product path), 1 = walk all P channels (parity tap, bit-identical log)."""
+        _ck(lib.vgsim_set_tau_variant(self._h, int(variant)))
 
 
 def test_poisson(lam, seed=1):

@@ -436,7 +436,7 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
     if (prepare(h, 1)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms);
+    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms, h->tau_variant);
     if (e != cudaSuccess) return fail(std::string("tau kernel: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(h->ev_k1, h->stream));
     h->ev_valid = true;
@@ -687,6 +687,12 @@ int vgsim_get_lockdowns(vgsim_handle h, int r, int64_t *state, int64_t *pop, dou
 }
 
 int64_t vgsim_launch_count(vgsim_handle h) { return h->launches; }
+
+int vgsim_set_tau_variant(vgsim_handle h, int variant) {
+    if (variant != 0 && variant != 1) return fail("tau variant must be 0 or 1");
+    h->tau_variant = variant;
+    return 0;
+}
 
 int vgsim_last_kernel_ms(vgsim_handle h, float *ms) {
     CK(cudaSetDevice(h->device));

@@ -46,6 +46,7 @@ struct Handle {
     std::vector<HostParams> hp;
     long long ev_bound = 0, leap_bound = 0;  // host upper bounds of log rows / leaps per replicate
     long long launches = 0;
+    int tau_variant = 0;  // 0 = infectious-cell list (product), 1 = walk all P channels (parity tap)
     bool state_set = false;
     GenealogyBuffers gen;
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
@@ -56,7 +57,7 @@ struct Handle {
 };
 
 // kernels' host launchers (defined in the .cu files)
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms);
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant);
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream);
 cudaError_t launch_prepare(const DevState &st, int first, int tau_mode, cudaStream_t stream);

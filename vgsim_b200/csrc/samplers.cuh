@@ -16,9 +16,10 @@ namespace vg {
 
 struct PhiloxCtx {
     uint2 key;
-    uint32_t c0, c1, c2;  // counter words x,y,z ; w = domain
-    __device__ __forceinline__ uint4 draw(uint32_t domain) const {
-        return philox4x32_10(make_uint4(c0, c1, c2, domain), key);
+    uint32_t c0, c1, c2;  // counter words x,y,z ; w = dom0 + kind * dstride
+    uint32_t dom0 = 0, dstride = 1;  // tau kernel: dom0 = channel group within the cell, dstride = groups per cell
+    __device__ __forceinline__ uint4 draw(uint32_t kind) const {
+        return philox4x32_10(make_uint4(c0, c1, c2, dom0 + kind * dstride), key);
     }
 };
 

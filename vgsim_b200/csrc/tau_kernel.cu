@@ -1,70 +1,94 @@
 // Replicate-batched tau-leaping (reference SimulatePopulation_tau, src/_BirthDeath.pyx:2293-2593).
 //
 // One CTA per replicate (grid-stride over replicates).  Compartment counts, drifts, per-leap deltas
-// and the parameter point live in shared memory for the whole run; per leap the CTA
-//   1. contracts the migration force of infection F[t,h] = sum_s eff[t,s] m[s,s] b[h] I[s,h]
-//   2. assembles the net drifts and tau (ChooseTau, :2432-2450, incl. the float-epsilon quirk)
-//   3. walks the P positional channels in chunks of 4: propensity -> lambda ->
-//      Poisson draw from Philox(key=seed, ctr=(chunk, leap, retry|epoch)) -> shared-memory deltas,
-//      and streams the int32 counts to the dense HBM log with 16-byte stores
-//   4. checks feasibility (:2522-2528, with the source-deme book-keeping quirk Q8); on failure
-//      halves tau and redraws the whole leap (:2316-2321)
-//   5. applies the deltas, appends the MULTITYPE row, runs CheckLockdown for every deme.
-// The same channel code backs the deterministic parity tap (propensity_kernel).
+// and the parameter point live in shared memory for the whole run.  The dense event log row of a leap
+// (4*P bytes, one int32 count per positional channel) is the only steady-state HBM
+// traffic, so the kernel is organised around it:
+//
+//   0. the row is zero-filled with 16-byte coalesced stores as soon as the leap starts (the stores
+//      drain while the CTA computes);
+//   1. F[t,h] = sum_s eff[t,s] m[s,s] b[h] I[s,h] only for haplotypes present anywhere (colcnt[h] > 0);
+//   2. net drifts and tau (ChooseTau, :2432-2450, incl. the float-epsilon quirk);
+//   3. Poisson draws only for channels that can fire: a compact list of infectious cells (p,h) with
+//      I > 0 is kept in shared memory; each cell owns LC = E + (K-1)*S channels (its E deme-block
+//      events and its out-migration to every other deme x group), walked in groups of 4 that share one
+//      Philox4x32-10 block keyed by (seed; cell, leap, retry|epoch, group).  Poisson(0) = 0 consumes no
+//      randomness in the reference either (numpy random_poisson), so skipping the other channels does
+//      not change the distribution.  Non-zero counts are scattered into the zero-filled row;
+//   4. feasibility (:2522-2528, with the source-deme book-keeping quirk Q8); on failure tau is halved
+//      and the whole leap redrawn (:2316-2321);
+//   5. deltas applied, the infectious-cell list rebuilt, MULTITYPE row appended, CheckLockdown for
+//      every deme (:2326-2329).
+//
+// tau_kernel<true> walks ALL P channels instead of the cell list (same Philox addressing, so the two
+// variants are bit-identical by construction); it is kept as a parity tap (vgsim_set_tau_variant).
+// The same channel code backs the deterministic propensity tap (propensity_kernel).
 #include "common.cuh"
 #include "rates.cuh"
 #include "samplers.cuh"
 
 namespace vg {
 
-struct TauShared {
-    // fp64
-    double *b, *d, *sr, *q, *tmq, *sigT, *T, *sm, *cd, *c, *mdiag, *sizeD, *maxEBM, *dI, *dS, *F, *red;
-    // int32
-    int *I, *Sx, *chkI, *updI, *dSx, *g, *lock, *tot;
-    int *flags;  // [0]=leap sampling count, [1]=bad flag, [2]=flip flag, [3]=overflow
+extern __shared__ __align__(16) unsigned char smem_raw[];
+
+// A shared-memory array addressed by a 32-bit byte offset from the dynamic shared-memory base: keeps the
+// ~30 array handles of TauShared in one register each and lets the compiler emit LDS/STS/ATOMS directly.
+template <class T>
+struct SArr {
+    int off;
+    __device__ __forceinline__ T *ptr() const { return reinterpret_cast<T *>(smem_raw + off); }
+    __device__ __forceinline__ T &operator[](int i) const { return ptr()[i]; }
+    __device__ __forceinline__ operator T *() const { return ptr(); }
 };
 
-__host__ __device__ inline size_t tau_smem_bytes(const Dims &D) {
-    size_t nd = (size_t)D.H * 4 + (size_t)D.H * D.U * 3 + (size_t)D.S * D.H + (size_t)D.S * D.S + (size_t)D.K * 7 +
-                (size_t)D.K * D.H * 2 + (size_t)D.K * D.S + 40;
-    size_t ni = (size_t)D.K * D.H * 3 + (size_t)D.K * D.S * 2 + D.H + D.K * 2 + 8;
-    return nd * 8 + ((ni + 1) & ~(size_t)1) * 4;
+struct TauShared {
+    // fp64
+    SArr<double> b, d, sr, q, tmq, sigT, T, sm, cd, c, mdiag, sizeD, maxEBM, startN, endN, dI, dS, F, red, effS;
+    bool has_effS;
+    // int32
+    SArr<int> I, Sx, chkI, updI, dSx, g, lock;
+    SArr<int> tot[2];     // per-deme infectious totals          (double-buffered: built for the next leap while
+    SArr<int> colcnt[2];  // #demes holding haplotype h           the current one is still being read)
+    SArr<int> act[2];     // compact list of cells with I > 0
+    SArr<int> flags;      // [0..5]=per-leap tallies by event type (EV_*) [6]=flip flag [7]=overflow [8+b]=nAct[b]
+                          // [10]=flips total
+    SArr<long long> tally64;  // [0..5] events by type since the kernel (or the last Restart) began
+    int bytes;
+};
+
+__host__ __device__ inline bool tau_eff_in_smem(const Dims &D) { return D.K <= 32; }
+
+__host__ __device__ inline TauShared tau_layout(const Dims &D) {
+    TauShared s;
+    int o = 0;
+    auto dbl = [&](SArr<double> &a, int n) { a.off = o; o += n * 8; };
+    auto i32 = [&](SArr<int> &a, int n) { a.off = o; o += n * 4; };
+    auto i64 = [&](SArr<long long> &a, int n) { o = (o + 7) & ~7; a.off = o; o += n * 8; };
+    dbl(s.b, D.H); dbl(s.d, D.H); dbl(s.sr, D.H); dbl(s.tmq, D.H);
+    dbl(s.q, D.H * D.U * 3);
+    dbl(s.sigT, D.S * D.H);
+    dbl(s.T, D.S * D.S);
+    dbl(s.sm, D.K); dbl(s.cd, D.K); dbl(s.c, D.K); dbl(s.mdiag, D.K); dbl(s.sizeD, D.K); dbl(s.maxEBM, D.K);
+    dbl(s.startN, D.K); dbl(s.endN, D.K);
+    o += D.K * 8;  // spare
+    dbl(s.dI, D.K * D.H); dbl(s.F, D.K * D.H);
+    dbl(s.dS, D.K * D.S);
+    dbl(s.red, 40);
+    s.has_effS = tau_eff_in_smem(D);
+    s.effS.off = o;
+    if (s.has_effS) o += D.K * D.K * 8;
+    i32(s.I, D.K * D.H); i32(s.chkI, D.K * D.H); i32(s.updI, D.K * D.H);
+    i32(s.act[0], D.K * D.H); i32(s.act[1], D.K * D.H);
+    i32(s.Sx, D.K * D.S); i32(s.dSx, D.K * D.S);
+    i32(s.g, D.H); i32(s.colcnt[0], D.H); i32(s.colcnt[1], D.H);
+    i32(s.lock, D.K); i32(s.tot[0], D.K); i32(s.tot[1], D.K);
+    i32(s.flags, 16);
+    i64(s.tally64, 8);
+    s.bytes = o;
+    return s;
 }
 
-__device__ inline void carve(TauShared &s, const Dims &D, unsigned char *base) {
-    double *p = reinterpret_cast<double *>(base);
-    s.b = p; p += D.H;
-    s.d = p; p += D.H;
-    s.sr = p; p += D.H;
-    s.tmq = p; p += D.H;
-    s.q = p; p += D.H * D.U * 3;
-    s.sigT = p; p += D.S * D.H;
-    s.T = p; p += D.S * D.S;
-    s.sm = p; p += D.K;
-    s.cd = p; p += D.K;
-    s.c = p; p += D.K;
-    s.mdiag = p; p += D.K;
-    s.sizeD = p; p += D.K;
-    s.maxEBM = p; p += D.K;
-    p += D.K;  // spare
-    s.dI = p; p += D.K * D.H;
-    s.F = p; p += D.K * D.H;
-    s.dS = p; p += D.K * D.S;
-    s.red = p; p += 40;
-    int *q = reinterpret_cast<int *>(p);
-    s.I = q; q += D.K * D.H;
-    s.chkI = q; q += D.K * D.H;
-    s.updI = q; q += D.K * D.H;
-    s.Sx = q; q += D.K * D.S;
-    s.dSx = q; q += D.K * D.S;
-    s.g = q; q += D.H;
-    s.lock = q; q += D.K;
-    s.tot = q; q += D.K;
-    s.flags = q;
-}
-
-// One reaction channel: positional index c -> propensity (per unit time), plus where its count goes.
+// One reaction channel: propensity (per unit time) plus where its count goes.
 struct Channel {
     int type;        // EV_* ; EV_MULTITYPE = padding (c >= P)
     int i_dec;       // I cell that loses n   (-1 none)
@@ -75,69 +99,101 @@ struct Channel {
     double prop;
 };
 
-__device__ __forceinline__ void decode_channel(int c, const Dims &D, const TauShared &s, const double *eff,
-                                               Channel &ch) {
+// Channel l of infectious cell (p,h): l < E are the deme-block events RECOVERY, SAMPLING, MUTATION[u][k],
+// TRANSMISSION[s]; l >= E is out-migration of h from p to the (l-E)/S-th other deme, group (l-E)%S.
+// Returns the positional index c of the channel in the dense row.
+__device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, const TauShared &s, const double *eff,
+                                            Channel &ch) {
     const int K = D.K, H = D.H, S = D.S;
+    const int cell = p * H + h;
+    const int Ii = s.I[cell];
     ch.i_dec = ch.i_inc = ch.i_chk = ch.s_dec = ch.s_inc = -1;
     ch.prop = 0.0;
+    if (l < D.E) {
+        if (l == 0) {  // RECOVERY (:2386)
+            ch.type = EV_DEATH;
+            ch.i_dec = cell;
+            ch.s_inc = p * S + s.g[h];
+            ch.prop = s.d[h] * (double)Ii;
+        } else if (l == 1) {  // SAMPLING (:2392)
+            ch.type = EV_SAMPLING;
+            ch.i_dec = cell;
+            ch.s_inc = p * S + s.g[h];
+            ch.prop = s.sr[h] * (double)Ii * s.sm[p];
+        } else if (l < 2 + 3 * D.U) {  // MUTATION (:2400-2401)
+            int uk = l - 2, u = uk / 3, k = uk - u * 3;
+            ch.type = EV_MUTATION;
+            ch.i_dec = cell;
+            ch.i_inc = ch.i_chk = p * H + mutate_hap(h, u, k, D.U);
+            ch.prop = s.q[h * D.U * 3 + uk] * (double)Ii;
+        } else {  // TRANSMISSION (:2410-2414)
+            int sn = l - 2 - 3 * D.U;
+            ch.type = EV_BIRTH;
+            ch.i_inc = ch.i_chk = cell;
+            ch.s_dec = p * S + sn;
+            if (Ii != 0) ch.prop = s.b[h] * s.sigT[sn * H + h] * s.c[p] * (double)s.Sx[p * S + sn] * (double)Ii;
+        }
+        return D.NA + p * D.PD + D.SS1 + h * D.E + l;
+    }
+    // MIGRATION  [sp][tp != sp][s][h]  (:2366-2367)
+    int mm = l - D.E;
+    int tpp = mm / S, sn = mm - tpp * S;
+    int tp = tpp + (tpp >= p ? 1 : 0);
+    ch.type = EV_MIGRATION;
+    ch.i_inc = tp * H + h;
+    ch.i_chk = cell;
+    ch.s_dec = tp * S + sn;
+    if (Ii != 0)
+        ch.prop = eff[tp * K + p] * (double)s.Sx[tp * S + sn] * (double)Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
+    return ((p * (K - 1) + tpp) * S + sn) * H + h;
+}
+
+// SUSCCHANGE channel l of deme p: [ss][ts != ss]  (:2378)
+__device__ __forceinline__ int susc_channel(int p, int l, const Dims &D, const TauShared &s, Channel &ch) {
+    const int S = D.S;
+    int ss = l / (S - 1), tsp = l - ss * (S - 1);
+    int ts = tsp + (tsp >= ss ? 1 : 0);
+    ch.i_dec = ch.i_inc = ch.i_chk = -1;
+    ch.type = EV_SUSCCHANGE;
+    ch.s_dec = p * S + ss;
+    ch.s_inc = p * S + ts;
+    ch.prop = s.T[ss * S + ts] * (double)s.Sx[p * S + ss];
+    return D.NA + p * D.PD + l;
+}
+
+// Positional index c -> channel, and its Philox address (owner id, local index).
+__device__ __forceinline__ void decode_channel(int c, const Dims &D, const TauShared &s, const double *eff, Channel &ch,
+                                               int &owner, int &l) {
+    const int K = D.K, H = D.H, S = D.S;
+    if (c >= D.P) {
+        ch.i_dec = ch.i_inc = ch.i_chk = ch.s_dec = ch.s_inc = -1;
+        ch.prop = 0.0;
+        ch.type = EV_MULTITYPE;
+        owner = l = 0;
+        return;
+    }
     if (c < D.NA) {
-        // MIGRATION  [sp][tp != sp][s][h]  (:2366-2367)
         int row = c >> D.hshift, h = c & (H - 1);
         int pair = row / S, sn = row - pair * S;
         int sp = pair / (K - 1), tpp = pair - sp * (K - 1);
-        int tp = tpp + (tpp >= sp ? 1 : 0);
-        ch.type = EV_MIGRATION;
-        ch.i_inc = tp * H + h;
-        ch.i_chk = sp * H + h;
-        ch.s_dec = tp * S + sn;
-        int Ii = s.I[sp * H + h];
-        if (Ii != 0)
-            ch.prop = eff[tp * K + sp] * (double)s.Sx[tp * S + sn] * (double)Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[sp];
-        return;
-    }
-    if (c >= D.P) {
-        ch.type = EV_MULTITYPE;
+        owner = sp * H + h;
+        l = D.E + tpp * S + sn;
+        cell_channel(sp, h, l, D, s, eff, ch);
         return;
     }
     int c2 = c - D.NA;
     int p = c2 / D.PD, r = c2 - p * D.PD;
     if (r < D.SS1) {
-        // SUSCCHANGE [p][ss][ts != ss]  (:2378)
-        int ss = r / (S - 1), tsp = r - ss * (S - 1);
-        int ts = tsp + (tsp >= ss ? 1 : 0);
-        ch.type = EV_SUSCCHANGE;
-        ch.s_dec = p * S + ss;
-        ch.s_inc = p * S + ts;
-        ch.prop = s.T[ss * S + ts] * (double)s.Sx[p * S + ss];
+        owner = K * H + p;
+        l = r;
+        susc_channel(p, r, D, s, ch);
         return;
     }
     int r2 = r - D.SS1;
-    int h = r2 / D.E, e = r2 - h * D.E;
-    int cell = p * H + h;
-    int Ii = s.I[cell];
-    if (e == 0) {  // RECOVERY (:2386)
-        ch.type = EV_DEATH;
-        ch.i_dec = cell;
-        ch.s_inc = p * S + s.g[h];
-        ch.prop = s.d[h] * (double)Ii;
-    } else if (e == 1) {  // SAMPLING (:2392)
-        ch.type = EV_SAMPLING;
-        ch.i_dec = cell;
-        ch.s_inc = p * S + s.g[h];
-        ch.prop = s.sr[h] * (double)Ii * s.sm[p];
-    } else if (e < 2 + 3 * D.U) {  // MUTATION (:2400-2401)
-        int uk = e - 2, u = uk / 3, k = uk - u * 3;
-        ch.type = EV_MUTATION;
-        ch.i_dec = cell;
-        ch.i_inc = ch.i_chk = p * H + mutate_hap(h, u, k, D.U);
-        ch.prop = s.q[h * D.U * 3 + uk] * (double)Ii;
-    } else {  // TRANSMISSION (:2410-2414)
-        int sn = e - 2 - 3 * D.U;
-        ch.type = EV_BIRTH;
-        ch.i_inc = ch.i_chk = cell;
-        ch.s_dec = p * S + sn;
-        if (Ii != 0) ch.prop = s.b[h] * s.sigT[sn * H + h] * s.c[p] * (double)s.Sx[p * S + sn] * (double)Ii;
-    }
+    int h = r2 / D.E;
+    l = r2 - h * D.E;
+    owner = p * H + h;
+    cell_channel(p, h, l, D, s, eff, ch);
 }
 
 __device__ __forceinline__ double block_min(double v, double *red) {
@@ -151,16 +207,47 @@ __device__ __forceinline__ double block_min(double v, double *red) {
     return v;
 }
 
+// Rebuild the infectious-cell list, the per-haplotype presence counts and the per-deme totals of buffer
+// `nb` from s.I (the buffer must have been zeroed and the zeroing made visible by a barrier).
+__device__ __forceinline__ void list_cell(const Dims &D, const TauShared &s, int nb, int i, int v) {
+    if (v != 0) {
+        int pos = atomicAdd(&s.flags[8 + nb], 1);
+        s.act[nb][pos] = i;
+        atomicAdd(&s.colcnt[nb][i & (D.H - 1)], 1);
+        atomicAdd(&s.tot[nb][i >> D.hshift], v);
+    }
+}
+
+__device__ __forceinline__ void zero_lists(const Dims &D, const TauShared &s, int nb) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < D.H; i += nt) s.colcnt[nb][i] = 0;
+    for (int i = tid; i < D.K; i += nt) s.tot[nb][i] = 0;
+    if (tid == 0) s.flags[8 + nb] = 0;
+}
+
+__device__ void rebuild_lists(const Dims &D, const TauShared &s, int nb) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    __syncthreads();
+    zero_lists(D, s, nb);
+    __syncthreads();
+    for (int i = tid; i < D.K * D.H; i += nt) list_cell(D, s, nb, i, s.I[i]);
+    __syncthreads();
+}
+
 // F, drifts and tau of the current shared-memory state (steps 1-2).  Returns tau (uniform).
-__device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double *eff) {
+// cb = which list buffer describes the current state.
+__device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double *eff, int cb) {
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const int *colcnt = s.colcnt[cb];
     for (int i = tid; i < K * H; i += nt) {
         int tp = i >> D.hshift, h = i & (H - 1);
         double acc = 0.0;
-        for (int sp = 0; sp < K; sp++) {
-            int Ii = s.I[sp * H + h];
-            if (sp != tp && Ii != 0) acc += eff[tp * K + sp] * s.mdiag[sp] * (s.b[h] * (double)Ii);
+        if (colcnt[h] != 0) {
+            for (int sp = 0; sp < K; sp++) {
+                int Ii = s.I[sp * H + h];
+                if (sp != tp && Ii != 0) acc += eff[tp * K + sp] * s.mdiag[sp] * (s.b[h] * (double)Ii);
+            }
         }
         s.F[i] = acc;
     }
@@ -179,8 +266,11 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
             for (int a = 0; a < 4; a++) {
                 if (a == hu) continue;
                 int src = h + ((a - hu) << sh);
-                int k = hu - (hu > a ? 1 : 0);
-                v += s.q[(src * U + u) * 3 + k] * (double)s.I[p * H + src];
+                int Is = s.I[p * H + src];
+                if (Is != 0) {
+                    int k = hu - (hu > a ? 1 : 0);
+                    v += s.q[(src * U + u) * 3 + k] * (double)Is;
+                }
             }
         }
         s.dI[i] = v;
@@ -190,29 +280,41 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
             tmin = fmin(tmin, t);
         }
     }
-    for (int i = tid; i < K * S; i += nt) {
+    // susceptible drifts: one warp per (deme, group), lanes over haplotypes, fixed-order butterfly reduction
+    for (int i = tid >> 5; i < K * S; i += nt >> 5) {
         int p = i / S, sn = i - p * S;
         double part = 0.0, rec = 0.0;
-        for (int h = 0; h < H; h++) {
-            double Ii = (double)s.I[p * H + h];
-            part += s.sigT[sn * H + h] * (s.F[p * H + h] + s.c[p] * s.b[h] * Ii);
-            if (s.g[h] == sn) rec += (s.d[h] + s.sr[h] * s.sm[p]) * Ii;
+        for (int h = tid & 31; h < H; h += 32) {
+            int In = s.I[p * H + h];
+            double Fv = s.F[p * H + h];
+            if (In != 0 || Fv != 0.0) {
+                double Ii = (double)In;
+                part += s.sigT[sn * H + h] * (Fv + s.c[p] * s.b[h] * Ii);
+                if (s.g[h] == sn) rec += (s.d[h] + s.sr[h] * s.sm[p]) * Ii;
+            }
         }
-        double v = -(double)s.Sx[i] * part + rec;
-        for (int s2 = 0; s2 < S; s2++)
-            if (s2 != sn) v += s.T[s2 * S + sn] * (double)s.Sx[p * S + s2] - s.T[sn * S + s2] * (double)s.Sx[i];
-        s.dS[i] = v;
-        if (fabs(v) >= 1e-8) {
-            double x = (double)(eps * (float)s.Sx[i]) / 2.0;
-            double t = (1.0 > x ? 1.0 : x) / fabs(v);
-            tmin = fmin(tmin, t);
+        for (int o = 16; o > 0; o >>= 1) {
+            part += __shfl_xor_sync(0xffffffffu, part, o);
+            rec += __shfl_xor_sync(0xffffffffu, rec, o);
+        }
+        if ((tid & 31) == 0) {
+            double v = -(double)s.Sx[i] * part + rec;
+            for (int s2 = 0; s2 < S; s2++)
+                if (s2 != sn) v += s.T[s2 * S + sn] * (double)s.Sx[p * S + s2] - s.T[sn * S + s2] * (double)s.Sx[i];
+            s.dS[i] = v;
+            if (fabs(v) >= 1e-8) {
+                double x = (double)(eps * (float)s.Sx[i]) / 2.0;
+                double t = (1.0 > x ? 1.0 : x) / fabs(v);
+                tmin = fmin(tmin, t);
+            }
         }
     }
     return block_min(tmin, s.red);
 }
 
-// Load the parameter point and replicate state into shared memory.
-__device__ void load_replicate(const DevState &st, int r, const Dims &D, TauShared &s, const double *pp) {
+// Load the parameter point and replicate state into shared memory (lists of buffer 0 are built).
+__device__ void load_replicate(const DevState &st, int r, const Dims &D, const TauShared &s, const double *pp,
+                               const double *eff_g) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     for (int i = tid; i < H; i += nt) {
@@ -229,11 +331,15 @@ __device__ void load_replicate(const DevState &st, int r, const Dims &D, TauShar
         s.sm[i] = pp[D.o_sm + i];
         s.mdiag[i] = pp[D.o_m + i * K + i];
         s.sizeD[i] = pp[D.o_size + i];
+        s.startN[i] = pp[D.o_startN + i];
+        s.endN[i] = pp[D.o_endN + i];
         s.cd[i] = st.cd[(size_t)r * K + i];
         s.c[i] = st.ceff[(size_t)r * K + i];
         s.maxEBM[i] = st.maxEBM[(size_t)r * K + i];
         s.lock[i] = st.lock[(size_t)r * K + i];
     }
+    if (s.has_effS)
+        for (int i = tid; i < K * K; i += nt) s.effS[i] = eff_g[i];
     int ovf = 0;
     for (int i = tid; i < K * H; i += nt) {
         long long v = st.I[(size_t)r * K * H + i];
@@ -245,81 +351,104 @@ __device__ void load_replicate(const DevState &st, int r, const Dims &D, TauShar
         if (v > 2147483647LL || v < 0) ovf = 1;
         s.Sx[i] = (int)v;
     }
-    if (tid < 8) s.flags[tid] = 0;
+    if (tid < 16) s.flags[tid] = 0;
+    if (tid < 6) s.tally64[tid] = 0;
     __syncthreads();
-    if (ovf) atomicOr(&s.flags[3], 1);
-    __syncthreads();
+    if (ovf) atomicOr(&s.flags[7], 1);
+    rebuild_lists(D, s, 0);
 }
 
-__device__ __forceinline__ long long block_sum_ll(long long v, double *red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    long long *r64 = reinterpret_cast<long long *>(red);
-    int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) r64[w] = v;
-    __syncthreads();
-    v = 0;
-    for (int i = 0; i < nw; i++) v += r64[i];
-    __syncthreads();
-    return v;
-}
-
-// per-deme infectious totals into s.tot[]; returns (uniformly) whether anyone is infectious
-__device__ __forceinline__ int deme_totals(const Dims &D, const TauShared &s) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    int any_inf = 0;
-    for (int p = tid >> 5; p < D.K; p += nt >> 5) {
-        int tot = 0;
-        for (int h = tid & 31; h < D.H; h += 32) tot += s.I[p * D.H + h];
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (tot != 0) any_inf = 1;
-        if ((tid & 31) == 0) s.tot[p] = tot;
-    }
-    return __syncthreads_or(any_inf);
-}
-
-// CheckLockdown for every deme (:2328-2329 / :449-450 / :736-737) by thread 0, then the rate refresh
+// CheckLockdown for every deme (:2328-2329 / :449-450 / :736-737).  All threads vote whether any deme
+// crosses a threshold; only then thread 0 runs the sequential reference pass and the CTA refreshes the
+// contact-density dependent rates.  Ends with a barrier only when something flipped.
 __device__ __forceinline__ void lockdown_pass(const DevState &st, int r, const Dims &D, const TauShared &s,
-                                              const double *pp, double *eff, double now) {
+                                              const double *pp, double *eff_g, double now, const int *tot) {
+    int pred = 0;
+    for (int p = threadIdx.x; p < D.K; p += blockDim.x) {
+        double ti = (double)tot[p];
+        if ((ti > s.startN[p] && s.lock[p] == 0) || (ti < s.endN[p] && s.lock[p] == 1)) pred = 1;
+    }
+    if (!__syncthreads_or(pred)) return;
     if (threadIdx.x == 0) {
         int flips = 0;
         for (int p = 0; p < D.K; p++)
-            flips += check_lockdown(D, pp, p, (long long)s.tot[p], s.cd, s.lock, now, &st.loc_n[r],
+            flips += check_lockdown(D, pp, p, (long long)tot[p], s.cd, s.lock, now, &st.loc_n[r],
                                     st.loc_sp + (size_t)r * st.loc_cap, st.loc_t + (size_t)r * st.loc_cap, st.loc_cap,
                                     &st.err[r]);
-        s.flags[2] = flips;
-        s.flags[5] += flips;
+        s.flags[6] = flips;
+        s.flags[10] += flips;
     }
     __syncthreads();
-    if (s.flags[2]) update_contact_rates(BlockGroup(), D, pp, s.cd, eff, s.c, s.maxEBM);
+    if (s.flags[6]) {
+        update_contact_rates(BlockGroup(), D, pp, s.cd, eff_g, s.c, s.maxEBM);
+        if (s.has_effS) {
+            for (int i = threadIdx.x; i < D.K * D.K; i += blockDim.x) s.effS[i] = eff_g[i];
+            __syncthreads();
+        }
+    }
 }
 
-__global__ void __launch_bounds__(256) tau_kernel(DevState st, SimArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Dims D = st.D;
+struct LeapTally {
+    int B, Dd, Sm, M, I, G;
+};
+
+// book n events of channel ch into the shared-memory deltas and the per-thread tallies
+__device__ __forceinline__ void book(const Channel &ch, int n, const TauShared &s, LeapTally &t) {
+    if (ch.i_dec >= 0) {
+        atomicSub(&s.chkI[ch.i_dec], n);
+        atomicSub(&s.updI[ch.i_dec], n);
+    }
+    if (ch.i_inc >= 0) {
+        atomicAdd(&s.updI[ch.i_inc], n);
+        atomicAdd(&s.chkI[ch.i_chk], n);
+    }
+    if (ch.s_dec >= 0) atomicSub(&s.dSx[ch.s_dec], n);
+    if (ch.s_inc >= 0) atomicAdd(&s.dSx[ch.s_inc], n);
+    if (ch.type == EV_MIGRATION) t.G += n;
+    else if (ch.type == EV_BIRTH) t.B += n;
+    else if (ch.type == EV_DEATH) t.Dd += n;
+    else if (ch.type == EV_SAMPLING) t.Sm += n;
+    else if (ch.type == EV_MUTATION) t.M += n;
+    else t.I += n;
+}
+
+// clear everything a (re)draw of the leap accumulates into: the dense row, the deltas, the type tallies
+__device__ __forceinline__ void wipe_leap(const Dims &D, const TauShared &s, int *row) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < D.Pp / 4; i += nt) reinterpret_cast<int4 *>(row)[i] = make_int4(0, 0, 0, 0);
+    for (int i = tid; i < D.K * D.H; i += nt) {
+        s.chkI[i] = 0;
+        s.updI[i] = 0;
+    }
+    for (int i = tid; i < D.K * D.S; i += nt) s.dSx[i] = 0;
+    if (tid < 6) s.flags[tid] = 0;
+}
+
+template <bool DENSE>
+__global__ void __launch_bounds__(256, 2) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
+                                                     const __grid_constant__ TauShared s) {
+    const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S;
     const int tid = threadIdx.x, nt = blockDim.x;
-    TauShared s;
-    carve(s, D, smem_raw);
+    const int LC = D.E + (K - 1) * S;                     // channels owned by one infectious cell
+    const int G1 = (LC + 3) >> 2, G2 = (D.SS1 + 3) >> 2;  // Philox groups per cell / per deme (SUSCCHANGE)
+    const int GS = G1 > G2 ? G1 : G2;
 
     for (int r = blockIdx.x; r < st.R; r += gridDim.x) {
         const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
-        double *eff = st.eff + (size_t)r * K * K;
+        double *eff_g = st.eff + (size_t)r * K * K;
         long long *ctr = st.counters + (size_t)r * NCOUNT;
         const uint64_t seed = st.seeds[r];
         const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
         __syncthreads();
-        load_replicate(st, r, D, s, pp);
-        if (s.flags[3]) {
+        load_replicate(st, r, D, s, pp, eff_g);
+        const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
+        if (s.flags[7]) {
             if (tid == 0) st.err[r] |= ERR_COUNT_OVERFLOW;
             continue;
         }
-
-        // per-thread event-type tallies; reduced into the global counters at the end of the run
-        long long accB = 0, accD = 0, accS = 0, accM = 0, accI = 0, accG = 0;
-        long long base[6];
-#pragma unroll
-        for (int j = 0; j < 6; j++) base[j] = ctr[j];  // C_B..C_MIGP carried over from earlier calls
+        int cb = 0;          // list buffer describing the current state
+        bool restarted = false;
         long long sC = ctr[C_S];
         long long evptr = ctr[C_EVPTR], leaps = ctr[C_LEAPS];
         double t = st.time[r];
@@ -327,72 +456,98 @@ __global__ void __launch_bounds__(256) tau_kernel(DevState st, SimArgs a) {
         long long good_attempt = ctr[C_GOOD];
         const long long ev_limit = evptr + a.iterations;  // events.ptr < events.size (:2312), intended capacity
         int *tau_counts = st.tau_counts + (size_t)r * st.leap_cap * D.Pp;
-        double *tau_tt = st.tau_tt + (size_t)r * st.leap_cap * 2;
-        double *ev_time = st.ev_time + (size_t)r * st.ev_cap;
-        unsigned long long *ev_desc = st.ev_desc + (size_t)r * st.ev_cap;
 
         for (long long attempt = 0; attempt < a.attempts; attempt++) {
             epoch++;
-            int any_inf = deme_totals(D, s);
-            if (any_inf) {
+            if (s.flags[8 + cb] != 0) {
                 while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
                        (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
-                    double tau = drifts_and_tau(D, s, eff);
-                    long long trB, trD, trS, trM, trI, trG;
                     int *row = tau_counts + (size_t)leaps * D.Pp;
-                    // ---- draw all channels; halve tau and redraw on an infeasible leap (:2316-2321)
+                    const int nb = cb ^ 1;
+                    // ---- 0. zero-fill the dense row; clear the per-leap deltas and the next list buffer
+                    wipe_leap(D, s, row);
+                    zero_lists(D, s, nb);
+                    // ---- 1-2. drifts and tau (its barriers also order the zero-fill before the scatter below)
+                    double tau = drifts_and_tau(D, s, eff, cb);
+                    const int nAct = s.flags[8 + cb];
+                    const int *act = s.act[cb];
+                    // ---- 3. draw; halve tau and redraw on an infeasible leap (:2316-2321)
                     for (unsigned retry = 0;; retry++) {
-                        for (int i = tid; i < K * H; i += nt) {
-                            s.chkI[i] = 0;
-                            s.updI[i] = 0;
-                        }
-                        for (int i = tid; i < K * S; i += nt) s.dSx[i] = 0;
-                        __syncthreads();
-                        trB = trD = trS = trM = trI = trG = 0;
+                        LeapTally tr;
+                        tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
                         PhiloxCtx ctx;
                         ctx.key = key;
                         ctx.c1 = (uint32_t)leaps;
                         ctx.c2 = (retry & 0xffu) | (epoch << 8);
-                        for (int chunk = tid; chunk < D.Pp / 4; chunk += nt) {
-                            ctx.c0 = (uint32_t)chunk;
-                            int n4[4];
-                            uint4 w = make_uint4(0, 0, 0, 0);
-                            bool have_w = false;
-#pragma unroll
-                            for (int j = 0; j < 4; j++) {
+                        ctx.dstride = (uint32_t)GS;
+                        if (DENSE) {
+                            for (int c = tid; c < D.P; c += nt) {
                                 Channel ch;
-                                decode_channel(chunk * 4 + j, D, s, eff, ch);
+                                int owner, l;
+                                decode_channel(c, D, s, eff, ch, owner, l);
                                 double lam = ch.prop * tau;
-                                int n = 0;
                                 if (lam > 0.0) {
-                                    if (!have_w) {
-                                        w = ctx.draw(0u);
-                                        have_w = true;
+                                    ctx.c0 = (uint32_t)owner;
+                                    ctx.dom0 = (uint32_t)(l >> 2);
+                                    uint4 w = ctx.draw(0u);
+                                    int n = (int)poisson_draw(lam, pick_word(w, l & 3), ctx, l & 3);
+                                    if (n != 0) {
+                                        row[c] = n;
+                                        book(ch, n, s, tr);
                                     }
-                                    n = (int)poisson_draw(lam, pick_word(w, j), ctx, j);
-                                }
-                                n4[j] = n;
-                                if (n != 0) {
-                                    if (ch.i_dec >= 0) {
-                                        atomicSub(&s.chkI[ch.i_dec], n);
-                                        atomicSub(&s.updI[ch.i_dec], n);
-                                    }
-                                    if (ch.i_inc >= 0) {
-                                        atomicAdd(&s.updI[ch.i_inc], n);
-                                        atomicAdd(&s.chkI[ch.i_chk], n);
-                                    }
-                                    if (ch.s_dec >= 0) atomicSub(&s.dSx[ch.s_dec], n);
-                                    if (ch.s_inc >= 0) atomicAdd(&s.dSx[ch.s_inc], n);
-                                    if (ch.type == EV_MIGRATION) trG += n;
-                                    else if (ch.type == EV_BIRTH) trB += n;
-                                    else if (ch.type == EV_DEATH) trD += n;
-                                    else if (ch.type == EV_SAMPLING) trS += n;
-                                    else if (ch.type == EV_MUTATION) trM += n;
-                                    else trI += n;
                                 }
                             }
-                            reinterpret_cast<int4 *>(row)[chunk] = make_int4(n4[0], n4[1], n4[2], n4[3]);
+                        } else {
+                            const int n1 = nAct * G1, nItems = n1 + K * G2;
+                            for (int item = tid; item < nItems; item += nt) {
+                                int p, h = 0, j, lim;
+                                const bool is_cell = item < n1;
+                                if (is_cell) {
+                                    int ai = item / G1;
+                                    j = item - ai * G1;
+                                    int cell = act[ai];
+                                    p = cell >> D.hshift;
+                                    h = cell & (H - 1);
+                                    ctx.c0 = (uint32_t)cell;
+                                    lim = LC;
+                                } else {
+                                    int it = item - n1;
+                                    p = it / G2;
+                                    j = it - p * G2;
+                                    ctx.c0 = (uint32_t)(K * H + p);
+                                    lim = D.SS1;
+                                }
+                                ctx.dom0 = (uint32_t)j;
+                                uint4 w = make_uint4(0, 0, 0, 0);
+                                bool have_w = false;
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    int l = j * 4 + q;
+                                    if (l < lim) {
+                                        Channel ch;
+                                        int c = is_cell ? cell_channel(p, h, l, D, s, eff, ch) : susc_channel(p, l, D, s, ch);
+                                        double lam = ch.prop * tau;
+                                        if (lam > 0.0) {
+                                            if (!have_w) {
+                                                w = ctx.draw(0u);
+                                                have_w = true;
+                                            }
+                                            int n = (int)poisson_draw(lam, pick_word(w, q), ctx, q);
+                                            if (n != 0) {
+                                                row[c] = n;
+                                                book(ch, n, s, tr);
+                                            }
+                                        }
+                                    }
+                                }
+                            }
                         }
+                        if (tr.B) atomicAdd(&s.flags[EV_BIRTH], tr.B);
+                        if (tr.Dd) atomicAdd(&s.flags[EV_DEATH], tr.Dd);
+                        if (tr.Sm) atomicAdd(&s.flags[EV_SAMPLING], tr.Sm);
+                        if (tr.M) atomicAdd(&s.flags[EV_MUTATION], tr.M);
+                        if (tr.I) atomicAdd(&s.flags[EV_SUSCCHANGE], tr.I);
+                        if (tr.G) atomicAdd(&s.flags[EV_MIGRATION], tr.G);
                         __syncthreads();
                         // feasibility (:2522-2528)
                         int bad = 0;
@@ -407,25 +562,33 @@ __global__ void __launch_bounds__(256) tau_kernel(DevState st, SimArgs a) {
                         bad = __syncthreads_or(bad);
                         if (!bad) break;
                         tau *= 0.5;
+                        wipe_leap(D, s, row);  // rare path
+                        __syncthreads();
                     }
-                    // ---- apply (UpdateCompartmentCounts_tau, :2536-2593)
-                    for (int i = tid; i < K * H; i += nt) s.I[i] += s.updI[i];
+                    // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) and rebuild the cell list
+                    for (int i = tid; i < K * H; i += nt) {
+                        int v = s.I[i] + s.updI[i];
+                        s.I[i] = v;
+                        list_cell(D, s, nb, i, v);
+                    }
                     for (int i = tid; i < K * S; i += nt) s.Sx[i] += s.dSx[i];
-                    accB += trB; accD += trD; accS += trS; accM += trM; accI += trI; accG += trG;
                     t += tau;
-                    sC += block_sum_ll(trS, s.red);  // sCounter gates the loop (:2312), so it is kept exact per leap
+                    sC += s.flags[EV_SAMPLING];  // sCounter gates the loop (:2312): exact per leap
+                    if (tid < 6) s.tally64[tid] += s.flags[tid];
                     if (tid == 0) {
-                        tau_tt[leaps * 2] = t;
-                        tau_tt[leaps * 2 + 1] = tau;
-                        ev_time[evptr] = t;
-                        ev_desc[evptr] = pack_multi((uint32_t)leaps);
+                        double *tau_tt = st.tau_tt + ((size_t)r * st.leap_cap + leaps) * 2;
+                        tau_tt[0] = t;
+                        tau_tt[1] = tau;
+                        st.ev_time[(size_t)r * st.ev_cap + evptr] = t;
+                        st.ev_desc[(size_t)r * st.ev_cap + evptr] = pack_multi((uint32_t)leaps);
                     }
                     leaps++;
                     evptr++;
+                    cb = nb;
+                    __syncthreads();
                     // ---- extinction test and CheckLockdown for every deme (:2326-2329)
-                    any_inf = deme_totals(D, s);
-                    if (!any_inf) break;
-                    lockdown_pass(st, r, D, s, pp, eff, t);
+                    if (s.flags[8 + cb] == 0) break;
+                    lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot[cb]);
                 }
             }
             // ---- extinction-retry (:2331-2335): <= 100 log rows with iterations > 100 => Restart (:714-738)
@@ -434,15 +597,14 @@ __global__ void __launch_bounds__(256) tau_kernel(DevState st, SimArgs a) {
                 leaps = 0;
                 sC = 0;
                 t = 0.0;
-                accB = accD = accS = accM = accI = accG = 0;
-#pragma unroll
-                for (int j = 0; j < 6; j++) base[j] = 0;
+                restarted = true;
                 __syncthreads();
+                if (tid < 6) s.tally64[tid] = 0;
                 for (int i = tid; i < K * H; i += nt) s.I[i] = (int)st.initI[(size_t)r * K * H + i];
                 for (int i = tid; i < K * S; i += nt) s.Sx[i] = (int)st.initSx[(size_t)r * K * S + i];
+                rebuild_lists(D, s, cb);
+                lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot[cb]);
                 __syncthreads();
-                deme_totals(D, s);
-                lockdown_pass(st, r, D, s, pp, eff, t);
                 good_attempt = 0;
                 if (tid == 0) ctr[C_MIGN] = 0;
             } else {
@@ -461,25 +623,18 @@ __global__ void __launch_bounds__(256) tau_kernel(DevState st, SimArgs a) {
             st.maxEBM[(size_t)r * K + i] = s.maxEBM[i];
             st.lock[(size_t)r * K + i] = s.lock[i];
         }
-        long long ginf = 0;
-        for (int i = tid; i < K * H; i += nt) ginf += s.I[i];
-        ginf = block_sum_ll(ginf, s.red);
-        accB = block_sum_ll(accB, s.red);
-        accD = block_sum_ll(accD, s.red);
-        accM = block_sum_ll(accM, s.red);
-        accI = block_sum_ll(accI, s.red);
-        accG = block_sum_ll(accG, s.red);
         if (tid == 0) {
-            ctr[C_B] = base[C_B] + accB;
-            ctr[C_D] = base[C_D] + accD;
+            // counters carried over from earlier calls unless a Restart wiped them (:714-738)
+            static_assert(C_B == EV_BIRTH && C_D == EV_DEATH && C_S == EV_SAMPLING && C_M == EV_MUTATION &&
+                          C_I == EV_SUSCCHANGE && C_MIGP == EV_MIGRATION, "counter order follows the event codes");
+            for (int j = 0; j < 6; j++) ctr[j] = (restarted ? 0 : ctr[j]) + s.tally64[j];
             ctr[C_S] = sC;
-            ctr[C_M] = base[C_M] + accM;
-            ctr[C_I] = base[C_I] + accI;
-            ctr[C_MIGP] = base[C_MIGP] + accG;
-            ctr[C_SWAP] += s.flags[5];
+            ctr[C_SWAP] += s.flags[10];
             ctr[C_GOOD] = good_attempt;
             ctr[C_EVPTR] = evptr;
             ctr[C_LEAPS] = leaps;
+            long long ginf = 0;
+            for (int p = 0; p < K; p++) ginf += s.tot[cb][p];
             ctr[C_GINF] = ginf;
             st.time[r] = t;
             st.epoch[r] = epoch;
@@ -489,19 +644,19 @@ __global__ void __launch_bounds__(256) tau_kernel(DevState st, SimArgs a) {
 }
 
 // Deterministic parity tap: propensities of the current state in positional order, drifts and tau.
-__global__ void __launch_bounds__(256) propensity_kernel(DevState st, int r, double *out, double *dI, double *dS,
-                                                         double *tau_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const Dims D = st.D;
-    TauShared s;
-    carve(s, D, smem_raw);
+__global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__ DevState st,
+                                                         const __grid_constant__ TauShared s, int r, double *out,
+                                                         double *dI, double *dS, double *tau_out) {
+    const Dims &D = st.D;
     const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
-    const double *eff = st.eff + (size_t)r * D.K * D.K;
-    load_replicate(st, r, D, s, pp);
-    double tau = drifts_and_tau(D, s, eff);
+    const double *eff_g = st.eff + (size_t)r * D.K * D.K;
+    load_replicate(st, r, D, s, pp, eff_g);
+    const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
+    double tau = drifts_and_tau(D, s, eff, 0);
     for (int c = threadIdx.x; c < D.P; c += blockDim.x) {
         Channel ch;
-        decode_channel(c, D, s, eff, ch);
+        int owner, l;
+        decode_channel(c, D, s, eff, ch, owner, l);
         out[c] = ch.prop;
     }
     for (int i = threadIdx.x; i < D.K * D.H; i += blockDim.x) dI[i] = s.dI[i];
@@ -510,26 +665,33 @@ __global__ void __launch_bounds__(256) propensity_kernel(DevState st, int r, dou
 }
 
 // host launchers ---------------------------------------------------------------------------------
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms) {
-    size_t smem = tau_smem_bytes(st.D);
-    cudaError_t e = cudaFuncSetAttribute(tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool DENSE>
+static cudaError_t launch_tau_variant(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms) {
+    const TauShared lay = tau_layout(st.D);
+    size_t smem = (size_t)lay.bytes;
+    cudaError_t e = cudaFuncSetAttribute(tau_kernel<DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel<DENSE>, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     int grid = num_sms * per_sm;
     if (grid > st.R) grid = st.R;
-    tau_kernel<<<grid, 256, smem, stream>>>(st, a);
+    tau_kernel<DENSE><<<grid, 256, smem, stream>>>(st, a, lay);
     return cudaGetLastError();
+}
+
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
+    return variant == 1 ? launch_tau_variant<true>(st, a, stream, num_sms) : launch_tau_variant<false>(st, a, stream, num_sms);
 }
 
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream) {
-    size_t smem = tau_smem_bytes(st.D);
+    const TauShared lay = tau_layout(st.D);
+    size_t smem = (size_t)lay.bytes;
     cudaError_t e = cudaFuncSetAttribute(propensity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    propensity_kernel<<<1, 256, smem, stream>>>(st, r, out, dI, dS, tau);
+    propensity_kernel<<<1, 256, smem, stream>>>(st, lay, r, out, dI, dS, tau);
     return cudaGetLastError();
 }
 
