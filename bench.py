@@ -42,6 +42,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 T_WARM = 60.0
 SEED0 = 1000
 WORKLOAD = "T3 tau-leap: 3 sites (64 haplotypes) x 10 demes x 3 susceptibility groups, 1e6/deme"
+CPU_SAMPLE_TIMEOUT = 180.0   # wall seconds allowed for one bounded CPU sample (all workers)
 EVENT_KEYS = ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus")
 
 
@@ -139,8 +140,13 @@ def run_cpu_sample(scenario, leaps, reps_per_worker, seed_base):
                str(reps_per_worker), str(leaps), scenario]
         procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
     outs = []
+    deadline = time.perf_counter() + CPU_SAMPLE_TIMEOUT
     for p in procs:
-        out, _ = p.communicate()
+        try:
+            out, _ = p.communicate(timeout=max(1.0, deadline - time.perf_counter()))
+        except subprocess.TimeoutExpired:  # a stuck worker must not stall the bench: drop it, keep the others
+            p.kill()
+            out, _ = p.communicate()
         for line in out.splitlines():
             if line.startswith("{"):
                 outs.append(json.loads(line))
@@ -261,7 +267,7 @@ def gpu_arm(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from scenarios import SCENARIOS
-    from vgsim_b200 import _capi
+    from vgsim_b200 import _capi, _shard
     from vgsim_b200._engine import BirthDeathModel as Eng
 
     if not torch.cuda.is_available():
@@ -273,7 +279,8 @@ def gpu_arm(args, rank, world, local_rank):
 
     R, L = args.replicates, args.leaps
     (U, K, S), setup = SCENARIOS[args.scenario]
-    seed_base = SEED0 + rank * R
+    lo, hi = _shard.replicate_range(rank, world, world * R)   # weak scaling: R replicates per GPU
+    seed_base = SEED0 + lo
     eng = Eng(U, K, S, seed_base, False, False, int(1e6), 0.0, replicates=R, device=local_rank)
     setup(eng)
     h = eng._sync_params()
@@ -303,7 +310,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     def seeds_for(step):
         # fresh Philox keys per step and per replicate, disjoint across ranks
-        s = np.uint64(SEED0) + np.uint64(1 << 32) * np.uint64(step + 1) + np.arange(R, dtype=np.uint64) + np.uint64(rank * R)
+        s = _shard.replicate_seeds(SEED0, lo, hi, batch=step + 1)
         seeds_pinned.numpy()[:] = s.view(np.int64)
         return seeds_pinned.numpy().view(np.uint64)
 
@@ -375,8 +382,8 @@ def gpu_arm(args, rank, world, local_rank):
     summ = torch.as_tensor(_DevArray(sptr, (R, _capi.NSUMMARY), "<f8"), device=dev)
     stream.synchronize()
     if world > 1:
-        gathered = torch.empty((world * R, _capi.NSUMMARY), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(gathered, summ.clone())
+        gathered = _shard.gather_summaries(summ.clone(), world)
+        assert gathered.shape == (world * R, _capi.NSUMMARY)
         t = torch.tensor([ms, ms_e2e, float(events), float(leaps), float(ev_e2e), float(launches), float(err),
                           sum(kernel_ms)], dtype=torch.float64, device=dev)
         tmax = t.clone()
@@ -449,6 +456,10 @@ def gpu_arm(args, rank, world, local_rank):
 
 def main():
     args = parse_args()
+    wd = float(os.environ.get("VGSIM_BENCH_WATCHDOG", "0") or 0)
+    if wd > 0:  # diagnostics: dump every thread's Python stack to stderr if the run is still going after wd seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, repeat=True, file=sys.stderr)
     if args.cpu_worker:
         seed, reps, leaps, scenario = args.cpu_worker
         cpu_worker(int(seed), int(reps), int(leaps), scenario)

@@ -156,16 +156,21 @@ int vgsim_get_migrations(vgsim_handle h, int replicate, int64_t *node, double *t
                          int64_t *new_pop);
 
 /* Fixed-size per-replicate summary vector (device-resident; what the multi-GPU all-gather moves):
- * counters, final time, and tree statistics when a genealogy exists.  out[R][VGSIM_NSUMMARY] f64.
+ * counters, final time, and tree statistics when a genealogy exists.  out[R][VGSIM_NSUMMARY] f64:
+ *   [0..11] the VGSIM_NCOUNTERS counters, [12] current time, [13] tree nodes (2n-1), [14] tree height,
+ *   [15] total branch length, [16] roots (1 = fully coalesced), [17] mutation rows, [18] migration rows,
+ *   [19] root time, [20] cherries, [21] Sackin index (sum of leaf depths), [22..23] reserved.
  * vgsim_summaries_dev returns the DEVICE pointer of the same buffer (valid until destroy). */
 #define VGSIM_NSUMMARY 24
 int vgsim_summaries(vgsim_handle h, double *out);
 int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr);
 
-/* Parity tap: variant 1 makes vgsim_simulate_tau walk all P channels of every leap instead of the
- * compact infectious-cell list (variant 0, the default).  Both address the Philox stream by
- * (cell, channel-within-cell), so their logs are bit-identical; tests use it to prove that skipping
- * zero-propensity channels changes nothing (numpy's random_poisson(0) consumes no randomness either). */
+/* Parity tap.  Variant 0 (default, product): per infectious cell the kernel draws ONE Poisson for the total of
+ * its mutation channels and ONE for the total of its out-migration channels whenever that total's lambda is
+ * <= 2, and splits a non-zero total multinomially over the group's channels (independent Poissons
+ * conditioned on their sum are multinomial, so the joint distribution is unchanged).  Variant 1 draws every
+ * channel separately, exactly like the reference's GenerateEvents_tau (src/_BirthDeath.pyx:2454-2532);
+ * tests compare both with theory and with each other. */
 int vgsim_set_tau_variant(vgsim_handle h, int variant);
 
 /* Launch accounting: kernels launched by this handle since creation. */

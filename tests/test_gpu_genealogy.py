@@ -119,3 +119,70 @@ def test_philox_genealogy_is_a_valid_tree():
         assert np.all(times[nz] >= times[tree[nz]])  # children are younger (later) than parents
     s = h.summaries()
     assert np.all(s[:, 16] == 1) and np.all(s[:, 13] == 2 * c["sCounter"] - 1)
+
+
+def tree_shape_stats(tree, times):
+    """Host restatement of the summary kernel's tree statistics (numpy): height, total branch length,
+    cherries, Sackin index."""
+    n = len(tree)
+    nz = tree >= 0
+    kids = np.bincount(tree[nz], minlength=n)
+    leaf = kids == 0
+    leaf_kids = np.bincount(tree[nz & leaf], minlength=n)
+    cherries = int((leaf_kids == 2).sum())
+    depth = np.zeros(n, np.int64)
+    for i in range(n - 1, -1, -1):  # parents have larger ids than their children
+        if tree[i] >= 0:
+            depth[i] = depth[tree[i]] + 1
+    return (times.max() - times.min(), float((times[nz] - times[tree[nz]]).sum()), cherries, int(depth[leaf].sum()))
+
+
+def test_summary_tree_statistics_match_host():
+    e = make_engine("s9", 42, replicates=40)
+    e.SimulatePopulation(20000, 20000, -1, 200)
+    e.GetGenealogy(None)
+    h = e._handle
+    s = h.summaries()
+    for r in range(0, 40, 3):
+        tree, pop, times = h.get_tree(r)
+        height, bl, cherries, sackin = tree_shape_stats(tree, times)
+        assert s[r, 20] == cherries and s[r, 21] == sackin
+        assert s[r, 14] == height
+        assert abs(s[r, 15] - bl) <= 1e-9 * bl
+
+
+@pytest.mark.parametrize("name", ["s1", "s5", "s9"])
+def test_tree_statistics_distribution_matches_oracle(name):
+    """Config 2 of BASELINE.json on the genealogy side: forward direct run + genealogy per replicate, device
+    (Philox) vs oracle == reference algorithm (PCG64); KS at alpha = 0.01 (Bonferroni) on tree statistics."""
+    from test_gpu_direct import _ks_all
+    R, N = 600, 2500
+    e = make_engine(name, 7000, replicates=R)
+    e.SimulatePopulation(N, N, -1, 200)
+    e.GetGenealogy(None)
+    s = e._handle.summaries()
+    has_tree = s[:, 13] > 0          # replicates with fewer than two samples have no genealogy
+    assert has_tree.mean() > 0.9 and np.all(s[has_tree, 16] == 1)
+    s = s[has_tree]
+    keys = ["samples", "height", "branch_length", "cherries", "sackin", "mutations", "migrations", "root_time"]
+    dev = {"samples": (s[:, 13] + 1) / 2, "height": s[:, 14], "branch_length": s[:, 15], "cherries": s[:, 20],
+           "sackin": s[:, 21], "mutations": s[:, 17], "migrations": s[:, 18], "root_time": s[:, 19]}
+    ora = {k: [] for k in keys}
+    for r in range(R):
+        om = O.OracleModel.from_engine(make_engine(name, 3000 + r))
+        om.simulate(N)
+        if om.counters()["sCounter"] < 2:
+            continue
+        om.genealogy(r)
+        tree, pop, times = om.tree()
+        height, bl, cherries, sackin = tree_shape_stats(tree, times)
+        ora["samples"].append((len(tree) + 1) / 2)
+        ora["height"].append(height)
+        ora["branch_length"].append(bl)
+        ora["cherries"].append(cherries)
+        ora["sackin"].append(sackin)
+        ora["mutations"].append(len(om.mutations()[0]))
+        ora["migrations"].append(len(om.migrations()[0]))
+        ora["root_time"].append(times.min())
+    bad = _ks_all(dev, ora, keys)
+    assert not bad, bad

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvgsim_b200.so")
+# VGSIM_B200_LIB: A/B debugging of two builds of this same library (never a different implementation)
+LIB_PATH = os.environ.get("VGSIM_B200_LIB") or os.path.join(_HERE, "libvgsim_b200.so")
 
 NCOUNTERS = 12
 NSUMMARY = 24
@@ -322,7 +323,8 @@ class Handle:
         return int(lib.vgsim_launch_count(self._h))
 
     def set_tau_variant(self, variant):
-        """0 = infectious-cell list (product path), 1 = walk all P channels (parity tap, bit-identical log)."""
+        """0 = small mutation / out-migration groups drawn as one Poisson total + multinomial split (product path),
+        1 = every channel drawn separately like the reference (parity tap)."""
         _ck(lib.vgsim_set_tau_variant(self._h, int(variant)))
 
 

@@ -479,6 +479,7 @@ int vgsim_synchronize(vgsim_handle h) {
         if (all & ERR_CLAMPED) g_err += " [tau-log coalescences clamped]";
         if (all & ERR_COUNT_OVERFLOW) g_err += " [compartment count overflow]";
         if (all & ERR_BADLOG) g_err += " [bad event log]";
+        if (all & ERR_TAU_STUCK) g_err += " [tau leap infeasible after 80 halvings]";
     }
     return all;
 }
@@ -712,9 +713,11 @@ int vgsim_counters_dev(vgsim_handle h, void **counters, void **current_time) {
 
 // ---------------------------------------------------------------------------------------------------
 namespace vg {
-// per-replicate summary vector: counters, final time, tree statistics (one warp per replicate)
+// per-replicate summary vector: counters, final time, tree statistics (one warp per replicate).
+// Node ids are assigned in creation order going BACKWARD in time (reference src/_BirthDeath.pyx:743-1000),
+// so a parent's id is always larger than its children's: depths resolve in one descending sweep.
 __global__ void summary_kernel(DevState st, const long long *node_off, const int *parent, const double *time,
-                               const int *n_nodes, const int *mut_n, const int *mig_n, double *out) {
+                               const int *n_nodes, const int *mut_n, const int *mig_n, int *scratch_all, double *out) {
     const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     for (int r = blockIdx.x * wpc + (threadIdx.x >> 5); r < st.R; r += gridDim.x * wpc) {
         double *o = out + (size_t)r * VGSIM_NSUMMARY;
@@ -727,26 +730,70 @@ __global__ void summary_kernel(DevState st, const long long *node_off, const int
         if (n == 0) continue;
         const int *par = parent + node_off[r];
         const double *tm = time + node_off[r];
+        int *sc = scratch_all + node_off[r];
         double tmin = 1e300, tmax = -1e300, bl = 0.0;
-        int cherries = 0, roots = 0;
+        int roots = 0;
         for (int i = lane; i < n; i += 32) {
             double t = tm[i];
             tmin = fmin(tmin, t);
             tmax = fmax(tmax, t);
             int p = par[i];
             if (p >= 0) bl += t - tm[p]; else roots++;
+            sc[i] = 0;
         }
-        // an internal node is a cherry when both children are leaves; leaves are the nodes nobody points to.
-        // children of node v have smaller ids than v only in creation order, so count via a second pass:
-        // node i is a leaf iff no j has par[j] == i  <=>  i was created by a SAMPLING row. Leaves never get
-        // children, and internal nodes always have exactly two, so "cherry" <=> both children are leaves.
-        // (computed on the host from the gathered parent array when needed; here: roots and lengths only)
+        __syncwarp();
+        // children per node (0 = leaf, i.e. created by a SAMPLING row; internal nodes have exactly 2)
+        for (int i = lane; i < n; i += 32)
+            if (par[i] >= 0) atomicAdd(&sc[par[i]], 1);
+        __syncwarp();
+        // leaf children per node in bits 2.. : a cherry is an internal node whose two children are leaves
+        for (int i = lane; i < n; i += 32)
+            if ((sc[i] & 3) == 0 && par[i] >= 0) atomicAdd(&sc[par[i]], 4);
+        __syncwarp();
+        int cherries = 0;
+        for (int i = lane; i < n; i += 32) {
+            int v = sc[i];
+            if ((v >> 2) == 2) cherries++;
+            sc[i] = (v & 3) == 0 ? 1 : 0;  // leaf bit; depth goes to bits 1..
+        }
+        __syncwarp();
+        // depth (edges to the root) by a descending sweep, 32 nodes at a time; dependencies inside a chunk
+        // are resolved by lane-to-lane shuffles.  Sackin index = sum of leaf depths.
+        long long sackin = 0;
+        for (int hi = n; hi > 0; hi -= 32) {
+            const int lo = hi - 32;
+            const int i = lo + lane;
+            const bool live = i >= 0;
+            int p = live ? par[i] : -1;
+            int depth = 0;
+            bool done = !live || p < 0;
+            if (live && p >= hi) {
+                depth = (sc[p] >> 1) + 1;
+                done = true;
+            }
+            while (__any_sync(0xffffffffu, !done)) {
+                int src = (!done) ? p - lo : lane;
+                int pd = __shfl_sync(0xffffffffu, depth, src & 31);
+                int pdone = __shfl_sync(0xffffffffu, (int)done, src & 31);
+                if (!done && pdone) {
+                    depth = pd + 1;
+                    done = true;
+                }
+            }
+            if (live) {
+                int leaf = sc[i] & 1;
+                sc[i] = (depth << 1) | leaf;
+                if (leaf) sackin += depth;
+            }
+            __syncwarp();
+        }
         for (int o2 = 16; o2 > 0; o2 >>= 1) {
             tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o2));
             tmax = fmax(tmax, __shfl_xor_sync(0xffffffffu, tmax, o2));
             bl += __shfl_xor_sync(0xffffffffu, bl, o2);
             roots += __shfl_xor_sync(0xffffffffu, roots, o2);
             cherries += __shfl_xor_sync(0xffffffffu, cherries, o2);
+            sackin += __shfl_xor_sync(0xffffffffu, sackin, o2);
         }
         if (lane == 0) {
             o[13] = (double)n;
@@ -756,6 +803,8 @@ __global__ void summary_kernel(DevState st, const long long *node_off, const int
             o[17] = (double)mut_n[r];
             o[18] = (double)mig_n[r];
             o[19] = tmin;          // time of the root (TMRCA in absolute time)
+            o[20] = (double)cherries;
+            o[21] = (double)sackin;
         }
     }
 }
@@ -769,7 +818,7 @@ int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr) {
     int wpc = 4, grid = (h->R + wpc - 1) / wpc;
     if (grid > h->num_sms * 8) grid = h->num_sms * 8;
     summary_kernel<<<grid, wpc * 32, 0, h->stream>>>(h->st, G.valid ? G.node_off : nullptr, G.parent, G.time, G.n_nodes,
-                                                      G.mut_n, G.mig_n, h->summaries);
+                                                      G.mut_n, G.mig_n, G.scratch, h->summaries);
     h->launches++;
     CK(cudaGetLastError());
     if (dev_ptr) *dev_ptr = h->summaries;

@@ -19,6 +19,7 @@ enum {
     ERR_CLAMPED = 16,         // tau-log BIRTH record asked for more coalescences than lineages allow
     ERR_COUNT_OVERFLOW = 32,  // compartment count does not fit int32
     ERR_BADLOG = 64,
+    ERR_TAU_STUCK = 128,      // tau leap infeasible after 80 halvings (state itself violates the bounds)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -545,7 +545,7 @@ void free_gen(Handle *h) {
     GenealogyBuffers &G = h->gen;
     void *ptrs[] = {G.node_off, G.parent, G.pop, G.time, G.mut_off, G.mig_off, G.mut_n, G.mig_n, G.mut_node, G.mut_hap,
                     G.mut_nhap, G.mut_time, G.mig_node, G.mig_old, G.mig_new, G.mig_time, G.arena_off, G.arena,
-                    G.cell_hdr, G.n_nodes};
+                    G.cell_hdr, G.n_nodes, G.scratch};
     for (void *p : ptrs) gfree(h, p);
     G = GenealogyBuffers();
 }
@@ -583,13 +583,12 @@ int vgsim_genealogy(vgsim_handle h, const uint64_t *seeds, const double *uniform
         if (2 * sC + 4 * KH > 1000000000LL) return vgsim_set_error("sample count too large for int32 lineage arena");
     }
     G.total_nodes = G.h_node_off[R];
-    int *nl = nullptr;
     unsigned long long *dseeds = nullptr;
     double *dstream = nullptr;
     long long *doff = nullptr, *dused = nullptr;
     if (galloc(h, &G.node_off, R + 1) || galloc(h, &G.mut_off, R + 1) || galloc(h, &G.mig_off, R + 1) ||
         galloc(h, &G.arena_off, R + 1) || galloc(h, &G.parent, G.total_nodes) || galloc(h, &G.pop, G.total_nodes) ||
-        galloc(h, &G.time, G.total_nodes) || galloc(h, &nl, G.total_nodes) || galloc(h, &G.arena, arena_off[R]) ||
+        galloc(h, &G.time, G.total_nodes) || galloc(h, &G.scratch, G.total_nodes) || galloc(h, &G.arena, arena_off[R]) ||
         galloc(h, &G.cell_hdr, (size_t)R * KH * 3) || galloc(h, &G.n_nodes, R) || galloc(h, &G.mut_n, R) ||
         galloc(h, &G.mig_n, R) || galloc(h, &G.mut_node, G.h_mut_off[R]) || galloc(h, &G.mut_hap, G.h_mut_off[R]) ||
         galloc(h, &G.mut_nhap, G.h_mut_off[R]) || galloc(h, &G.mut_time, G.h_mut_off[R]) ||
@@ -606,7 +605,7 @@ int vgsim_genealogy(vgsim_handle h, const uint64_t *seeds, const double *uniform
     ga.parent = G.parent;
     ga.pop = G.pop;
     ga.time = G.time;
-    ga.nl = nl;
+    ga.nl = G.scratch;
     ga.arena_off = G.arena_off;
     ga.arena = G.arena;
     ga.hdr = G.cell_hdr;
@@ -648,7 +647,6 @@ int vgsim_genealogy(vgsim_handle h, const uint64_t *seeds, const double *uniform
     h->launches++;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    gfree(h, nl);
     gfree(h, dseeds);
     gfree(h, dstream);
     gfree(h, doff);

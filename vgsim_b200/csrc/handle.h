@@ -32,6 +32,7 @@ struct GenealogyBuffers {
     int *arena = nullptr;
     int *cell_hdr = nullptr;         // [R][K*H][3] (offset, size, cap)
     int *n_nodes = nullptr;          // [R] nodes actually created
+    int *scratch = nullptr;          // one int per node: newLineages scratch of the replay, then tree-shape scratch
     bool valid = false;
     std::vector<long long> h_node_off, h_mut_off, h_mig_off;
 };
@@ -46,7 +47,7 @@ struct Handle {
     std::vector<HostParams> hp;
     long long ev_bound = 0, leap_bound = 0;  // host upper bounds of log rows / leaps per replicate
     long long launches = 0;
-    int tau_variant = 0;  // 0 = infectious-cell list (product), 1 = walk all P channels (parity tap)
+    int tau_variant = 0;  // 0 = aggregated small groups (product), 1 = one Poisson draw per channel (parity tap)
     bool state_set = false;
     GenealogyBuffers gen;
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]

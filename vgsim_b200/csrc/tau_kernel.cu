@@ -9,20 +9,28 @@
 //      drain while the CTA computes);
 //   1. F[t,h] = sum_s eff[t,s] m[s,s] b[h] I[s,h] only for haplotypes present anywhere (colcnt[h] > 0);
 //   2. net drifts and tau (ChooseTau, :2432-2450, incl. the float-epsilon quirk);
-//   3. Poisson draws only for channels that can fire: a compact list of infectious cells (p,h) with
-//      I > 0 is kept in shared memory; each cell owns LC = E + (K-1)*S channels (its E deme-block
-//      events and its out-migration to every other deme x group), walked in groups of 4 that share one
-//      Philox4x32-10 block keyed by (seed; cell, leap, retry|epoch, group).  Poisson(0) = 0 consumes no
-//      randomness in the reference either (numpy random_poisson), so skipping the other channels does
-//      not change the distribution.  Non-zero counts are scattered into the zero-filled row;
+//   3. Poisson draws only where something can fire.  A compact list of infectious cells (p,h) with I > 0
+//      is kept in shared memory; a cell owns LC = E + (K-1)*S channels: RECOVERY, SAMPLING, 3U MUTATION,
+//      S TRANSMISSION, and its out-MIGRATION to every other deme x group.  Poisson(0) = 0 consumes no
+//      randomness in the reference either (numpy random_poisson), so channels of empty cells are never
+//      touched.  Per cell the kernel makes "primary" draws in blocks of 4 sharing one Philox4x32-10 call
+//      keyed (seed; cell, leap, retry|epoch, block): RECOVERY, SAMPLING, the TOTAL of the mutation group,
+//      the TOTAL of the out-migration group, and each TRANSMISSION channel.  A group total is used when
+//      its lambda <= 2: independent Poissons conditioned on their sum are multinomial, so drawing the sum
+//      and splitting a non-zero sum over the group's channels has exactly the reference's joint
+//      distribution; larger groups are "expanded" and drawn channel by channel.  A draw whose count the
+//      top 32 bits of its uniform already prove to be 0 (U < 1 - lambda) ends there; the others are pushed
+//      to a shared-memory queue and finished in a second pass with all lanes busy (inversion for
+//      lambda < 10 from the bottom of the queue, Hoermann PTRS from the top, so warps do not mix them).
+//      Non-zero counts are scattered into the zero-filled row;
 //   4. feasibility (:2522-2528, with the source-deme book-keeping quirk Q8); on failure tau is halved
 //      and the whole leap redrawn (:2316-2321);
 //   5. deltas applied, the infectious-cell list rebuilt, MULTITYPE row appended, CheckLockdown for
 //      every deme (:2326-2329).
 //
-// tau_kernel<true> walks ALL P channels instead of the cell list (same Philox addressing, so the two
-// variants are bit-identical by construction); it is kept as a parity tap (vgsim_set_tau_variant).
-// The same channel code backs the deterministic propensity tap (propensity_kernel).
+// variant 1 (vgsim_set_tau_variant) expands every group, i.e. draws each channel separately exactly like
+// the reference; it is kept as a parity tap.  The same channel code backs the deterministic propensity
+// tap (propensity_kernel).
 #include "common.cuh"
 #include "rates.cuh"
 #include "samplers.cuh"
@@ -43,15 +51,19 @@ struct SArr {
 
 struct TauShared {
     // fp64
-    SArr<double> b, d, sr, q, tmq, sigT, T, sm, cd, c, mdiag, sizeD, maxEBM, startN, endN, dI, dS, F, red, effS;
+    SArr<double> b, d, sr, q, tmq, sigT, T, sm, cd, c, mdiag, sizeD, maxEBM, startN, endN, dI, dS, F, Qm, red, effS;
+    SArr<double> qlam;    // slow-path queue: lambda of the pending draw
     bool has_effS;
     // int32
     SArr<int> I, Sx, chkI, updI, dSx, g, lock;
     SArr<int> tot[2];     // per-deme infectious totals          (double-buffered: built for the next leap while
     SArr<int> colcnt[2];  // #demes holding haplotype h           the current one is still being read)
     SArr<int> act[2];     // compact list of cells with I > 0
+    SArr<int> qhi, qown, qcode;  // slow-path queue: primary Philox word, owner id, draw code
+    SArr<int> xq;         // expansion queues: [0,256) cells whose mutation group, [256,512) whose migration group
+                          // is drawn channel by channel
     SArr<int> flags;      // [0..5]=per-leap tallies by event type (EV_*) [6]=flip flag [7]=overflow [8+b]=nAct[b]
-                          // [10]=flips total
+                          // [10]=flips total [12+4*parity .. +3]=queue counters of the live draw round
     SArr<long long> tally64;  // [0..5] events by type since the kernel (or the last Restart) began
     int bytes;
 };
@@ -71,7 +83,8 @@ __host__ __device__ inline TauShared tau_layout(const Dims &D) {
     dbl(s.sm, D.K); dbl(s.cd, D.K); dbl(s.c, D.K); dbl(s.mdiag, D.K); dbl(s.sizeD, D.K); dbl(s.maxEBM, D.K);
     dbl(s.startN, D.K); dbl(s.endN, D.K);
     o += D.K * 8;  // spare
-    dbl(s.dI, D.K * D.H); dbl(s.F, D.K * D.H);
+    dbl(s.dI, D.K * D.H); dbl(s.F, D.K * D.H); dbl(s.Qm, D.K * D.H);
+    dbl(s.qlam, 1024);
     dbl(s.dS, D.K * D.S);
     dbl(s.red, 40);
     s.has_effS = tau_eff_in_smem(D);
@@ -82,7 +95,8 @@ __host__ __device__ inline TauShared tau_layout(const Dims &D) {
     i32(s.Sx, D.K * D.S); i32(s.dSx, D.K * D.S);
     i32(s.g, D.H); i32(s.colcnt[0], D.H); i32(s.colcnt[1], D.H);
     i32(s.lock, D.K); i32(s.tot[0], D.K); i32(s.tot[1], D.K);
-    i32(s.flags, 16);
+    i32(s.qhi, 1024); i32(s.qown, 1024); i32(s.qcode, 1024); i32(s.xq, 512);
+    i32(s.flags, 24);
     i64(s.tally64, 8);
     s.bytes = o;
     return s;
@@ -242,6 +256,9 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
     const int *colcnt = s.colcnt[cb];
     for (int i = tid; i < K * H; i += nt) {
         int tp = i >> D.hshift, h = i & (H - 1);
+        double Q = 0.0;
+        for (int sn = 0; sn < S; sn++) Q += (double)s.Sx[tp * S + sn] * s.sigT[sn * H + h];
+        s.Qm[i] = Q;  // Q[p,h] = sum_s Sx[p,s] sigma[s,h]: reused by the out-migration totals
         double acc = 0.0;
         if (colcnt[h] != 0) {
             for (int sp = 0; sp < K; sp++) {
@@ -256,8 +273,7 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
     const float eps = 0.03f;
     for (int i = tid; i < K * H; i += nt) {
         int p = i >> D.hshift, h = i & (H - 1);
-        double Q = 0.0;
-        for (int sn = 0; sn < S; sn++) Q += (double)s.Sx[p * S + sn] * s.sigT[sn * H + h];
+        const double Q = s.Qm[i];
         double Ii = (double)s.I[i];
         double v = Q * s.F[i] + s.c[p] * s.b[h] * Ii * Q - (s.d[h] + s.sr[h] * s.sm[p] + s.tmq[h]) * Ii;
         for (int u = 0; u < U; u++) {
@@ -351,7 +367,7 @@ __device__ void load_replicate(const DevState &st, int r, const Dims &D, const T
         if (v > 2147483647LL || v < 0) ovf = 1;
         s.Sx[i] = (int)v;
     }
-    if (tid < 16) s.flags[tid] = 0;
+    if (tid < 24) s.flags[tid] = 0;
     if (tid < 6) s.tally64[tid] = 0;
     __syncthreads();
     if (ovf) atomicOr(&s.flags[7], 1);
@@ -424,22 +440,185 @@ __device__ __forceinline__ void wipe_leap(const Dims &D, const TauShared &s, int
     if (tid < 6) s.flags[tid] = 0;
 }
 
-template <bool DENSE>
-__global__ void __launch_bounds__(256, 2) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
-                                                     const __grid_constant__ TauShared s) {
+// Geometry of the draws one owner makes in a leap, and of its Philox domains (word 3 of the counter).
+// An owner is an infectious cell (p,h) (id p*H+h) or deme p's SUSCCHANGE block (id K*H+p).
+//   primary block 0 of a cell : {RECOVERY, SAMPLING, total MUTATION, total out-MIGRATION}
+//   primary blocks 1..        : TRANSMISSION to group s, 4 per block
+//   primary blocks of a deme  : its S(S-1) SUSCCHANGE channels, 4 per block
+//   then the per-channel blocks of an EXPANDED mutation group, of an EXPANDED migration group, and the
+//   domains that feed the multinomial split of an aggregated total.
+struct DrawGeom {
+    int NB1;   // primary blocks per cell
+    int G2;    // primary blocks per deme (SUSCCHANGE)
+    int NBP;   // max(NB1, G2): first expanded-mutation domain
+    int nbm;   // blocks of an expanded mutation group  (3U channels)
+    int nbg;   // blocks of an expanded migration group ((K-1)S channels)
+    int GS;    // domains per owner = stride between Philox "kinds"
+    int LC;    // channels owned by a cell
+};
+
+__device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
+    DrawGeom g;
+    g.LC = D.E + (D.K - 1) * D.S;
+    g.NB1 = 1 + ((D.S + 3) >> 2);
+    g.G2 = (D.SS1 + 3) >> 2;
+    g.NBP = g.NB1 > g.G2 ? g.NB1 : g.G2;
+    g.nbm = (3 * D.U + 3) >> 2;
+    g.nbg = ((D.K - 1) * D.S + 3) >> 2;
+    g.GS = g.NBP + g.nbm + g.nbg + 2;
+    return g;
+}
+
+#define TAU_QCAP 1024        // slow-path queue entries per round (4 draws x 256 threads)
+#define TAU_THETA 2.0        // a mutation / out-migration group is drawn as ONE Poisson total when lam_total <= theta
+
+// total out-migration propensity of cell (p,h): sum over targets and groups of the channel propensities,
+// factorised through Q[tp,h] = sum_s Sx[tp,s] sigma[s,h]
+__device__ __forceinline__ double mig_total(int p, int h, int Ii, const Dims &D, const TauShared &s, const double *eff) {
+    double acc = 0.0;
+    for (int tp = 0; tp < D.K; tp++)
+        if (tp != p) acc += eff[tp * D.K + p] * s.Qm[tp * D.H + h];
+    return (double)Ii * s.b[h] * s.mdiag[p] * acc;
+}
+
+// One primary draw: nothing to do for lam == 0 (numpy's random_poisson(0) consumes no randomness either); a
+// count that the top 32 bits of the uniform already prove to be 0 is settled here; everything else goes to
+// the slow-path queue (inversion entries from the bottom, PTRS entries from the top) or, for group totals
+// that are too large to aggregate, to the expansion queues.
+__device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner, int code, const TauShared &s, int *qn) {
+    if (lam < 10.0) {
+        if ((double)hi + 1.0 <= (1.0 - lam) * 4294967296.0) return;  // U < 1-lam <= exp(-lam)  =>  0
+        int e = atomicAdd(&qn[0], 1);
+        s.qlam[e] = lam;
+        s.qhi[e] = (int)hi;
+        s.qown[e] = owner;
+        s.qcode[e] = code;
+    } else {
+        int e = TAU_QCAP - 1 - atomicAdd(&qn[1], 1);
+        s.qlam[e] = lam;
+        s.qhi[e] = (int)hi;
+        s.qown[e] = owner;
+        s.qcode[e] = code;
+    }
+}
+
+// multinomial split of an aggregated total: n events of cell (p,h), each assigned to one channel of the
+// group with probability prop_channel / prop_total (exact: independent Poissons conditioned on their sum)
+static __device__ __noinline__ void split_total(int n, int p, int h, int code, int *row, const Dims &D, const TauShared &s,
+                                                const double *eff, const DrawGeom &g, PhiloxCtx ctx, LeapTally &tr) {
+    const int K = D.K, H = D.H, S = D.S, U = D.U;
+    const int cell = p * H + h;
+    const double Ii = (double)s.I[cell];
+    ctx.dom0 = (uint32_t)(g.NBP + g.nbm + g.nbg + (code == 2 ? 0 : 1));
+    uint4 w = make_uint4(0, 0, 0, 0);
+    for (int e = 0; e < n; e++) {
+        if ((e & 1) == 0) w = ctx.draw((uint32_t)(e >> 1));
+        const double u = (e & 1) ? u53(w.z, w.w) : u53(w.x, w.y);
+        int l = -1;
+        if (code == 2) {  // mutation: 3U channels with propensities q[h][uk] * I
+            const double x = u * (s.tmq[h] * Ii);
+            double acc = 0.0;
+            for (int uk = 0; uk < 3 * U; uk++) {
+                double pr = s.q[h * U * 3 + uk] * Ii;
+                if (pr > 0.0) {
+                    l = 2 + uk;
+                    acc += pr;
+                    if (x < acc) break;
+                }
+            }
+        } else {  // out-migration: first the target deme by eff[tp,p] Q[tp,h], then the group
+            const double common = Ii * s.b[h] * s.mdiag[p];
+            double tot = 0.0;
+            for (int tp = 0; tp < K; tp++)
+                if (tp != p) tot += eff[tp * K + p] * s.Qm[tp * H + h];
+            double x = u * tot, acc = 0.0, before = 0.0;
+            int tsel = -1;
+            for (int tp = 0; tp < K; tp++) {
+                if (tp == p) continue;
+                double wt = eff[tp * K + p] * s.Qm[tp * H + h];
+                if (wt > 0.0) {
+                    tsel = tp;
+                    before = acc;
+                    acc += wt;
+                    if (x < acc) break;
+                }
+            }
+            if (tsel >= 0) {
+                double x2 = (x - before) * common, acc2 = 0.0;
+                int ssel = -1;
+                for (int sn = 0; sn < S; sn++) {
+                    double pr = eff[tsel * K + p] * (double)s.Sx[tsel * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
+                    if (pr > 0.0) {
+                        ssel = sn;
+                        acc2 += pr;
+                        if (x2 < acc2) break;
+                    }
+                }
+                if (ssel >= 0) l = D.E + (tsel - (tsel > p ? 1 : 0)) * S + ssel;
+            }
+        }
+        if (l >= 0) {
+            Channel ch;
+            int c = cell_channel(p, h, l, D, s, eff, ch);
+            atomicAdd(&row[c], 1);
+            book(ch, 1, s, tr);
+        }
+    }
+}
+
+// one slow-path queue entry: finish the Poisson draw, then write / split the count
+__device__ __forceinline__ void process_entry(int e, int *row, const Dims &D, const TauShared &s, const double *eff,
+                                              const DrawGeom &g, PhiloxCtx &ctx, LeapTally &tr) {
+    const double lam = s.qlam[e];
+    const uint32_t hi = (uint32_t)s.qhi[e];
+    const int owner = s.qown[e], code = s.qcode[e];
+    const int KH = D.K * D.H;
+    const bool cell_owned = owner < KH;
+    int blk, q;
+    if (!cell_owned) {
+        blk = code >> 2;
+        q = code & 3;
+    } else if (code < 4) {
+        blk = 0;
+        q = code;
+    } else {
+        blk = 1 + ((code - 4) >> 2);
+        q = (code - 4) & 3;
+    }
+    ctx.c0 = (uint32_t)owner;
+    ctx.dom0 = (uint32_t)blk;
+    const int n = (int)(lam < 10.0 ? poisson_inversion(lam, hi, ctx, q) : poisson_ptrs(lam, ctx, q));
+    if (n == 0) return;
+    Channel ch;
+    if (!cell_owned) {
+        int c = susc_channel(owner - KH, code, D, s, ch);
+        row[c] = n;
+        book(ch, n, s, tr);
+        return;
+    }
+    const int p = owner >> D.hshift, h = owner & (D.H - 1);
+    if (code == 2 || code == 3) {
+        split_total(n, p, h, code, row, D, s, eff, g, ctx, tr);
+        return;
+    }
+    const int l = code == 0 ? 0 : code == 1 ? 1 : 2 + 3 * D.U + (code - 4);
+    int c = cell_channel(p, h, l, D, s, eff, ch);
+    row[c] = n;
+    book(ch, n, s, tr);
+}
+
+__global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
+                                                     const __grid_constant__ TauShared s, const int variant) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int LC = D.E + (K - 1) * S;                     // channels owned by one infectious cell
-    const int G1 = (LC + 3) >> 2, G2 = (D.SS1 + 3) >> 2;  // Philox groups per cell / per deme (SUSCCHANGE)
-    const int GS = G1 > G2 ? G1 : G2;
+    const DrawGeom g = draw_geom(D);
 
     for (int r = blockIdx.x; r < st.R; r += gridDim.x) {
         const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
         double *eff_g = st.eff + (size_t)r * K * K;
         long long *ctr = st.counters + (size_t)r * NCOUNT;
         const uint64_t seed = st.seeds[r];
-        const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
         __syncthreads();
         load_replicate(st, r, D, s, pp, eff_g);
         const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
@@ -448,6 +627,7 @@ __global__ void __launch_bounds__(256, 2) tau_kernel(const __grid_constant__ Dev
             continue;
         }
         int cb = 0;          // list buffer describing the current state
+        unsigned rnd = 0;    // draw-round parity: which pair of queue counters is live
         bool restarted = false;
         long long sC = ctr[C_S];
         long long evptr = ctr[C_EVPTR], leaps = ctr[C_LEAPS];
@@ -476,71 +656,127 @@ __global__ void __launch_bounds__(256, 2) tau_kernel(const __grid_constant__ Dev
                         LeapTally tr;
                         tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
                         PhiloxCtx ctx;
-                        ctx.key = key;
+                        ctx.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
                         ctx.c1 = (uint32_t)leaps;
                         ctx.c2 = (retry & 0xffu) | (epoch << 8);
-                        ctx.dstride = (uint32_t)GS;
-                        if (DENSE) {
-                            for (int c = tid; c < D.P; c += nt) {
-                                Channel ch;
-                                int owner, l;
-                                decode_channel(c, D, s, eff, ch, owner, l);
-                                double lam = ch.prop * tau;
-                                if (lam > 0.0) {
-                                    ctx.c0 = (uint32_t)owner;
-                                    ctx.dom0 = (uint32_t)(l >> 2);
-                                    uint4 w = ctx.draw(0u);
-                                    int n = (int)poisson_draw(lam, pick_word(w, l & 3), ctx, l & 3);
-                                    if (n != 0) {
-                                        row[c] = n;
-                                        book(ch, n, s, tr);
+                        ctx.dstride = (uint32_t)g.GS;
+                        const int n1 = nAct * g.NB1, nItems = n1 + K * g.G2;
+                        for (int base = 0; base < nItems; base += nt, rnd++) {
+                            int *qn = &s.flags[12 + 4 * (rnd & 1)];  // [0] inversion [1] PTRS [2] expand-mut [3] expand-mig
+                            const int item = base + tid;
+                            // ---- 3a. primary draws of this round's owners
+                            if (item < n1) {
+                                const int ai = item / g.NB1, blk = item - ai * g.NB1;
+                                const int cell = act[ai];
+                                const int p = cell >> D.hshift, h = cell & (H - 1);
+                                const int Ii = s.I[cell];
+                                double lam[4];
+                                if (blk == 0) {
+                                    lam[0] = s.d[h] * (double)Ii * tau;
+                                    lam[1] = s.sr[h] * (double)Ii * s.sm[p] * tau;
+                                    lam[2] = s.tmq[h] * (double)Ii * tau;
+                                    lam[3] = K > 1 ? mig_total(p, h, Ii, D, s, eff) * tau : 0.0;
+                                    if (lam[2] > 0.0 && (variant == 1 || lam[2] > TAU_THETA)) {
+                                        s.xq[atomicAdd(&qn[2], 1)] = cell;
+                                        lam[2] = 0.0;
+                                    }
+                                    if (lam[3] > 0.0 && (variant == 1 || lam[3] > TAU_THETA)) {
+                                        s.xq[nt + atomicAdd(&qn[3], 1)] = cell;
+                                        lam[3] = 0.0;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 4; q++) {
+                                        const int sn = (blk - 1) * 4 + q;
+                                        lam[q] = sn < S ? s.b[h] * s.sigT[sn * H + h] * s.c[p] * (double)s.Sx[p * S + sn] * (double)Ii * tau
+                                                        : 0.0;
                                     }
                                 }
-                            }
-                        } else {
-                            const int n1 = nAct * G1, nItems = n1 + K * G2;
-                            for (int item = tid; item < nItems; item += nt) {
-                                int p, h = 0, j, lim;
-                                const bool is_cell = item < n1;
-                                if (is_cell) {
-                                    int ai = item / G1;
-                                    j = item - ai * G1;
-                                    int cell = act[ai];
-                                    p = cell >> D.hshift;
-                                    h = cell & (H - 1);
+                                if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
                                     ctx.c0 = (uint32_t)cell;
-                                    lim = LC;
-                                } else {
-                                    int it = item - n1;
-                                    p = it / G2;
-                                    j = it - p * G2;
-                                    ctx.c0 = (uint32_t)(K * H + p);
-                                    lim = D.SS1;
+                                    ctx.dom0 = (uint32_t)blk;
+                                    const uint4 w = ctx.draw(0u);
+                                    const int code0 = blk == 0 ? 0 : 4 + (blk - 1) * 4;
+                                    if (lam[0] > 0.0) primary_draw(lam[0], w.x, cell, code0, s, qn);
+                                    if (lam[1] > 0.0) primary_draw(lam[1], w.y, cell, code0 + 1, s, qn);
+                                    if (lam[2] > 0.0) primary_draw(lam[2], w.z, cell, code0 + 2, s, qn);
+                                    if (lam[3] > 0.0) primary_draw(lam[3], w.w, cell, code0 + 3, s, qn);
                                 }
-                                ctx.dom0 = (uint32_t)j;
-                                uint4 w = make_uint4(0, 0, 0, 0);
-                                bool have_w = false;
+                            } else if (item < nItems) {
+                                const int it = item - n1;
+                                const int p = it / g.G2, j = it - p * g.G2;
+                                double lam[4];
+                                Channel ch;
 #pragma unroll
                                 for (int q = 0; q < 4; q++) {
-                                    int l = j * 4 + q;
-                                    if (l < lim) {
-                                        Channel ch;
-                                        int c = is_cell ? cell_channel(p, h, l, D, s, eff, ch) : susc_channel(p, l, D, s, ch);
-                                        double lam = ch.prop * tau;
-                                        if (lam > 0.0) {
-                                            if (!have_w) {
-                                                w = ctx.draw(0u);
-                                                have_w = true;
-                                            }
-                                            int n = (int)poisson_draw(lam, pick_word(w, q), ctx, q);
-                                            if (n != 0) {
-                                                row[c] = n;
-                                                book(ch, n, s, tr);
-                                            }
+                                    const int l = j * 4 + q;
+                                    lam[q] = 0.0;
+                                    if (l < D.SS1) {
+                                        susc_channel(p, l, D, s, ch);
+                                        lam[q] = ch.prop * tau;
+                                    }
+                                }
+                                if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
+                                    ctx.c0 = (uint32_t)(K * H + p);
+                                    ctx.dom0 = (uint32_t)j;
+                                    const uint4 w = ctx.draw(0u);
+                                    if (lam[0] > 0.0) primary_draw(lam[0], w.x, K * H + p, j * 4, s, qn);
+                                    if (lam[1] > 0.0) primary_draw(lam[1], w.y, K * H + p, j * 4 + 1, s, qn);
+                                    if (lam[2] > 0.0) primary_draw(lam[2], w.z, K * H + p, j * 4 + 2, s, qn);
+                                    if (lam[3] > 0.0) primary_draw(lam[3], w.w, K * H + p, j * 4 + 3, s, qn);
+                                }
+                            }
+                            __syncthreads();
+                            // ---- 3b. drain: slow-path draws (inversion from the bottom, PTRS from the top of the
+                            //          queue, so the two kinds sit in different warps), then the expanded groups
+                            const int ninv = qn[0], nptr = qn[1], nxm = qn[2], nxg = qn[3];
+                            if (tid < 4) s.flags[12 + 4 * ((rnd + 1) & 1) + tid] = 0;
+                            for (int e = tid; e < ninv; e += nt) process_entry(e, row, D, s, eff, g, ctx, tr);
+                            for (int k = nt - 1 - tid; k < nptr; k += nt) process_entry(TAU_QCAP - 1 - k, row, D, s, eff, g, ctx, tr);
+                            const int itM = nxm * g.nbm, itX = itM + nxg * g.nbg;
+                            for (int it = tid; it < itX; it += nt) {
+                                int owner, b, lbase, lend, domb;
+                                if (it < itM) {
+                                    const int xi = it / g.nbm;
+                                    b = it - xi * g.nbm;
+                                    owner = s.xq[xi];
+                                    lbase = 2;
+                                    lend = 2 + 3 * D.U;
+                                    domb = g.NBP + b;
+                                } else {
+                                    const int it2 = it - itM, xi = it2 / g.nbg;
+                                    b = it2 - xi * g.nbg;
+                                    owner = s.xq[nt + xi];
+                                    lbase = D.E;
+                                    lend = g.LC;
+                                    domb = g.NBP + g.nbm + b;
+                                }
+                                const int p = owner >> D.hshift, h = owner & (H - 1);
+                                ctx.c0 = (uint32_t)owner;
+                                ctx.dom0 = (uint32_t)domb;
+                                uint4 w = make_uint4(0, 0, 0, 0);
+                                bool have_w = false;
+#pragma unroll 1
+                                for (int q = 0; q < 4; q++) {
+                                    const int l = lbase + 4 * b + q;
+                                    if (l >= lend) break;
+                                    Channel ch;
+                                    const int c = cell_channel(p, h, l, D, s, eff, ch);
+                                    const double lam = ch.prop * tau;
+                                    if (lam > 0.0) {
+                                        if (!have_w) {
+                                            w = ctx.draw(0u);
+                                            have_w = true;
+                                        }
+                                        const int n = (int)poisson_draw(lam, pick_word(w, q), ctx, q);
+                                        if (n != 0) {
+                                            row[c] = n;
+                                            book(ch, n, s, tr);
                                         }
                                     }
                                 }
                             }
+                            __syncthreads();
                         }
                         if (tr.B) atomicAdd(&s.flags[EV_BIRTH], tr.B);
                         if (tr.Dd) atomicAdd(&s.flags[EV_DEATH], tr.Dd);
@@ -549,11 +785,16 @@ __global__ void __launch_bounds__(256, 2) tau_kernel(const __grid_constant__ Dev
                         if (tr.I) atomicAdd(&s.flags[EV_SUSCCHANGE], tr.I);
                         if (tr.G) atomicAdd(&s.flags[EV_MIGRATION], tr.G);
                         __syncthreads();
-                        // feasibility (:2522-2528)
+                        // feasibility (:2522-2528).  The reference books migration arrivals on the SOURCE cell
+                        // (quirk Q8), so its test can pass while the cell that is really depleted goes negative;
+                        // from then on every redraw fails and the reference halves tau forever.  Here a leap must
+                        // pass the reference's test AND leave the applied state inside [0, size].
                         int bad = 0;
                         for (int i = tid; i < K * H; i += nt) {
+                            const double sz = s.sizeD[i >> D.hshift];
                             double v = (double)s.I[i] + (double)s.chkI[i];
-                            if (v < 0.0 || v > s.sizeD[i >> D.hshift]) bad = 1;
+                            double u = (double)s.I[i] + (double)s.updI[i];
+                            if (v < 0.0 || v > sz || u < 0.0 || u > sz) bad = 1;
                         }
                         for (int i = tid; i < K * S; i += nt) {
                             double v = (double)s.Sx[i] + (double)s.dSx[i];
@@ -564,6 +805,11 @@ __global__ void __launch_bounds__(256, 2) tau_kernel(const __grid_constant__ Dev
                         tau *= 0.5;
                         wipe_leap(D, s, row);  // rare path
                         __syncthreads();
+                        if (retry >= 80) {  // tau * 2^-80: nothing can fire any more, yet the state fails the test
+                            if (tid == 0) st.err[r] |= ERR_TAU_STUCK;
+                            tau = 0.0;
+                            break;
+                        }
                     }
                     // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) and rebuild the cell list
                     for (int i = tid; i < K * H; i += nt) {
@@ -665,24 +911,19 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
 }
 
 // host launchers ---------------------------------------------------------------------------------
-template <bool DENSE>
-static cudaError_t launch_tau_variant(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms) {
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
     const TauShared lay = tau_layout(st.D);
     size_t smem = (size_t)lay.bytes;
-    cudaError_t e = cudaFuncSetAttribute(tau_kernel<DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel<DENSE>, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     int grid = num_sms * per_sm;
     if (grid > st.R) grid = st.R;
-    tau_kernel<DENSE><<<grid, 256, smem, stream>>>(st, a, lay);
+    tau_kernel<<<grid, 256, smem, stream>>>(st, a, lay, variant);
     return cudaGetLastError();
-}
-
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
-    return variant == 1 ? launch_tau_variant<true>(st, a, stream, num_sms) : launch_tau_variant<false>(st, a, stream, num_sms);
 }
 
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
