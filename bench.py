@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--leaps", type=int, default=32, help="tau leaps per replicate per step")
     ap.add_argument("--scenario", default="t3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--phases", action="store_true", help="add the tau kernel's per-phase critical-path cycles (timing tap)")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="target timed CPU seconds per worker")
     ap.add_argument("--cpu-worker", nargs=4, metavar=("SEED", "REPS", "LEAPS", "SCENARIO"), default=None)
     return ap.parse_args()
@@ -287,6 +288,8 @@ def gpu_arm(args, rank, world, local_rank):
     P, H = h.P, h.H
     stream = torch.cuda.Stream(device=dev)
     h.set_stream(stream.cuda_stream)
+    if args.phases:
+        h.set_tau_variant(2)
 
     # ---- Phase A (untimed): device direct method to T_WARM for every replicate; snapshot the states
     h.simulate_direct(250000, -1, T_WARM, 200)
@@ -347,6 +350,8 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         clocks.start()
     launches0 = h.launch_count()
+    if args.phases:
+        h.tau_phase_cycles(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for i in range(args.warmup, n_total):
@@ -356,6 +361,7 @@ def gpu_arm(args, rank, world, local_rank):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = h.launch_count() - launches0
+    phase_cycles = h.tau_phase_cycles(reset=True) if args.phases else None
     err = h.synchronize(strict=False)
     cnt = acc[args.warmup:n_total].cpu().numpy()
     events = int(cnt[:, :, :6].sum())
@@ -431,6 +437,10 @@ def gpu_arm(args, rank, world, local_rank):
             "phase_a": {"mean_events": float(np.mean(cA["events"])), "mean_time": float(np.mean(cA["time"])),
                         "mean_infectious": float(I0.sum() / R)},
         }
+        if phase_cycles is not None:
+            names = ["wipe+lists+Q", "drifts+tau", "primary draws", "slow-path drain", "feasibility", "apply", "lockdown vote"]
+            nl = max(int(phase_cycles[7]), 1)
+            line["tau_phase_cycles_per_leap"] = {n: float(phase_cycles[i]) / nl for i, n in enumerate(names)}
         prof = os.path.join(ROOT, "profiles", "tau_kernel_traffic.json")
         if os.path.exists(prof):
             try:

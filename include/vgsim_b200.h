@@ -167,11 +167,16 @@ int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr);
 
 /* Parity tap.  Variant 0 (default, product): per infectious cell the kernel draws ONE Poisson for the total of
  * its mutation channels and ONE for the total of its out-migration channels whenever that total's lambda is
- * <= 2, and splits a non-zero total multinomially over the group's channels (independent Poissons
+ * <= 1, and splits a non-zero total multinomially over the group's channels (independent Poissons
  * conditioned on their sum are multinomial, so the joint distribution is unchanged).  Variant 1 draws every
  * channel separately, exactly like the reference's GenerateEvents_tau (src/_BirthDeath.pyx:2454-2532);
  * tests compare both with theory and with each other. */
 int vgsim_set_tau_variant(vgsim_handle h, int variant);
+/* Measurement tap: with bit 1 of the variant set, thread 0 of every CTA of the tau kernel accumulates the clock
+ * cycles between consecutive barriers of the leap loop (critical path per phase: 0 row wipe + lists + Q,
+ * 1 drifts + tau, 2 primary draws, 3 slow-path drain, 4 feasibility, 5 apply, 6 lockdown vote, 7 = #leaps)
+ * summed over CTAs since the last reset.  out16[16]. */
+int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset);
 
 /* Launch accounting: kernels launched by this handle since creation. */
 int64_t vgsim_launch_count(vgsim_handle h);

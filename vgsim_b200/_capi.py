@@ -67,6 +67,7 @@ def _load():
         "vgsim_summaries_dev": (c_int, [P, ctypes.POINTER(c_void_p)]),
         "vgsim_launch_count": (c_int64, [P]),
         "vgsim_set_tau_variant": (c_int, [P, c_int]),
+        "vgsim_debug_tau_phases": (c_int, [P, P, c_int]),
         "vgsim_last_kernel_ms": (c_int, [P, ctypes.POINTER(c_float)]),
         "vgsim_counters_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vgsim_test_poisson": (c_int, [P, c_int64, c_uint64, P]),
@@ -321,6 +322,12 @@ class Handle:
 
     def launch_count(self):
         return int(lib.vgsim_launch_count(self._h))
+
+    def tau_phase_cycles(self, reset=True):
+        """Critical-path cycles per leap phase accumulated by the tau kernel when variant bit 1 is set."""
+        out = np.zeros(16, np.uint64)
+        _ck(lib.vgsim_debug_tau_phases(self._h, _p(out), 1 if reset else 0))
+        return out
 
     def set_tau_variant(self, variant):
         """0 = small mutation / out-migration groups drawn as one Poisson total + multinomial split (product path),

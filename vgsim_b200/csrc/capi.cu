@@ -689,8 +689,15 @@ int vgsim_get_lockdowns(vgsim_handle h, int r, int64_t *state, int64_t *pop, dou
 
 int64_t vgsim_launch_count(vgsim_handle h) { return h->launches; }
 
+int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(tau_phase_cycles((unsigned long long *)out16, reset));
+    return 0;
+}
+
 int vgsim_set_tau_variant(vgsim_handle h, int variant) {
-    if (variant != 0 && variant != 1) return fail("tau variant must be 0 or 1");
+    if (variant < 0 || variant > 3) return fail("tau variant must be 0..3 (bit 0: per-channel draws, bit 1: phase timing)");
     h->tau_variant = variant;
     return 0;
 }

@@ -28,12 +28,25 @@ __device__ __forceinline__ uint32_t pick_word(const uint4 &w, int lane) {
     return lane == 0 ? w.x : lane == 1 ? w.y : lane == 2 ? w.z : w.w;
 }
 
+// log(k!) : exact table for k < 16, Stirling series beyond (next term 1/(1680 k^7) < 3e-12 at k = 16)
+__device__ const double LOGFACT16[16] = {
+    0.0, 0.0, 0.6931471805599453, 1.791759469228055, 3.1780538303479458, 4.787491742782046, 6.579251212010101,
+    8.525161361065415, 10.60460290274525, 12.801827480081469, 15.104412573075516, 17.502307845873887,
+    19.987214495661885, 22.552163853123425, 25.19122118273868, 27.89927138384089};
+
+__device__ __forceinline__ double log_factorial(long long k) {
+    if (k < 16) return LOGFACT16[k];
+    const double x = (double)k, r = 1.0 / x, r2 = r * r;
+    return (x + 0.5) * log(x) - x + 0.9189385332046728 + r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
+}
+
 static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCtx &ctx, int lane) {
-    const double slam = sqrt(lam), loglam = log(lam);
+    const double slam = sqrt(lam);
     const double b = 0.931 + 2.53 * slam;
     const double a = -0.059 + 0.02483 * b;
-    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
     const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    double loglam = 0.0, invalpha = 0.0;  // only the (rare) full acceptance test needs them
+    bool have = false;
     for (uint32_t t = 0; t < 64; t++) {
         // trial t: domain 2 + 4*t + lane gives 4 words = two 53-bit uniforms private to this channel
         uint4 w = ctx.draw(2u + 4u * t + (uint32_t)lane);
@@ -43,8 +56,13 @@ static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCt
         long long k = (long long)floor((2.0 * a / us + b) * U + lam + 0.43);
         if (us >= 0.07 && V <= vr) return k;
         if (k < 0 || (us < 0.013 && V > us)) continue;
-        if ((log(V) + log(invalpha) - log(a / (us * us) + b)) <= (-lam + (double)k * loglam - lgamma((double)k + 1.0)))
-            return k;
+        if (!have) {
+            loglam = log(lam);
+            invalpha = 1.1239 + 1.1328 / (b - 3.4);
+            have = true;
+        }
+        // log(V) + log(invalpha) - log(a/us^2 + b) <= -lam + k log(lam) - log(k!)
+        if (log(V * invalpha / (a / (us * us) + b)) <= -lam + (double)k * loglam - log_factorial(k)) return k;
     }
     return (long long)floor(lam + 0.5);  // unreachable in practice (acceptance ~0.9 per trial)
 }

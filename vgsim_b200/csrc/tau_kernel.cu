@@ -16,7 +16,7 @@
 //      touched.  Per cell the kernel makes "primary" draws in blocks of 4 sharing one Philox4x32-10 call
 //      keyed (seed; cell, leap, retry|epoch, block): RECOVERY, SAMPLING, the TOTAL of the mutation group,
 //      the TOTAL of the out-migration group, and each TRANSMISSION channel.  A group total is used when
-//      its lambda <= 2: independent Poissons conditioned on their sum are multinomial, so drawing the sum
+//      its lambda <= 1: independent Poissons conditioned on their sum are multinomial, so drawing the sum
 //      and splitting a non-zero sum over the group's channels has exactly the reference's joint
 //      distribution; larger groups are "expanded" and drawn channel by channel.  A draw whose count the
 //      top 32 bits of its uniform already prove to be 0 (U < 1 - lambda) ends there; the others are pushed
@@ -31,6 +31,8 @@
 // variant 1 (vgsim_set_tau_variant) expands every group, i.e. draws each channel separately exactly like
 // the reference; it is kept as a parity tap.  The same channel code backs the deterministic propensity
 // tap (propensity_kernel).
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "rates.cuh"
 #include "samplers.cuh"
@@ -50,52 +52,71 @@ struct SArr {
 };
 
 struct TauShared {
-    // fp64
-    SArr<double> b, d, sr, q, tmq, sigT, T, sm, cd, c, mdiag, sizeD, maxEBM, startN, endN, dI, dS, F, Qm, red, effS;
-    SArr<double> qlam;    // slow-path queue: lambda of the pending draw
+    // fp64 parameters
+    SArr<double> b, d, sr, q, tmq, sigT, sb, T, sm, cd, c, mdiag, sizeD, maxEBM, startN, endN, effS;
     bool has_effS;
+    // fp64 state (counts are exact in fp64; kept as doubles so the rate arithmetic needs no conversions)
+    SArr<double> I, Sx;       // infectious [K][H], susceptible [K][S]
+    SArr<double> dI, dS, Qm;  // drifts; Q[p,h] = sum_s Sx[p,s] sigma[s,h]
+    SArr<double> Bp, Rp;      // per (deme, group): infection pressure sum_h sigma b I, and return flow into the group
+    SArr<double> red;
+    SArr<unsigned long long> nbrmask;  // [H] (H <= 64) haplotypes one substitution away from h
+    SArr<unsigned long long> rowmask;  // [K] (H <= 64) haplotypes present in deme p
     // int32
-    SArr<int> I, Sx, chkI, updI, dSx, g, lock;
-    SArr<int> tot[2];     // per-deme infectious totals          (double-buffered: built for the next leap while
-    SArr<int> colcnt[2];  // #demes holding haplotype h           the current one is still being read)
-    SArr<int> act[2];     // compact list of cells with I > 0
-    SArr<int> qhi, qown, qcode;  // slow-path queue: primary Philox word, owner id, draw code
+    SArr<int> chkI, updI, dSx, g, lock;
+    SArr<int> tot;        // per-deme infectious totals (built by the apply pass)
+    SArr<int> colcnt;     // #demes holding haplotype h
+    SArr<int> colmask;    // (K <= 32) bit p set when deme p holds haplotype h
+    SArr<int> act;        // cells with I > 0 in ascending cell order (so every sum over it has a fixed order)
+    SArr<int> dstart;     // [K+1] first entry of deme p in act
+    SArr<int> segcnt;     // infectious cells per 32-cell segment (ordered compaction)
+    SArr<int> qhi, qoc;   // slow-path queue: primary Philox word; owner id | draw code << 20
     SArr<int> xq;         // expansion queues: [0,256) cells whose mutation group, [256,512) whose migration group
                           // is drawn channel by channel
-    SArr<int> flags;      // [0..5]=per-leap tallies by event type (EV_*) [6]=flip flag [7]=overflow [8+b]=nAct[b]
+    SArr<int> flags;      // [0..5]=per-leap tallies by event type (EV_*) [6]=flip flag [7]=overflow [8]=nAct
                           // [10]=flips total [12+4*parity .. +3]=queue counters of the live draw round
     SArr<long long> tally64;  // [0..5] events by type since the kernel (or the last Restart) began
+    int nseg;             // number of 32-cell segments
+    int qcap;             // slow-path queue capacity
+    bool store_drift;     // the propensity tap keeps dI/dS; the simulation kernel only needs tau
+    bool use_masks;       // H <= 64 and K <= 32: presence bit masks drive the sparse drift sums
     int bytes;
 };
 
 __host__ __device__ inline bool tau_eff_in_smem(const Dims &D) { return D.K <= 32; }
 
-__host__ __device__ inline TauShared tau_layout(const Dims &D) {
+__host__ __device__ inline TauShared tau_layout(const Dims &D, bool store_drift, int nt = 256) {
     TauShared s;
+    s.store_drift = store_drift;
+    s.qcap = 4 * nt;  // slow-path queue entries per round: at most 4 pushes per thread
     int o = 0;
     auto dbl = [&](SArr<double> &a, int n) { a.off = o; o += n * 8; };
+    auto u64 = [&](SArr<unsigned long long> &a, int n) { a.off = o; o += n * 8; };
     auto i32 = [&](SArr<int> &a, int n) { a.off = o; o += n * 4; };
     auto i64 = [&](SArr<long long> &a, int n) { o = (o + 7) & ~7; a.off = o; o += n * 8; };
+    const int KH = D.K * D.H, KS = D.K * D.S;
+    s.use_masks = D.H <= 64 && D.K <= 32;
+    s.nseg = (KH + 31) / 32;
     dbl(s.b, D.H); dbl(s.d, D.H); dbl(s.sr, D.H); dbl(s.tmq, D.H);
     dbl(s.q, D.H * D.U * 3);
-    dbl(s.sigT, D.S * D.H);
+    dbl(s.sigT, D.S * D.H); dbl(s.sb, D.S * D.H);
     dbl(s.T, D.S * D.S);
     dbl(s.sm, D.K); dbl(s.cd, D.K); dbl(s.c, D.K); dbl(s.mdiag, D.K); dbl(s.sizeD, D.K); dbl(s.maxEBM, D.K);
     dbl(s.startN, D.K); dbl(s.endN, D.K);
-    o += D.K * 8;  // spare
-    dbl(s.dI, D.K * D.H); dbl(s.F, D.K * D.H); dbl(s.Qm, D.K * D.H);
-    dbl(s.qlam, 1024);
-    dbl(s.dS, D.K * D.S);
-    dbl(s.red, 40);
     s.has_effS = tau_eff_in_smem(D);
     s.effS.off = o;
     if (s.has_effS) o += D.K * D.K * 8;
-    i32(s.I, D.K * D.H); i32(s.chkI, D.K * D.H); i32(s.updI, D.K * D.H);
-    i32(s.act[0], D.K * D.H); i32(s.act[1], D.K * D.H);
-    i32(s.Sx, D.K * D.S); i32(s.dSx, D.K * D.S);
-    i32(s.g, D.H); i32(s.colcnt[0], D.H); i32(s.colcnt[1], D.H);
-    i32(s.lock, D.K); i32(s.tot[0], D.K); i32(s.tot[1], D.K);
-    i32(s.qhi, 1024); i32(s.qown, 1024); i32(s.qcode, 1024); i32(s.xq, 512);
+    dbl(s.I, KH); dbl(s.Sx, KS);
+    dbl(s.dI, store_drift ? KH : 0); dbl(s.dS, store_drift ? KS : 0); dbl(s.Qm, KH);
+    dbl(s.Bp, KS); dbl(s.Rp, KS);
+    dbl(s.red, 64);
+    u64(s.nbrmask, s.use_masks ? D.H : 0); u64(s.rowmask, s.use_masks ? D.K : 0);
+    i32(s.chkI, KH); i32(s.updI, KH); i32(s.act, KH);
+    i32(s.dSx, KS);
+    i32(s.g, D.H); i32(s.colcnt, D.H); i32(s.colmask, D.H);
+    i32(s.lock, D.K); i32(s.tot, D.K); i32(s.dstart, D.K + 1);
+    i32(s.segcnt, s.nseg + 1);
+    i32(s.qhi, s.qcap); i32(s.qoc, s.qcap); i32(s.xq, 2 * nt);
     i32(s.flags, 24);
     i64(s.tally64, 8);
     s.bytes = o;
@@ -120,7 +141,7 @@ __device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, 
                                             Channel &ch) {
     const int K = D.K, H = D.H, S = D.S;
     const int cell = p * H + h;
-    const int Ii = s.I[cell];
+    const double Ii = s.I[cell];
     ch.i_dec = ch.i_inc = ch.i_chk = ch.s_dec = ch.s_inc = -1;
     ch.prop = 0.0;
     if (l < D.E) {
@@ -128,24 +149,24 @@ __device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, 
             ch.type = EV_DEATH;
             ch.i_dec = cell;
             ch.s_inc = p * S + s.g[h];
-            ch.prop = s.d[h] * (double)Ii;
+            ch.prop = s.d[h] * Ii;
         } else if (l == 1) {  // SAMPLING (:2392)
             ch.type = EV_SAMPLING;
             ch.i_dec = cell;
             ch.s_inc = p * S + s.g[h];
-            ch.prop = s.sr[h] * (double)Ii * s.sm[p];
+            ch.prop = s.sr[h] * Ii * s.sm[p];
         } else if (l < 2 + 3 * D.U) {  // MUTATION (:2400-2401)
             int uk = l - 2, u = uk / 3, k = uk - u * 3;
             ch.type = EV_MUTATION;
             ch.i_dec = cell;
             ch.i_inc = ch.i_chk = p * H + mutate_hap(h, u, k, D.U);
-            ch.prop = s.q[h * D.U * 3 + uk] * (double)Ii;
+            ch.prop = s.q[h * D.U * 3 + uk] * Ii;
         } else {  // TRANSMISSION (:2410-2414)
             int sn = l - 2 - 3 * D.U;
             ch.type = EV_BIRTH;
             ch.i_inc = ch.i_chk = cell;
             ch.s_dec = p * S + sn;
-            if (Ii != 0) ch.prop = s.b[h] * s.sigT[sn * H + h] * s.c[p] * (double)s.Sx[p * S + sn] * (double)Ii;
+            if (Ii != 0.0) ch.prop = s.b[h] * s.sigT[sn * H + h] * s.c[p] * s.Sx[p * S + sn] * Ii;
         }
         return D.NA + p * D.PD + D.SS1 + h * D.E + l;
     }
@@ -157,8 +178,7 @@ __device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, 
     ch.i_inc = tp * H + h;
     ch.i_chk = cell;
     ch.s_dec = tp * S + sn;
-    if (Ii != 0)
-        ch.prop = eff[tp * K + p] * (double)s.Sx[tp * S + sn] * (double)Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
+    if (Ii != 0.0) ch.prop = eff[tp * K + p] * s.Sx[tp * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
     return ((p * (K - 1) + tpp) * S + sn) * H + h;
 }
 
@@ -171,7 +191,7 @@ __device__ __forceinline__ int susc_channel(int p, int l, const Dims &D, const T
     ch.type = EV_SUSCCHANGE;
     ch.s_dec = p * S + ss;
     ch.s_inc = p * S + ts;
-    ch.prop = s.T[ss * S + ts] * (double)s.Sx[p * S + ss];
+    ch.prop = s.T[ss * S + ts] * s.Sx[p * S + ss];
     return D.NA + p * D.PD + l;
 }
 
@@ -210,125 +230,223 @@ __device__ __forceinline__ void decode_channel(int c, const Dims &D, const TauSh
     cell_channel(p, h, l, D, s, eff, ch);
 }
 
-__device__ __forceinline__ double block_min(double v, double *red) {
+// fixed-slot minimum over the CTA with ONE barrier: `slot` alternates between calls so that the previous call's
+// values are never overwritten while a slower warp still reads them
+__device__ __forceinline__ double block_min(double v, double *red, int slot) {
     for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-    int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    double *r = red + 32 * (slot & 1);
+    if ((threadIdx.x & 31) == 0) r[w] = v;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[w] = v;
-    __syncthreads();
-    v = red[0];
-    for (int i = 1; i < nw; i++) v = fmin(v, red[i]);
+    v = r[0];
+    for (int i = 1; i < nw; i++) v = fmin(v, r[i]);
     return v;
 }
 
-// Rebuild the infectious-cell list, the per-haplotype presence counts and the per-deme totals of buffer
-// `nb` from s.I (the buffer must have been zeroed and the zeroing made visible by a barrier).
-__device__ __forceinline__ void list_cell(const Dims &D, const TauShared &s, int nb, int i, int v) {
-    if (v != 0) {
-        int pos = atomicAdd(&s.flags[8 + nb], 1);
-        s.act[nb][pos] = i;
-        atomicAdd(&s.colcnt[nb][i & (D.H - 1)], 1);
-        atomicAdd(&s.tot[nb][i >> D.hshift], v);
+__device__ __forceinline__ int warp_sum_i(int v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- ordered compaction of the infectious cells ------------------------------------------------------
+// Pass 1 (count_cells): one ballot per 32-cell segment -> segcnt[]; also clears the presence tables.
+// Pass 2 (write_lists, after a barrier): every segment's base is the sum of the counts before it, so the
+// list comes out in ascending cell order regardless of warp scheduling; deme p's cells are the range
+// [dstart[p], dstart[p+1]).  colcnt / colmask / rowmask record where each haplotype is present.
+__device__ __forceinline__ void count_cells(const Dims &D, const TauShared &s) {
+    const int tid = threadIdx.x, nt = blockDim.x, KH = D.K * D.H;
+    for (int base = 0; base < KH; base += nt) {
+        const int i = base + tid;
+        const bool on = i < KH && s.I[i] != 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if ((tid & 31) == 0 && base + tid < KH) s.segcnt[i >> 5] = __popc(m);
+    }
+    for (int i = tid; i < D.H; i += nt) {
+        s.colcnt[i] = 0;
+        s.colmask[i] = 0;
+    }
+    if (s.use_masks)
+        for (int i = tid; i < D.K; i += nt) s.rowmask[i] = 0ull;
+}
+
+// number of infectious cells = sum of segcnt (every thread gets the value; warp-parallel, no barrier)
+__device__ __forceinline__ int total_cells(const TauShared &s) {
+    int acc = 0;
+    for (int k = threadIdx.x & 31; k < s.nseg; k += 32) acc += s.segcnt[k];
+    return warp_sum_i(acc);
+}
+
+__device__ __forceinline__ void write_lists(const Dims &D, const TauShared &s) {
+    const int tid = threadIdx.x, nt = blockDim.x, KH = D.K * D.H, lane = tid & 31;
+    for (int base = 0; base < KH; base += nt) {
+        const int i = base + tid;
+        const int seg = (base + (tid & ~31)) >> 5;  // this warp's segment in this sweep
+        int before = 0;
+        for (int k = lane; k < seg && k < s.nseg; k += 32) before += s.segcnt[k];
+        before = warp_sum_i(before);
+        const bool on = i < KH && s.I[i] != 0.0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        const int pos = before + __popc(m & ((1u << lane) - 1u));
+        if (i < KH) {
+            const int p = i >> D.hshift, h = i & (D.H - 1);
+            if (h == 0) s.dstart[p] = pos;
+            if (on) {
+                s.act[pos] = i;
+                atomicAdd(&s.colcnt[h], 1);
+                if (s.use_masks) {
+                    atomicOr(&s.colmask[h], 1 << p);
+                    atomicOr(&s.rowmask[p], 1ull << h);
+                }
+            }
+            if (i == KH - 1) {
+                s.dstart[D.K] = pos + (on ? 1 : 0);
+                s.flags[8] = pos + (on ? 1 : 0);
+            }
+        }
     }
 }
 
-__device__ __forceinline__ void zero_lists(const Dims &D, const TauShared &s, int nb) {
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < D.H; i += nt) s.colcnt[nb][i] = 0;
-    for (int i = tid; i < D.K; i += nt) s.tot[nb][i] = 0;
-    if (tid == 0) s.flags[8 + nb] = 0;
-}
-
-__device__ void rebuild_lists(const Dims &D, const TauShared &s, int nb) {
+// full rebuild from s.I (load, Restart): leaves tot[] too
+__device__ void rebuild_lists(const Dims &D, const TauShared &s) {
     const int tid = threadIdx.x, nt = blockDim.x;
     __syncthreads();
-    zero_lists(D, s, nb);
+    for (int i = tid; i < D.K; i += nt) s.tot[i] = 0;
+    count_cells(D, s);
     __syncthreads();
-    for (int i = tid; i < D.K * D.H; i += nt) list_cell(D, s, nb, i, s.I[i]);
+    for (int i = tid; i < D.K * D.H; i += nt) {
+        const double v = s.I[i];
+        if (v != 0.0) atomicAdd(&s.tot[i >> D.hshift], (int)v);
+    }
+    write_lists(D, s);
     __syncthreads();
 }
 
-// F, drifts and tau of the current shared-memory state (steps 1-2).  Returns tau (uniform).
-// cb = which list buffer describes the current state.
-__device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double *eff, int cb) {
+// Q[p,h] = sum_s Sx[p,s] sigma[s,h] for every cell (needs only Sx; runs before the list barrier)
+__device__ __forceinline__ void q_pass(const Dims &D, const TauShared &s) {
+    const int H = D.H, S = D.S;
+    for (int i = threadIdx.x; i < D.K * H; i += blockDim.x) {
+        const int p = i >> D.hshift, h = i & (H - 1);
+        double Q = 0.0;
+        for (int sn = 0; sn < S; sn++) Q += s.Sx[p * S + sn] * s.sigT[sn * H + h];
+        s.Qm[i] = Q;
+    }
+}
+
+// Drifts and tau of the current shared-memory state (Propensities :2351-2417 summed per compartment, ChooseTau
+// :2432-2450).  Needs the lists and Qm; contains two barriers; returns tau (uniform).  Every sum runs over the
+// ordered cell list / set bits in ascending order, so the result does not depend on warp scheduling.
+__device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double *eff, int slot) {
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const int *colcnt = s.colcnt[cb];
-    for (int i = tid; i < K * H; i += nt) {
-        int tp = i >> D.hshift, h = i & (H - 1);
-        double Q = 0.0;
-        for (int sn = 0; sn < S; sn++) Q += (double)s.Sx[tp * S + sn] * s.sigT[sn * H + h];
-        s.Qm[i] = Q;  // Q[p,h] = sum_s Sx[p,s] sigma[s,h]: reused by the out-migration totals
-        double acc = 0.0;
-        if (colcnt[h] != 0) {
-            for (int sp = 0; sp < K; sp++) {
-                int Ii = s.I[sp * H + h];
-                if (sp != tp && Ii != 0) acc += eff[tp * K + sp] * s.mdiag[sp] * (s.b[h] * (double)Ii);
+    // ---- A. per (deme, group): pressure B = sum_h sigma[s,h] b[h] I[p,h], return flow R = sum_{g[h]=s} (d + sr sm) I.
+    //         8 lanes share one (deme, group) sum (strided over the deme's cells) and combine in a fixed butterfly.
+    for (int t0 = 0; t0 < K * S; t0 += nt >> 3) {
+        const int task = t0 + (tid >> 3), j = tid & 7;
+        double Bv = 0.0, Rv = 0.0;
+        int p = 0, sn = 0;
+        if (task < K * S) {
+            p = task / S;
+            sn = task - p * S;
+            const int a1 = s.dstart[p + 1];
+            for (int a = s.dstart[p] + j; a < a1; a += 8) {
+                const int cell = s.act[a], h = cell & (H - 1);
+                const double Iv = s.I[cell];
+                Bv += s.sb[sn * H + h] * Iv;
+                if (s.g[h] == sn) Rv += (s.d[h] + s.sr[h] * s.sm[p]) * Iv;
             }
         }
-        s.F[i] = acc;
+        for (int o = 4; o > 0; o >>= 1) {
+            Bv += __shfl_xor_sync(0xffffffffu, Bv, o);
+            Rv += __shfl_xor_sync(0xffffffffu, Rv, o);
+        }
+        if (task < K * S && j == 0) {
+            s.Bp[task] = Bv;
+            s.Rp[task] = Rv;
+        }
     }
     __syncthreads();
     double tmin = 1.0;
     const float eps = 0.03f;
+    // ---- B1. infectious drifts, one thread per cell
     for (int i = tid; i < K * H; i += nt) {
-        int p = i >> D.hshift, h = i & (H - 1);
-        const double Q = s.Qm[i];
-        double Ii = (double)s.I[i];
-        double v = Q * s.F[i] + s.c[p] * s.b[h] * Ii * Q - (s.d[h] + s.sr[h] * s.sm[p] + s.tmq[h]) * Ii;
-        for (int u = 0; u < U; u++) {
-            int sh = 2 * (U - u - 1);
-            int hu = (h >> sh) & 3;
-            for (int a = 0; a < 4; a++) {
-                if (a == hu) continue;
-                int src = h + ((a - hu) << sh);
-                int Is = s.I[p * H + src];
-                if (Is != 0) {
-                    int k = hu - (hu > a ? 1 : 0);
-                    v += s.q[(src * U + u) * 3 + k] * (double)Is;
+        const int p = i >> D.hshift, h = i & (H - 1);
+        const double Iv = s.I[i];
+        double v = 0.0;
+        if (s.colcnt[h] != 0) {
+            // force of infection on (p,h): own deme + migration from every deme holding h  (:2366-2367, :2410-2414)
+            double F = 0.0;
+            if (s.use_masks) {
+                unsigned cm = (unsigned)s.colmask[h] & ~(1u << p);
+                while (cm) {
+                    const int sp = __ffs(cm) - 1;
+                    cm &= cm - 1;
+                    F += eff[p * K + sp] * s.mdiag[sp] * (s.b[h] * s.I[sp * H + h]);
+                }
+            } else {
+                for (int sp = 0; sp < K; sp++) {
+                    const double Is = s.I[sp * H + h];
+                    if (sp != p && Is != 0.0) F += eff[p * K + sp] * s.mdiag[sp] * (s.b[h] * Is);
+                }
+            }
+            const double Q = s.Qm[i];
+            v = Q * F + s.c[p] * s.b[h] * Iv * Q - (s.d[h] + s.sr[h] * s.sm[p] + s.tmq[h]) * Iv;
+        }
+        // mutation inflow from the haplotypes one substitution away that are present in this deme (:2400-2401)
+        if (s.use_masks) {
+            unsigned long long nm = s.rowmask[p] & s.nbrmask[h];
+            while (nm) {
+                const int src = __ffsll((long long)nm) - 1;
+                nm &= nm - 1;
+                const int x = src ^ h;
+                const int sh = (31 - __clz(x)) & ~1;
+                const int u = U - 1 - (sh >> 1);
+                const int as = (src >> sh) & 3, hu = (h >> sh) & 3;
+                const int k = hu - (hu > as ? 1 : 0);
+                v += s.q[(src * U + u) * 3 + k] * s.I[p * H + src];
+            }
+        } else {
+            for (int u = 0; u < U; u++) {
+                const int sh = 2 * (U - u - 1);
+                const int hu = (h >> sh) & 3;
+                for (int a = 0; a < 4; a++) {
+                    if (a == hu) continue;
+                    const int src = h + ((a - hu) << sh);
+                    const double Is = s.I[p * H + src];
+                    if (Is != 0.0) v += s.q[(src * U + u) * 3 + (hu - (hu > a ? 1 : 0))] * Is;
                 }
             }
         }
-        s.dI[i] = v;
-        if (fabs(v) >= 1e-8) {
-            double x = (double)(eps * (float)s.I[i]) / 2.0;  // float product, like the reference's generated C
-            double t = (1.0 > x ? 1.0 : x) / fabs(v);
-            tmin = fmin(tmin, t);
+        if (s.store_drift) s.dI[i] = v;
+        const double av = fabs(v);
+        if (av >= 1e-8) {
+            double x = (double)(eps * (float)Iv) / 2.0;  // float product, like the reference's generated C
+            x = 1.0 > x ? 1.0 : x;
+            if (x < tmin * av) tmin = fmin(tmin, x / av);  // divide only when the candidate can lower the minimum
         }
     }
-    // susceptible drifts: one warp per (deme, group), lanes over haplotypes, fixed-order butterfly reduction
-    for (int i = tid >> 5; i < K * S; i += nt >> 5) {
-        int p = i / S, sn = i - p * S;
-        double part = 0.0, rec = 0.0;
-        for (int h = tid & 31; h < H; h += 32) {
-            int In = s.I[p * H + h];
-            double Fv = s.F[p * H + h];
-            if (In != 0 || Fv != 0.0) {
-                double Ii = (double)In;
-                part += s.sigT[sn * H + h] * (Fv + s.c[p] * s.b[h] * Ii);
-                if (s.g[h] == sn) rec += (s.d[h] + s.sr[h] * s.sm[p]) * Ii;
-            }
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            part += __shfl_xor_sync(0xffffffffu, part, o);
-            rec += __shfl_xor_sync(0xffffffffu, rec, o);
-        }
-        if ((tid & 31) == 0) {
-            double v = -(double)s.Sx[i] * part + rec;
-            for (int s2 = 0; s2 < S; s2++)
-                if (s2 != sn) v += s.T[s2 * S + sn] * (double)s.Sx[p * S + s2] - s.T[sn * S + s2] * (double)s.Sx[i];
-            s.dS[i] = v;
-            if (fabs(v) >= 1e-8) {
-                double x = (double)(eps * (float)s.Sx[i]) / 2.0;
-                double t = (1.0 > x ? 1.0 : x) / fabs(v);
-                tmin = fmin(tmin, t);
-            }
+    // ---- B2. susceptible drifts, one thread per (deme, group), taken from the END of the CTA (those threads
+    //          own one cell fewer in B1)
+    for (int i = nt - 1 - tid; i < K * S; i += nt) {
+        const int p = i / S, sn = i - p * S;
+        double phi = s.c[p] * s.Bp[i];
+        for (int sp = 0; sp < K; sp++)
+            if (sp != p) phi += eff[p * K + sp] * s.mdiag[sp] * s.Bp[sp * S + sn];
+        const double Sv = s.Sx[i];
+        double v = -Sv * phi + s.Rp[i];
+        for (int s2 = 0; s2 < S; s2++)
+            if (s2 != sn) v += s.T[s2 * S + sn] * s.Sx[p * S + s2] - s.T[sn * S + s2] * Sv;
+        if (s.store_drift) s.dS[i] = v;
+        const double av = fabs(v);
+        if (av >= 1e-8) {
+            double x = (double)(eps * (float)Sv) / 2.0;
+            x = 1.0 > x ? 1.0 : x;
+            if (x < tmin * av) tmin = fmin(tmin, x / av);
         }
     }
-    return block_min(tmin, s.red);
+    return block_min(tmin, s.red, slot);
 }
 
-// Load the parameter point and replicate state into shared memory (lists of buffer 0 are built).
+// Load the parameter point and replicate state into shared memory and build the lists.
 __device__ void load_replicate(const DevState &st, int r, const Dims &D, const TauShared &s, const double *pp,
                                const double *eff_g) {
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -339,9 +457,18 @@ __device__ void load_replicate(const DevState &st, int r, const Dims &D, const T
         s.sr[i] = pp[D.o_sr + i];
         s.tmq[i] = pp[D.o_tmq + i];
         s.g[i] = (int)pp[D.o_g + i];
+        if (s.use_masks) {
+            unsigned long long m = 0ull;
+            for (int u = 0; u < U; u++)
+                for (int a = 1; a < 4; a++) m |= 1ull << (i ^ (a << (2 * u)));
+            s.nbrmask[i] = m;
+        }
     }
     for (int i = tid; i < H * U * 3; i += nt) s.q[i] = pp[D.o_q + i];
-    for (int i = tid; i < S * H; i += nt) s.sigT[i] = pp[D.o_sigT + i];
+    for (int i = tid; i < S * H; i += nt) {
+        s.sigT[i] = pp[D.o_sigT + i];
+        s.sb[i] = pp[D.o_sigT + i] * pp[D.o_b + (i % H)];
+    }
     for (int i = tid; i < S * S; i += nt) s.T[i] = pp[D.o_T + i];
     for (int i = tid; i < K; i += nt) {
         s.sm[i] = pp[D.o_sm + i];
@@ -360,18 +487,18 @@ __device__ void load_replicate(const DevState &st, int r, const Dims &D, const T
     for (int i = tid; i < K * H; i += nt) {
         long long v = st.I[(size_t)r * K * H + i];
         if (v > 2147483647LL || v < 0) ovf = 1;
-        s.I[i] = (int)v;
+        s.I[i] = (double)v;
     }
     for (int i = tid; i < K * S; i += nt) {
         long long v = st.Sx[(size_t)r * K * S + i];
         if (v > 2147483647LL || v < 0) ovf = 1;
-        s.Sx[i] = (int)v;
+        s.Sx[i] = (double)v;
     }
     if (tid < 24) s.flags[tid] = 0;
     if (tid < 6) s.tally64[tid] = 0;
     __syncthreads();
     if (ovf) atomicOr(&s.flags[7], 1);
-    rebuild_lists(D, s, 0);
+    rebuild_lists(D, s);
 }
 
 // CheckLockdown for every deme (:2328-2329 / :449-450 / :736-737).  All threads vote whether any deme
@@ -403,6 +530,16 @@ __device__ __forceinline__ void lockdown_pass(const DevState &st, int r, const D
         }
     }
 }
+
+// Phase timing tap (variant bit 1): thread 0 of every CTA accumulates the cycles between consecutive barrier exits
+// of the leap loop, i.e. the critical path of each phase, into this buffer (read by vgsim_debug_tau_phases).
+__device__ unsigned long long g_tau_phase_cycles[16];
+#define TAU_MARK(k)                                   \
+    if (prof && tid == 0) {                           \
+        const long long now_ = clock64();             \
+        pc[k] += (unsigned long long)(now_ - tmark);  \
+        tmark = now_;                                 \
+    }
 
 struct LeapTally {
     int B, Dd, Sm, M, I, G;
@@ -440,6 +577,12 @@ __device__ __forceinline__ void wipe_leap(const Dims &D, const TauShared &s, int
     if (tid < 6) s.flags[tid] = 0;
 }
 
+// the apply pass re-accumulates the per-deme totals: clear them at the top of the leap (CheckLockdown of the
+// previous leap has consumed them by then)
+__device__ __forceinline__ void zero_totals(const Dims &D, const TauShared &s) {
+    for (int i = threadIdx.x; i < D.K; i += blockDim.x) s.tot[i] = 0;
+}
+
 // Geometry of the draws one owner makes in a leap, and of its Philox domains (word 3 of the counter).
 // An owner is an infectious cell (p,h) (id p*H+h) or deme p's SUSCCHANGE block (id K*H+p).
 //   primary block 0 of a cell : {RECOVERY, SAMPLING, total MUTATION, total out-MIGRATION}
@@ -469,16 +612,15 @@ __device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
     return g;
 }
 
-#define TAU_QCAP 1024        // slow-path queue entries per round (4 draws x 256 threads)
-#define TAU_THETA 2.0        // a mutation / out-migration group is drawn as ONE Poisson total when lam_total <= theta
+#define TAU_THETA 1.0        // a mutation / out-migration group is drawn as ONE Poisson total when lam_total <= theta
 
 // total out-migration propensity of cell (p,h): sum over targets and groups of the channel propensities,
 // factorised through Q[tp,h] = sum_s Sx[tp,s] sigma[s,h]
-__device__ __forceinline__ double mig_total(int p, int h, int Ii, const Dims &D, const TauShared &s, const double *eff) {
+__device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims &D, const TauShared &s, const double *eff) {
     double acc = 0.0;
     for (int tp = 0; tp < D.K; tp++)
         if (tp != p) acc += eff[tp * D.K + p] * s.Qm[tp * D.H + h];
-    return (double)Ii * s.b[h] * s.mdiag[p] * acc;
+    return Ii * s.b[h] * s.mdiag[p] * acc;
 }
 
 // One primary draw: nothing to do for lam == 0 (numpy's random_poisson(0) consumes no randomness either); a
@@ -486,20 +628,15 @@ __device__ __forceinline__ double mig_total(int p, int h, int Ii, const Dims &D,
 // the slow-path queue (inversion entries from the bottom, PTRS entries from the top) or, for group totals
 // that are too large to aggregate, to the expansion queues.
 __device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner, int code, const TauShared &s, int *qn) {
+    int e;
     if (lam < 10.0) {
         if ((double)hi + 1.0 <= (1.0 - lam) * 4294967296.0) return;  // U < 1-lam <= exp(-lam)  =>  0
-        int e = atomicAdd(&qn[0], 1);
-        s.qlam[e] = lam;
-        s.qhi[e] = (int)hi;
-        s.qown[e] = owner;
-        s.qcode[e] = code;
+        e = atomicAdd(&qn[0], 1);
     } else {
-        int e = TAU_QCAP - 1 - atomicAdd(&qn[1], 1);
-        s.qlam[e] = lam;
-        s.qhi[e] = (int)hi;
-        s.qown[e] = owner;
-        s.qcode[e] = code;
+        e = s.qcap - 1 - atomicAdd(&qn[1], 1);
     }
+    s.qhi[e] = (int)hi;
+    s.qoc[e] = owner | (code << 20);
 }
 
 // multinomial split of an aggregated total: n events of cell (p,h), each assigned to one channel of the
@@ -508,7 +645,7 @@ static __device__ __noinline__ void split_total(int n, int p, int h, int code, i
                                                 const double *eff, const DrawGeom &g, PhiloxCtx ctx, LeapTally &tr) {
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     const int cell = p * H + h;
-    const double Ii = (double)s.I[cell];
+    const double Ii = s.I[cell];
     ctx.dom0 = (uint32_t)(g.NBP + g.nbm + g.nbg + (code == 2 ? 0 : 1));
     uint4 w = make_uint4(0, 0, 0, 0);
     for (int e = 0; e < n; e++) {
@@ -547,7 +684,7 @@ static __device__ __noinline__ void split_total(int n, int p, int h, int code, i
                 double x2 = (x - before) * common, acc2 = 0.0;
                 int ssel = -1;
                 for (int sn = 0; sn < S; sn++) {
-                    double pr = eff[tsel * K + p] * (double)s.Sx[tsel * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
+                    double pr = eff[tsel * K + p] * s.Sx[tsel * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
                     if (pr > 0.0) {
                         ssel = sn;
                         acc2 += pr;
@@ -566,53 +703,58 @@ static __device__ __noinline__ void split_total(int n, int p, int h, int code, i
     }
 }
 
-// one slow-path queue entry: finish the Poisson draw, then write / split the count
-__device__ __forceinline__ void process_entry(int e, int *row, const Dims &D, const TauShared &s, const double *eff,
-                                              const DrawGeom &g, PhiloxCtx &ctx, LeapTally &tr) {
-    const double lam = s.qlam[e];
+// one slow-path queue entry: recompute its lambda (same expression as the primary pass), finish the Poisson
+// draw, then write / split the count
+__device__ __forceinline__ void process_entry(int e, double tau, int *row, const Dims &D, const TauShared &s,
+                                              const double *eff, const DrawGeom &g, PhiloxCtx &ctx, LeapTally &tr) {
     const uint32_t hi = (uint32_t)s.qhi[e];
-    const int owner = s.qown[e], code = s.qcode[e];
+    const int oc = s.qoc[e];
+    const int owner = oc & 0xfffff, code = oc >> 20;
     const int KH = D.K * D.H;
-    const bool cell_owned = owner < KH;
-    int blk, q;
-    if (!cell_owned) {
-        blk = code >> 2;
-        q = code & 3;
-    } else if (code < 4) {
-        blk = 0;
-        q = code;
-    } else {
-        blk = 1 + ((code - 4) >> 2);
-        q = (code - 4) & 3;
-    }
-    ctx.c0 = (uint32_t)owner;
-    ctx.dom0 = (uint32_t)blk;
-    const int n = (int)(lam < 10.0 ? poisson_inversion(lam, hi, ctx, q) : poisson_ptrs(lam, ctx, q));
-    if (n == 0) return;
     Channel ch;
-    if (!cell_owned) {
-        int c = susc_channel(owner - KH, code, D, s, ch);
-        row[c] = n;
-        book(ch, n, s, tr);
+    ctx.c0 = (uint32_t)owner;
+    if (owner >= KH) {  // SUSCCHANGE channel `code` of deme owner - KH
+        const int c = susc_channel(owner - KH, code, D, s, ch);
+        const double lam = ch.prop * tau;
+        ctx.dom0 = (uint32_t)(code >> 2);
+        const int n = (int)(lam < 10.0 ? poisson_inversion(lam, hi, ctx, code & 3) : poisson_ptrs(lam, ctx, code & 3));
+        if (n != 0) {
+            row[c] = n;
+            book(ch, n, s, tr);
+        }
         return;
     }
     const int p = owner >> D.hshift, h = owner & (D.H - 1);
-    if (code == 2 || code == 3) {
-        split_total(n, p, h, code, row, D, s, eff, g, ctx, tr);
+    if (code == 2 || code == 3) {  // aggregated total of the mutation / out-migration group (lambda <= theta < 10)
+        const double Ii = s.I[owner];
+        const double lam = code == 2 ? s.tmq[h] * Ii * tau : mig_total(p, h, Ii, D, s, eff) * tau;
+        ctx.dom0 = 0u;
+        const int n = (int)poisson_inversion(lam, hi, ctx, code);
+        if (n != 0) split_total(n, p, h, code, row, D, s, eff, g, ctx, tr);
         return;
     }
     const int l = code == 0 ? 0 : code == 1 ? 1 : 2 + 3 * D.U + (code - 4);
-    int c = cell_channel(p, h, l, D, s, eff, ch);
-    row[c] = n;
-    book(ch, n, s, tr);
+    const int c = cell_channel(p, h, l, D, s, eff, ch);
+    const double lam = ch.prop * tau;
+    const int blk = code < 4 ? 0 : 1 + ((code - 4) >> 2), q = code < 4 ? code : (code - 4) & 3;
+    ctx.dom0 = (uint32_t)blk;
+    const int n = (int)(lam < 10.0 ? poisson_inversion(lam, hi, ctx, q) : poisson_ptrs(lam, ctx, q));
+    if (n != 0) {
+        row[c] = n;
+        book(ch, n, s, tr);
+    }
 }
 
-__global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
+template <int NT, int OCC>
+__global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
                                                      const __grid_constant__ TauShared s, const int variant) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S;
     const int tid = threadIdx.x, nt = blockDim.x;
     const DrawGeom g = draw_geom(D);
+    const bool prof = (variant & 2) != 0;
+    unsigned long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tmark = 0;
 
     for (int r = blockIdx.x; r < st.R; r += gridDim.x) {
         const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
@@ -626,7 +768,6 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
             if (tid == 0) st.err[r] |= ERR_COUNT_OVERFLOW;
             continue;
         }
-        int cb = 0;          // list buffer describing the current state
         unsigned rnd = 0;    // draw-round parity: which pair of queue counters is live
         bool restarted = false;
         long long sC = ctr[C_S];
@@ -636,21 +777,29 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
         long long good_attempt = ctr[C_GOOD];
         const long long ev_limit = evptr + a.iterations;  // events.ptr < events.size (:2312), intended capacity
         int *tau_counts = st.tau_counts + (size_t)r * st.leap_cap * D.Pp;
+        bool lists_ready = true;  // false: segcnt is current but act/dstart/masks still have to be written
 
         for (long long attempt = 0; attempt < a.attempts; attempt++) {
             epoch++;
-            if (s.flags[8 + cb] != 0) {
+            if (s.flags[8] != 0) {
                 while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
                        (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
                     int *row = tau_counts + (size_t)leaps * D.Pp;
-                    const int nb = cb ^ 1;
-                    // ---- 0. zero-fill the dense row; clear the per-leap deltas and the next list buffer
+                    if (prof && tid == 0) tmark = clock64();
+                    // ---- 0. zero-fill the dense row, clear the per-leap deltas, finish the cell lists of the
+                    //         state the previous leap left, Q[p,h]
                     wipe_leap(D, s, row);
-                    zero_lists(D, s, nb);
-                    // ---- 1-2. drifts and tau (its barriers also order the zero-fill before the scatter below)
-                    double tau = drifts_and_tau(D, s, eff, cb);
-                    const int nAct = s.flags[8 + cb];
-                    const int *act = s.act[cb];
+                    zero_totals(D, s);
+                    if (!lists_ready) write_lists(D, s);
+                    lists_ready = true;
+                    q_pass(D, s);
+                    __syncthreads();
+                    TAU_MARK(0)
+                    // ---- 1-2. drifts and tau (the barriers also order the zero-fill before the scatter below)
+                    double tau = drifts_and_tau(D, s, eff, (int)leaps);
+                    TAU_MARK(1)
+                    const int nAct = s.flags[8];
+                    const int *act = s.act;
                     // ---- 3. draw; halve tau and redraw on an infeasible leap (:2316-2321)
                     for (unsigned retry = 0;; retry++) {
                         LeapTally tr;
@@ -669,18 +818,18 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                                 const int ai = item / g.NB1, blk = item - ai * g.NB1;
                                 const int cell = act[ai];
                                 const int p = cell >> D.hshift, h = cell & (H - 1);
-                                const int Ii = s.I[cell];
+                                const double Ii = s.I[cell];
                                 double lam[4];
                                 if (blk == 0) {
-                                    lam[0] = s.d[h] * (double)Ii * tau;
-                                    lam[1] = s.sr[h] * (double)Ii * s.sm[p] * tau;
-                                    lam[2] = s.tmq[h] * (double)Ii * tau;
+                                    lam[0] = s.d[h] * Ii * tau;
+                                    lam[1] = s.sr[h] * Ii * s.sm[p] * tau;
+                                    lam[2] = s.tmq[h] * Ii * tau;
                                     lam[3] = K > 1 ? mig_total(p, h, Ii, D, s, eff) * tau : 0.0;
-                                    if (lam[2] > 0.0 && (variant == 1 || lam[2] > TAU_THETA)) {
+                                    if (lam[2] > 0.0 && ((variant & 1) || lam[2] > TAU_THETA)) {
                                         s.xq[atomicAdd(&qn[2], 1)] = cell;
                                         lam[2] = 0.0;
                                     }
-                                    if (lam[3] > 0.0 && (variant == 1 || lam[3] > TAU_THETA)) {
+                                    if (lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA)) {
                                         s.xq[nt + atomicAdd(&qn[3], 1)] = cell;
                                         lam[3] = 0.0;
                                     }
@@ -688,7 +837,7 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
 #pragma unroll
                                     for (int q = 0; q < 4; q++) {
                                         const int sn = (blk - 1) * 4 + q;
-                                        lam[q] = sn < S ? s.b[h] * s.sigT[sn * H + h] * s.c[p] * (double)s.Sx[p * S + sn] * (double)Ii * tau
+                                        lam[q] = sn < S ? s.b[h] * s.sigT[sn * H + h] * s.c[p] * s.Sx[p * S + sn] * Ii * tau
                                                         : 0.0;
                                     }
                                 }
@@ -727,48 +876,45 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                                 }
                             }
                             __syncthreads();
-                            // ---- 3b. drain: slow-path draws (inversion from the bottom, PTRS from the top of the
-                            //          queue, so the two kinds sit in different warps), then the expanded groups
+                            TAU_MARK(2)
+                            // ---- 3b. drain.  The round's critical path is its slowest warp, so the three kinds of
+                            //          slow work go to different warps and every unit gets its own thread:
+                            //          inversion entries from thread 0 up, PTRS entries from the last thread
+                            //          down, the channels of expanded groups from the first warp after the
+                            //          inversion entries (one CHANNEL per thread; its Philox block is shared
+                            //          by 4 channels, each thread recomputes it and keeps its own word)
                             const int ninv = qn[0], nptr = qn[1], nxm = qn[2], nxg = qn[3];
                             if (tid < 4) s.flags[12 + 4 * ((rnd + 1) & 1) + tid] = 0;
-                            for (int e = tid; e < ninv; e += nt) process_entry(e, row, D, s, eff, g, ctx, tr);
-                            for (int k = nt - 1 - tid; k < nptr; k += nt) process_entry(TAU_QCAP - 1 - k, row, D, s, eff, g, ctx, tr);
-                            const int itM = nxm * g.nbm, itX = itM + nxg * g.nbg;
-                            for (int it = tid; it < itX; it += nt) {
-                                int owner, b, lbase, lend, domb;
-                                if (it < itM) {
-                                    const int xi = it / g.nbm;
-                                    b = it - xi * g.nbm;
-                                    owner = s.xq[xi];
-                                    lbase = 2;
-                                    lend = 2 + 3 * D.U;
-                                    domb = g.NBP + b;
-                                } else {
-                                    const int it2 = it - itM, xi = it2 / g.nbg;
-                                    b = it2 - xi * g.nbg;
-                                    owner = s.xq[nt + xi];
-                                    lbase = D.E;
-                                    lend = g.LC;
-                                    domb = g.NBP + g.nbm + b;
-                                }
-                                const int p = owner >> D.hshift, h = owner & (H - 1);
-                                ctx.c0 = (uint32_t)owner;
-                                ctx.dom0 = (uint32_t)domb;
-                                uint4 w = make_uint4(0, 0, 0, 0);
-                                bool have_w = false;
-#pragma unroll 1
-                                for (int q = 0; q < 4; q++) {
-                                    const int l = lbase + 4 * b + q;
-                                    if (l >= lend) break;
+                            for (int e = tid; e < ninv; e += nt) process_entry(e, tau, row, D, s, eff, g, ctx, tr);
+                            for (int k = nt - 1 - tid; k < nptr; k += nt) process_entry(s.qcap - 1 - k, tau, row, D, s, eff, g, ctx, tr);
+                            const int nchM = 3 * D.U, nchG = (K - 1) * S;
+                            const int itM = nxm * nchM, itX = itM + nxg * nchG;
+                            if (itX > 0) {
+                                const int first = (ninv + 31) & ~31 & (nt - 1);
+                                for (int it = (tid - first) & (nt - 1); it < itX; it += nt) {
+                                    int owner, lc, lbase, domb;
+                                    if (it < itM) {
+                                        const int xi = it / nchM;
+                                        lc = it - xi * nchM;
+                                        owner = s.xq[xi];
+                                        lbase = 2;
+                                        domb = g.NBP;
+                                    } else {
+                                        const int it2 = it - itM, xi = it2 / nchG;
+                                        lc = it2 - xi * nchG;
+                                        owner = s.xq[nt + xi];
+                                        lbase = D.E;
+                                        domb = g.NBP + g.nbm;
+                                    }
+                                    const int p = owner >> D.hshift, h = owner & (H - 1);
                                     Channel ch;
-                                    const int c = cell_channel(p, h, l, D, s, eff, ch);
+                                    const int c = cell_channel(p, h, lbase + lc, D, s, eff, ch);
                                     const double lam = ch.prop * tau;
                                     if (lam > 0.0) {
-                                        if (!have_w) {
-                                            w = ctx.draw(0u);
-                                            have_w = true;
-                                        }
-                                        const int n = (int)poisson_draw(lam, pick_word(w, q), ctx, q);
+                                        ctx.c0 = (uint32_t)owner;
+                                        ctx.dom0 = (uint32_t)(domb + (lc >> 2));
+                                        const uint4 w = ctx.draw(0u);
+                                        const int n = (int)poisson_draw(lam, pick_word(w, lc & 3), ctx, lc & 3);
                                         if (n != 0) {
                                             row[c] = n;
                                             book(ch, n, s, tr);
@@ -776,15 +922,16 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                                     }
                                 }
                             }
+                            if (tr.B) atomicAdd(&s.flags[EV_BIRTH], tr.B);
+                            if (tr.Dd) atomicAdd(&s.flags[EV_DEATH], tr.Dd);
+                            if (tr.Sm) atomicAdd(&s.flags[EV_SAMPLING], tr.Sm);
+                            if (tr.M) atomicAdd(&s.flags[EV_MUTATION], tr.M);
+                            if (tr.I) atomicAdd(&s.flags[EV_SUSCCHANGE], tr.I);
+                            if (tr.G) atomicAdd(&s.flags[EV_MIGRATION], tr.G);
+                            tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
                             __syncthreads();
+                            TAU_MARK(3)
                         }
-                        if (tr.B) atomicAdd(&s.flags[EV_BIRTH], tr.B);
-                        if (tr.Dd) atomicAdd(&s.flags[EV_DEATH], tr.Dd);
-                        if (tr.Sm) atomicAdd(&s.flags[EV_SAMPLING], tr.Sm);
-                        if (tr.M) atomicAdd(&s.flags[EV_MUTATION], tr.M);
-                        if (tr.I) atomicAdd(&s.flags[EV_SUSCCHANGE], tr.I);
-                        if (tr.G) atomicAdd(&s.flags[EV_MIGRATION], tr.G);
-                        __syncthreads();
                         // feasibility (:2522-2528).  The reference books migration arrivals on the SOURCE cell
                         // (quirk Q8), so its test can pass while the cell that is really depleted goes negative;
                         // from then on every redraw fails and the reference halves tau forever.  Here a leap must
@@ -792,15 +939,16 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                         int bad = 0;
                         for (int i = tid; i < K * H; i += nt) {
                             const double sz = s.sizeD[i >> D.hshift];
-                            double v = (double)s.I[i] + (double)s.chkI[i];
-                            double u = (double)s.I[i] + (double)s.updI[i];
+                            const double v = s.I[i] + (double)s.chkI[i];
+                            const double u = s.I[i] + (double)s.updI[i];
                             if (v < 0.0 || v > sz || u < 0.0 || u > sz) bad = 1;
                         }
                         for (int i = tid; i < K * S; i += nt) {
-                            double v = (double)s.Sx[i] + (double)s.dSx[i];
+                            const double v = s.Sx[i] + (double)s.dSx[i];
                             if (v < 0.0 || v > s.sizeD[i / S]) bad = 1;
                         }
                         bad = __syncthreads_or(bad);
+                        TAU_MARK(4)
                         if (!bad) break;
                         tau *= 0.5;
                         wipe_leap(D, s, row);  // rare path
@@ -811,13 +959,16 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                             break;
                         }
                     }
-                    // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) and rebuild the cell list
+                    // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593); per-deme totals; first pass of the
+                    //         ordered cell compaction (the second pass runs at the top of the next leap)
                     for (int i = tid; i < K * H; i += nt) {
-                        int v = s.I[i] + s.updI[i];
+                        const double v = s.I[i] + (double)s.updI[i];
                         s.I[i] = v;
-                        list_cell(D, s, nb, i, v);
+                        if (v != 0.0) atomicAdd(&s.tot[i >> D.hshift], (int)v);
                     }
-                    for (int i = tid; i < K * S; i += nt) s.Sx[i] += s.dSx[i];
+                    for (int i = tid; i < K * S; i += nt) s.Sx[i] += (double)s.dSx[i];
+                    count_cells(D, s);
+                    lists_ready = false;
                     t += tau;
                     sC += s.flags[EV_SAMPLING];  // sCounter gates the loop (:2312): exact per leap
                     if (tid < 6) s.tally64[tid] += s.flags[tid];
@@ -830,11 +981,16 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                     }
                     leaps++;
                     evptr++;
-                    cb = nb;
                     __syncthreads();
+                    TAU_MARK(5)
                     // ---- extinction test and CheckLockdown for every deme (:2326-2329)
-                    if (s.flags[8 + cb] == 0) break;
-                    lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot[cb]);
+                    const int alive = total_cells(s);
+                    if (tid == 0) s.flags[8] = alive;  // (every thread computed the same value; nobody reads it before
+                                                       //  the next barrier)
+                    if (alive == 0) break;
+                    lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot);
+                    TAU_MARK(6)
+                    if (prof && tid == 0) pc[7] += 1;
                 }
             }
             // ---- extinction-retry (:2331-2335): <= 100 log rows with iterations > 100 => Restart (:714-738)
@@ -846,10 +1002,11 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
                 restarted = true;
                 __syncthreads();
                 if (tid < 6) s.tally64[tid] = 0;
-                for (int i = tid; i < K * H; i += nt) s.I[i] = (int)st.initI[(size_t)r * K * H + i];
-                for (int i = tid; i < K * S; i += nt) s.Sx[i] = (int)st.initSx[(size_t)r * K * S + i];
-                rebuild_lists(D, s, cb);
-                lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot[cb]);
+                for (int i = tid; i < K * H; i += nt) s.I[i] = (double)st.initI[(size_t)r * K * H + i];
+                for (int i = tid; i < K * S; i += nt) s.Sx[i] = (double)st.initSx[(size_t)r * K * S + i];
+                rebuild_lists(D, s);
+                lists_ready = true;
+                lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot);
                 __syncthreads();
                 good_attempt = 0;
                 if (tid == 0) ctr[C_MIGN] = 0;
@@ -861,8 +1018,8 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
 
         // ---- commit the replicate back to HBM
         __syncthreads();
-        for (int i = tid; i < K * H; i += nt) st.I[(size_t)r * K * H + i] = s.I[i];
-        for (int i = tid; i < K * S; i += nt) st.Sx[(size_t)r * K * S + i] = s.Sx[i];
+        for (int i = tid; i < K * H; i += nt) st.I[(size_t)r * K * H + i] = (long long)s.I[i];
+        for (int i = tid; i < K * S; i += nt) st.Sx[(size_t)r * K * S + i] = (long long)s.Sx[i];
         for (int i = tid; i < K; i += nt) {
             st.cd[(size_t)r * K + i] = s.cd[i];
             st.ceff[(size_t)r * K + i] = s.c[i];
@@ -880,13 +1037,15 @@ __global__ void __launch_bounds__(256, 3) tau_kernel(const __grid_constant__ Dev
             ctr[C_EVPTR] = evptr;
             ctr[C_LEAPS] = leaps;
             long long ginf = 0;
-            for (int p = 0; p < K; p++) ginf += s.tot[cb][p];
+            for (int i = 0; i < K * H; i++) ginf += (long long)s.I[i];
             ctr[C_GINF] = ginf;
             st.time[r] = t;
             st.epoch[r] = epoch;
         }
         __syncthreads();
     }
+    if (prof && tid == 0)
+        for (int k = 0; k < 8; k++) atomicAdd(&g_tau_phase_cycles[k], pc[k]);
 }
 
 // Deterministic parity tap: propensities of the current state in positional order, drifts and tau.
@@ -898,6 +1057,8 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
     const double *eff_g = st.eff + (size_t)r * D.K * D.K;
     load_replicate(st, r, D, s, pp, eff_g);
     const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
+    q_pass(D, s);
+    __syncthreads();
     double tau = drifts_and_tau(D, s, eff, 0);
     for (int c = threadIdx.x; c < D.P; c += blockDim.x) {
         Channel ch;
@@ -911,24 +1072,50 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
 }
 
 // host launchers ---------------------------------------------------------------------------------
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
-    const TauShared lay = tau_layout(st.D);
+template <int NT, int OCC>
+static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant,
+                                  int ctas_cap) {
+    const TauShared lay = tau_layout(st.D, false, NT);
     size_t smem = (size_t)lay.bytes;
-    cudaError_t e = cudaFuncSetAttribute(tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tau_kernel<NT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel<NT, OCC>, NT, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (ctas_cap > 0 && per_sm > ctas_cap) per_sm = ctas_cap;
     int grid = num_sms * per_sm;
     if (grid > st.R) grid = st.R;
-    tau_kernel<<<grid, 256, smem, stream>>>(st, a, lay, variant);
+    tau_kernel<NT, OCC><<<grid, NT, smem, stream>>>(st, a, lay, variant);
     return cudaGetLastError();
+}
+
+// Builds of the same kernel with different CTA sizes / register budgets.  VGSIM_TAU_CFG = "<threads>x<ctas per SM>"
+// overrides the default for A/B measurements (e.g. 256x3, 256x4, 512x2, 1024x1; a smaller second number caps
+// the resident CTAs below what the build allows).
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
+    if ((long long)st.D.K * st.D.H + st.D.K >= (1 << 20)) return cudaErrorInvalidValue;  // owner id is packed in 20 bits
+    int nt = 256, occ = 3;
+    if (const char *e = getenv("VGSIM_TAU_CFG")) sscanf(e, "%dx%d", &nt, &occ);
+    if (nt >= 1024) return launch_tau_cfg<1024, 1>(st, a, stream, num_sms, variant, occ);
+    if (nt >= 512) return launch_tau_cfg<512, 2>(st, a, stream, num_sms, variant, occ);
+    if (occ >= 5) return launch_tau_cfg<256, 5>(st, a, stream, num_sms, variant, occ);
+    if (occ == 4) return launch_tau_cfg<256, 4>(st, a, stream, num_sms, variant, occ);
+    return launch_tau_cfg<256, 3>(st, a, stream, num_sms, variant, occ);
+}
+
+cudaError_t tau_phase_cycles(unsigned long long *out16, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out16, g_tau_phase_cycles, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[16] = {0};
+        e = cudaMemcpyToSymbol(g_tau_phase_cycles, z, sizeof(z));
+    }
+    return e;
 }
 
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream) {
-    const TauShared lay = tau_layout(st.D);
+    const TauShared lay = tau_layout(st.D, true);
     size_t smem = (size_t)lay.bytes;
     cudaError_t e = cudaFuncSetAttribute(propensity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
