@@ -9,5 +9,5 @@ echo "bench exit $?" >> gpurun_out/bench.err
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tau_kernel -s 1 -c 1 -o gpurun_out/prof_tau \
-    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --replicates 1776 --leaps 16 > gpurun_out/bench_ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 1 --no-cpu-baseline --replicates 2368 --leaps 16 > gpurun_out/bench_ncu_full.log 2>&1
 tail -5 gpurun_out/pytest_gpu.log; cat gpurun_out/bench.log; tail -5 gpurun_out/bench.err

@@ -41,12 +41,53 @@ namespace vg {
 
 extern __shared__ __align__(16) unsigned char smem_raw[];
 
+// ---- teams ------------------------------------------------------------------------------------------
+// A CTA is blockDim.y TEAMS of blockDim.x = 256 threads; every team simulates its own replicate with its own
+// slice of the dynamic shared memory and its own named barrier, so threadIdx.x / blockDim.x are team-local and
+// the per-replicate control flow stays independent.  All teams of the SM re-align at the top of every leap
+// (align_teams): they then walk the same code at the same time, so an instruction line fetched from L2 by one
+// team is found in the SM's instruction cache by the others.  The leap loop is far larger than the 32 KB L1.5
+// instruction cache, and with independent CTAs the kernel was bound by instruction fetch (ncu: icc hit rate
+// 59 %, gcc instruction requests 84 % of peak, every phase costing ~300 cycles per 128-byte code line).
+#define TAU_TEAM 256
+#define TAU_ZB 16384      // zero buffer (bytes) at the start of the CTA tail: source of the bulk row wipes
+#define TAU_CTA_TAIL (TAU_ZB + 16)  // bytes after the team slices: zero buffer, then [0] = number of finished teams
+
+__device__ __forceinline__ unsigned dyn_smem_bytes() {
+    unsigned v;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(v));
+    return v;
+}
+__device__ __forceinline__ unsigned team_stride() { return (dyn_smem_bytes() - TAU_CTA_TAIL) / blockDim.y; }
+__device__ __forceinline__ unsigned char *team_base() { return smem_raw + threadIdx.y * team_stride(); }
+__device__ __forceinline__ unsigned char *zero_buf() { return smem_raw + (dyn_smem_bytes() - TAU_CTA_TAIL); }
+__device__ __forceinline__ int *cta_tail() { return reinterpret_cast<int *>(smem_raw + (dyn_smem_bytes() - 16)); }
+__device__ __forceinline__ void team_sync() { asm volatile("bar.sync %0, %1;" ::"r"(2 + (int)threadIdx.y), "r"(TAU_TEAM) : "memory"); }
+__device__ __forceinline__ int team_or(int pred) {
+    int r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.s32 q, %1, 0;\n\tbar.red.or.pred p, %2, %3, q;\n\tselp.s32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"(pred), "r"(2 + (int)threadIdx.y), "r"(TAU_TEAM)
+        : "memory");
+    return r;
+}
+// barrier 1: every thread of the CTA (running teams at the top of a leap, finished teams in their idle loop)
+__device__ __forceinline__ void align_teams() {
+    asm volatile("bar.sync 1, %0;" ::"r"((int)(blockDim.x * blockDim.y)) : "memory");
+}
+struct TeamGroup {
+    __device__ __forceinline__ int tid() const { return threadIdx.x; }
+    __device__ __forceinline__ int size() const { return blockDim.x; }
+    __device__ __forceinline__ void sync() const { team_sync(); }
+};
+
 // A shared-memory array addressed by a 32-bit byte offset from the dynamic shared-memory base: keeps the
 // ~30 array handles of TauShared in one register each and lets the compiler emit LDS/STS/ATOMS directly.
 template <class T>
 struct SArr {
     int off;
-    __device__ __forceinline__ T *ptr() const { return reinterpret_cast<T *>(smem_raw + off); }
+    __device__ __forceinline__ T *ptr() const { return reinterpret_cast<T *>(team_base() + off); }
     __device__ __forceinline__ T &operator[](int i) const { return ptr()[i]; }
     __device__ __forceinline__ operator T *() const { return ptr(); }
 };
@@ -237,7 +278,7 @@ __device__ __forceinline__ double block_min(double v, double *red, int slot) {
     const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     double *r = red + 32 * (slot & 1);
     if ((threadIdx.x & 31) == 0) r[w] = v;
-    __syncthreads();
+    align_teams();  // generation barrier 4 of 5 (see tau_kernel)
     v = r[0];
     for (int i = 1; i < nw; i++) v = fmin(v, r[i]);
     return v;
@@ -309,16 +350,16 @@ __device__ __forceinline__ void write_lists(const Dims &D, const TauShared &s) {
 // full rebuild from s.I (load, Restart): leaves tot[] too
 __device__ void rebuild_lists(const Dims &D, const TauShared &s) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    __syncthreads();
+    team_sync();
     for (int i = tid; i < D.K; i += nt) s.tot[i] = 0;
     count_cells(D, s);
-    __syncthreads();
+    team_sync();
     for (int i = tid; i < D.K * D.H; i += nt) {
         const double v = s.I[i];
         if (v != 0.0) atomicAdd(&s.tot[i >> D.hshift], (int)v);
     }
     write_lists(D, s);
-    __syncthreads();
+    team_sync();
 }
 
 // Q[p,h] = sum_s Sx[p,s] sigma[s,h] for every cell (needs only Sx; runs before the list barrier)
@@ -364,7 +405,7 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
             s.Rp[task] = Rv;
         }
     }
-    __syncthreads();
+    align_teams();  // generation barrier 3 of 5
     double tmin = 1.0;
     const float eps = 0.03f;
     // ---- B1. infectious drifts, one thread per cell
@@ -496,7 +537,7 @@ __device__ void load_replicate(const DevState &st, int r, const Dims &D, const T
     }
     if (tid < 24) s.flags[tid] = 0;
     if (tid < 6) s.tally64[tid] = 0;
-    __syncthreads();
+    team_sync();
     if (ovf) atomicOr(&s.flags[7], 1);
     rebuild_lists(D, s);
 }
@@ -511,7 +552,7 @@ __device__ __forceinline__ void lockdown_pass(const DevState &st, int r, const D
         double ti = (double)tot[p];
         if ((ti > s.startN[p] && s.lock[p] == 0) || (ti < s.endN[p] && s.lock[p] == 1)) pred = 1;
     }
-    if (!__syncthreads_or(pred)) return;
+    if (!team_or(pred)) return;
     if (threadIdx.x == 0) {
         int flips = 0;
         for (int p = 0; p < D.K; p++)
@@ -521,12 +562,12 @@ __device__ __forceinline__ void lockdown_pass(const DevState &st, int r, const D
         s.flags[6] = flips;
         s.flags[10] += flips;
     }
-    __syncthreads();
+    team_sync();
     if (s.flags[6]) {
-        update_contact_rates(BlockGroup(), D, pp, s.cd, eff_g, s.c, s.maxEBM);
+        update_contact_rates(TeamGroup(), D, pp, s.cd, eff_g, s.c, s.maxEBM);
         if (s.has_effS) {
             for (int i = threadIdx.x; i < D.K * D.K; i += blockDim.x) s.effS[i] = eff_g[i];
-            __syncthreads();
+            team_sync();
         }
     }
 }
@@ -565,10 +606,25 @@ __device__ __forceinline__ void book(const Channel &ch, int n, const TauShared &
     else t.I += n;
 }
 
+// Zero-fill of a dense log row by the TMA engine: thread 0 of the team issues shared->global bulk copies out
+// of the CTA's zero buffer (no LSU store instructions, no registers, the SM keeps computing); the writes are
+// complete once wipe_wait() returns, which the team calls before the first count is scattered into the row.
+__device__ __forceinline__ void wipe_row_async(int *row, int bytes) {
+    const unsigned src = (unsigned)__cvta_generic_to_shared(zero_buf());
+    unsigned long long dst = (unsigned long long)(uintptr_t)row;
+    asm volatile("fence.proxy.async;" ::: "memory");  // earlier generic-proxy stores to this row (a failed draw) stay before the wipe
+    for (int off = 0; off < bytes; off += TAU_ZB) {
+        const int n = bytes - off < TAU_ZB ? bytes - off : TAU_ZB;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src), "r"(n) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void wipe_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // clear everything a (re)draw of the leap accumulates into: the dense row, the deltas, the type tallies
 __device__ __forceinline__ void wipe_leap(const Dims &D, const TauShared &s, int *row) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    for (int i = tid; i < D.Pp / 4; i += nt) reinterpret_cast<int4 *>(row)[i] = make_int4(0, 0, 0, 0);
+    if (tid == 0) wipe_row_async(row, D.Pp * 4);
     for (int i = tid; i < D.K * D.H; i += nt) {
         s.chkI[i] = 0;
         s.updI[i] = 0;
@@ -745,8 +801,8 @@ __device__ __forceinline__ void process_entry(int e, double tau, int *row, const
     }
 }
 
-template <int NT, int OCC>
-__global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
+template <int TEAMS>
+__global__ void __launch_bounds__(TAU_TEAM * TEAMS, 1) tau_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
                                                      const __grid_constant__ TauShared s, const int variant) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S;
@@ -756,12 +812,17 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
     unsigned long long pc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark = 0;
 
-    for (int r = blockIdx.x; r < st.R; r += gridDim.x) {
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < TAU_ZB / 16; i += blockDim.x * blockDim.y)
+        reinterpret_cast<int4 *>(zero_buf())[i] = make_int4(0, 0, 0, 0);
+    if (threadIdx.x == 0 && threadIdx.y == 0) cta_tail()[0] = 0;
+    __syncthreads();  // barrier 0, once: zero buffer and tail are initialised before any team uses them
+    if (tid == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
+    for (int r = blockIdx.x * blockDim.y + threadIdx.y; r < st.R; r += gridDim.x * blockDim.y) {
         const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
         double *eff_g = st.eff + (size_t)r * K * K;
         long long *ctr = st.counters + (size_t)r * NCOUNT;
         const uint64_t seed = st.seeds[r];
-        __syncthreads();
+        team_sync();
         load_replicate(st, r, D, s, pp, eff_g);
         const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
         if (s.flags[7]) {
@@ -785,6 +846,11 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                 while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
                        (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
                     int *row = tau_counts + (size_t)leaps * D.Pp;
+                    // A leap is one GENERATION of the CTA: every team passes exactly five CTA-wide barriers (here, after
+                    // Q, after the pressure sums, inside the tau minimum, after the apply pass), so all teams of the SM
+                    // enter every long phase together and share its instruction fetch.  The barriers inside the
+                    // variable-trip loops (draw rounds, tau halving) stay team-local.
+                    align_teams();  // generation barrier 1 of 5
                     if (prof && tid == 0) tmark = clock64();
                     // ---- 0. zero-fill the dense row, clear the per-leap deltas, finish the cell lists of the
                     //         state the previous leap left, Q[p,h]
@@ -793,7 +859,7 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                     if (!lists_ready) write_lists(D, s);
                     lists_ready = true;
                     q_pass(D, s);
-                    __syncthreads();
+                    align_teams();  // generation barrier 2 of 5
                     TAU_MARK(0)
                     // ---- 1-2. drifts and tau (the barriers also order the zero-fill before the scatter below)
                     double tau = drifts_and_tau(D, s, eff, (int)leaps);
@@ -875,7 +941,8 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                                     if (lam[3] > 0.0) primary_draw(lam[3], w.w, K * H + p, j * 4 + 3, s, qn);
                                 }
                             }
-                            __syncthreads();
+                            if (tid == 0) wipe_wait();  // the row is zero in HBM/L2 before any count is scattered into it
+                            team_sync();
                             TAU_MARK(2)
                             // ---- 3b. drain.  The round's critical path is its slowest warp, so the three kinds of
                             //          slow work go to different warps and every unit gets its own thread:
@@ -929,7 +996,7 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                             if (tr.I) atomicAdd(&s.flags[EV_SUSCCHANGE], tr.I);
                             if (tr.G) atomicAdd(&s.flags[EV_MIGRATION], tr.G);
                             tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
-                            __syncthreads();
+                            team_sync();
                             TAU_MARK(3)
                         }
                         // feasibility (:2522-2528).  The reference books migration arrivals on the SOURCE cell
@@ -947,12 +1014,12 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                             const double v = s.Sx[i] + (double)s.dSx[i];
                             if (v < 0.0 || v > s.sizeD[i / S]) bad = 1;
                         }
-                        bad = __syncthreads_or(bad);
+                        bad = team_or(bad);
                         TAU_MARK(4)
                         if (!bad) break;
                         tau *= 0.5;
                         wipe_leap(D, s, row);  // rare path
-                        __syncthreads();
+                        team_sync();
                         if (retry >= 80) {  // tau * 2^-80: nothing can fire any more, yet the state fails the test
                             if (tid == 0) st.err[r] |= ERR_TAU_STUCK;
                             tau = 0.0;
@@ -981,7 +1048,7 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                     }
                     leaps++;
                     evptr++;
-                    __syncthreads();
+                    align_teams();  // generation barrier 5 of 5
                     TAU_MARK(5)
                     // ---- extinction test and CheckLockdown for every deme (:2326-2329)
                     const int alive = total_cells(s);
@@ -1000,14 +1067,14 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
                 sC = 0;
                 t = 0.0;
                 restarted = true;
-                __syncthreads();
+                team_sync();
                 if (tid < 6) s.tally64[tid] = 0;
                 for (int i = tid; i < K * H; i += nt) s.I[i] = (double)st.initI[(size_t)r * K * H + i];
                 for (int i = tid; i < K * S; i += nt) s.Sx[i] = (double)st.initSx[(size_t)r * K * S + i];
                 rebuild_lists(D, s);
                 lists_ready = true;
                 lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot);
-                __syncthreads();
+                team_sync();
                 good_attempt = 0;
                 if (tid == 0) ctr[C_MIGN] = 0;
             } else {
@@ -1017,7 +1084,8 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
         }
 
         // ---- commit the replicate back to HBM
-        __syncthreads();
+        if (tid == 0) wipe_wait();
+        team_sync();
         for (int i = tid; i < K * H; i += nt) st.I[(size_t)r * K * H + i] = (long long)s.I[i];
         for (int i = tid; i < K * S; i += nt) st.Sx[(size_t)r * K * S + i] = (long long)s.Sx[i];
         for (int i = tid; i < K; i += nt) {
@@ -1042,10 +1110,23 @@ __global__ void __launch_bounds__(NT, OCC) tau_kernel(const __grid_constant__ De
             st.time[r] = t;
             st.epoch[r] = epoch;
         }
-        __syncthreads();
+        team_sync();
     }
     if (prof && tid == 0)
         for (int k = 0; k < 8; k++) atomicAdd(&g_tau_phase_cycles[k], pc[k]);
+    // ---- this team is out of replicates: keep answering the generation barriers until every team is.  A team
+    // announces itself between barrier 5 of its last generation and barrier 1 of the next; the counter is read
+    // between barriers 1 and 2, where no announcement can be in flight, so all teams take the same decision.
+    team_sync();
+    if (tid == 0) atomicAdd(&cta_tail()[0], 1);
+    for (;;) {
+        align_teams();
+        if (*(volatile int *)cta_tail() >= (int)blockDim.y) break;
+        align_teams();
+        align_teams();
+        align_teams();
+        align_teams();
+    }
 }
 
 // Deterministic parity tap: propensities of the current state in positional order, drifts and tau.
@@ -1058,7 +1139,7 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
     load_replicate(st, r, D, s, pp, eff_g);
     const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
     q_pass(D, s);
-    __syncthreads();
+    team_sync();
     double tau = drifts_and_tau(D, s, eff, 0);
     for (int c = threadIdx.x; c < D.P; c += blockDim.x) {
         Channel ch;
@@ -1072,36 +1153,39 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
 }
 
 // host launchers ---------------------------------------------------------------------------------
-template <int NT, int OCC>
+template <int TEAMS>
 static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant,
                                   int ctas_cap) {
-    const TauShared lay = tau_layout(st.D, false, NT);
-    size_t smem = (size_t)lay.bytes;
-    cudaError_t e = cudaFuncSetAttribute(tau_kernel<NT, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const TauShared lay = tau_layout(st.D, false, TAU_TEAM);
+    const size_t stride = ((size_t)lay.bytes + 15) & ~(size_t)15;
+    const size_t smem = stride * TEAMS + TAU_CTA_TAIL;
+    cudaError_t e = cudaFuncSetAttribute(tau_kernel<TEAMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel<NT, OCC>, NT, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tau_kernel<TEAMS>, TAU_TEAM * TEAMS, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     if (ctas_cap > 0 && per_sm > ctas_cap) per_sm = ctas_cap;
     int grid = num_sms * per_sm;
-    if (grid > st.R) grid = st.R;
-    tau_kernel<NT, OCC><<<grid, NT, smem, stream>>>(st, a, lay, variant);
+    const int need = (st.R + TEAMS - 1) / TEAMS;
+    if (grid > need) grid = need;
+    tau_kernel<TEAMS><<<grid, dim3(TAU_TEAM, TEAMS), smem, stream>>>(st, a, lay, variant);
     return cudaGetLastError();
 }
 
-// Builds of the same kernel with different CTA sizes / register budgets.  VGSIM_TAU_CFG = "<threads>x<ctas per SM>"
-// overrides the default for A/B measurements (e.g. 256x3, 256x4, 512x2, 1024x1; a smaller second number caps
-// the resident CTAs below what the build allows).
+// Teams per CTA: as many 256-thread teams as the shared memory of one SM holds (at most 4 = 1024 threads), one
+// CTA per SM.  VGSIM_TAU_CFG = "<teams>x<ctas per SM>" overrides the choice for A/B measurements.
 cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
     if ((long long)st.D.K * st.D.H + st.D.K >= (1 << 20)) return cudaErrorInvalidValue;  // owner id is packed in 20 bits
-    int nt = 256, occ = 3;
-    if (const char *e = getenv("VGSIM_TAU_CFG")) sscanf(e, "%dx%d", &nt, &occ);
-    if (nt >= 1024) return launch_tau_cfg<1024, 1>(st, a, stream, num_sms, variant, occ);
-    if (nt >= 512) return launch_tau_cfg<512, 2>(st, a, stream, num_sms, variant, occ);
-    if (occ >= 5) return launch_tau_cfg<256, 5>(st, a, stream, num_sms, variant, occ);
-    if (occ == 4) return launch_tau_cfg<256, 4>(st, a, stream, num_sms, variant, occ);
-    return launch_tau_cfg<256, 3>(st, a, stream, num_sms, variant, occ);
+    const size_t stride = ((size_t)tau_layout(st.D, false, TAU_TEAM).bytes + 15) & ~(size_t)15;
+    int teams = (int)((227 * 1024 - TAU_CTA_TAIL) / stride), cap = 0;
+    if (teams > 4) teams = 4;
+    if (teams < 1) teams = 1;
+    if (const char *e = getenv("VGSIM_TAU_CFG")) sscanf(e, "%dx%d", &teams, &cap);
+    if (teams >= 4) return launch_tau_cfg<4>(st, a, stream, num_sms, variant, cap);
+    if (teams == 3) return launch_tau_cfg<3>(st, a, stream, num_sms, variant, cap);
+    if (teams == 2) return launch_tau_cfg<2>(st, a, stream, num_sms, variant, cap);
+    return launch_tau_cfg<1>(st, a, stream, num_sms, variant, cap);
 }
 
 cudaError_t tau_phase_cycles(unsigned long long *out16, int reset) {
@@ -1116,10 +1200,10 @@ cudaError_t tau_phase_cycles(unsigned long long *out16, int reset) {
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream) {
     const TauShared lay = tau_layout(st.D, true);
-    size_t smem = (size_t)lay.bytes;
+    size_t smem = (((size_t)lay.bytes + 15) & ~(size_t)15) + TAU_CTA_TAIL;
     cudaError_t e = cudaFuncSetAttribute(propensity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    propensity_kernel<<<1, 256, smem, stream>>>(st, lay, r, out, dI, dS, tau);
+    propensity_kernel<<<1, dim3(TAU_TEAM, 1), smem, stream>>>(st, lay, r, out, dI, dS, tau);
     return cudaGetLastError();
 }
 
