@@ -16,7 +16,7 @@ so no L2 flush is needed between steps).
            from pinned memory and counters + final states are read back device->host every step.
            The event log stays in HBM, as it stays inside the engine object in the reference; it is
            what vgsim_genealogy consumes.
-  roofline: dominant kernel = tau_kernel; achieved = leaps * (4P+16) B / its CUDA-event duration
+  roofline: dominant kernel = tau_warp_kernel; achieved = leaps * (4P+16) B / its CUDA-event duration
            (events recorded inside vgsim_simulate_tau on the launching stream).
   cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref, Cython build of
            /root/reference made by oracle/build_ref.py) on the host cores, one process per core,
@@ -43,6 +43,8 @@ T_WARM = 60.0
 SEED0 = 1000
 WORKLOAD = "T3 tau-leap: 3 sites (64 haplotypes) x 10 demes x 3 susceptibility groups, 1e6/deme"
 CPU_SAMPLE_TIMEOUT = 180.0   # wall seconds allowed for one bounded CPU sample (all workers)
+# the team kernel (parity tap) is selected with VGSIM_TAU_KERNEL=team; the default is the warp-per-replicate kernel
+KERNEL = "tau_kernel" if os.environ.get("VGSIM_TAU_KERNEL", "").startswith("t") else "tau_warp_kernel"
 EVENT_KEYS = ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus")
 
 
@@ -428,7 +430,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "parallelism": "replicates sharded %dx%d, no data-path collective" % (world, R)},
             "leaps_per_s": leaps / (ms * 1e-3), "channel_draws_per_s": leaps * P / (ms * 1e-3),
             "events_per_leap": events / max(leaps, 1),
-            "roofline": {"bound": "hbm", "kernel": "tau_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_leap": b_leap, "kernel_ms": k_ms},
             "e2e": {"value": ev_e2e / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d * world,
@@ -438,13 +440,17 @@ def gpu_arm(args, rank, world, local_rank):
                         "mean_infectious": float(I0.sum() / R)},
         }
         if phase_cycles is not None:
-            names = ["wipe+lists+Q", "drifts+tau", "primary draws", "slow-path drain", "feasibility", "apply", "lockdown vote"]
+            names = (["wipe+lists+Q", "drifts+tau", "primary draws", "slow-path drain", "feasibility", "apply", "lockdown vote"]
+                     if KERNEL == "tau_kernel" else
+                     ["-", "row wipe issue + drifts + tau", "primary draws + drain", "feasibility", "apply + lists", "-", "-"])
             nl = max(int(phase_cycles[7]), 1)
             line["tau_phase_cycles_per_leap"] = {n: float(phase_cycles[i]) / nl for i, n in enumerate(names)}
         prof = os.path.join(ROOT, "profiles", "tau_kernel_traffic.json")
         if os.path.exists(prof):
             try:
-                line["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+                tj = json.load(open(prof))
+                if tj.get("kernel") == KERNEL and tj.get("replicates") == R and tj.get("leaps") == L:
+                    line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
         if world == 1 and not args.no_cpu_baseline:

@@ -280,3 +280,59 @@ def test_aggregated_and_per_channel_variants_agree(name, seed, t0, dt):
         res.append(d)
     bad = _ks_all(res[0], res[1], list(res[0]))
     assert not bad, bad
+
+
+def _run_kernel(name, Sx0, I0, R, variant, leaps, dt, seed0, two_points=False):
+    """R replicates from one state through vgsim_simulate_tau with the given variant; returns everything
+    the kernel leaves behind for replicate-by-replicate comparison."""
+    (U, K, S), setup = SCENARIOS[name]
+    e = Eng(U, K, S, seed0, False, False, int(1e6), 0.0)
+    setup(e)
+    h = _capi.Handle(U, K, S, R, 2 if two_points else 1, None)
+    h.set_seeds((np.uint64(seed0) + np.arange(R, dtype=np.uint64)).astype(np.uint64))
+    h.upload_params(0, e.param_arrays())
+    if two_points:
+        e2 = Eng(U, K, S, seed0, False, False, int(1e6), 0.0)
+        setup(e2)
+        e2.set_transmission_rate(0.4, None)
+        e2.set_recovery_rate(0.12, None)
+        h.upload_params(1, e2.param_arrays())
+        h.set_replicate_params((np.arange(R) % 3 == 1).astype(np.int32))
+    h.set_state(np.ascontiguousarray(np.broadcast_to(Sx0, (R,) + Sx0.shape)),
+                np.ascontiguousarray(np.broadcast_to(I0, (R,) + I0.shape)))
+    h.set_tau_variant(variant)
+    h.simulate_tau(leaps, -1, dt, 1)
+    c = h.get_counters()
+    Sx_f, I_f = h.get_state()
+    logs = [h.get_tau_log(r) for r in range(0, R, max(1, R // 16))]
+    return c, Sx_f, I_f, logs, h.error_flags() if hasattr(h, "error_flags") else None
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name,seed,t0,dt,two", [("t3small", 5, 60.0, 6.0, False), ("t3", 11, 70.0, 2.0, False),
+                                                 ("s9", 2020, 4.0, 2.0, False), ("s7", 2020, 6.0, 3.0, False),
+                                                 ("table3_k10", 3, 60.0, 3.0, False), ("t3small", 5, 60.0, 6.0, True),
+                                                 ("w", 4, 80.0, 0.5, False)])
+def test_warp_kernel_reproduces_team_kernel(name, seed, t0, dt, two, variant):
+    """The warp-per-replicate kernel (default) and the team kernel (variant bit 2) share the drift / propensity
+    expressions, the summation orders, the Philox addressing and the samplers, so from the same state and seeds
+    they must leave the same log: identical leap counts, per-type counters, final compartments and dense rows.
+    Covers the mask path (H <= 64, K <= 32), the generic path (w: K = 100), lockdown flips (s7, s9, table3) and
+    parameter points staged per warp (two points mixed over the replicates)."""
+    Sx0, I0 = warm_state(name, seed, t0)
+    assert I0.sum() > 0
+    R = 24 if name == "w" else 150
+    a = _run_kernel(name, Sx0, I0, R, variant, 40, dt, 700 + variant, two)
+    b = _run_kernel(name, Sx0, I0, R, variant | 4, 40, dt, 700 + variant, two)
+    ca, cb = a[0], b[0]
+    assert ca["leaps"].min() >= 1
+    for k in ("leaps", "bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus", "swapLockdown"):
+        if k in ca:
+            assert np.array_equal(ca[k], cb[k]), (k, np.flatnonzero(ca[k] != cb[k])[:10])
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    np.testing.assert_allclose(ca["time"], cb["time"], rtol=1e-13, atol=0)
+    for (cnt_a, tt_a), (cnt_b, tt_b) in zip(a[3], b[3]):
+        assert np.array_equal(cnt_a, cnt_b)
+        np.testing.assert_allclose(tt_a, tt_b, rtol=1e-13, atol=0)
+    exact = all(np.array_equal(x[1], y[1]) for x, y in zip(a[3], b[3]))
+    assert exact, "tau/time streams agree to 1e-13 but not bit for bit"

@@ -436,7 +436,10 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
     if (prepare(h, 1)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms, h->tau_variant);
+    int uniform_pp = h->rep_pp_host.empty() ? 0 : h->rep_pp_host[0];  // every replicate on one parameter point?
+    for (int v : h->rep_pp_host)
+        if (v != uniform_pp) uniform_pp = -1;
+    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms, h->tau_variant, uniform_pp);
     if (e != cudaSuccess) return fail(std::string("tau kernel: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(h->ev_k1, h->stream));
     h->ev_valid = true;
@@ -697,7 +700,8 @@ int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset) {
 }
 
 int vgsim_set_tau_variant(vgsim_handle h, int variant) {
-    if (variant < 0 || variant > 3) return fail("tau variant must be 0..3 (bit 0: per-channel draws, bit 1: phase timing)");
+    if (variant < 0 || variant > 7)
+        return fail("tau variant must be 0..7 (bit 0: per-channel draws, bit 1: phase timing, bit 2: team kernel)");
     h->tau_variant = variant;
     return 0;
 }

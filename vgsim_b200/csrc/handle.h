@@ -58,7 +58,7 @@ struct Handle {
 };
 
 // kernels' host launchers (defined in the .cu files)
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant);
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp);
 cudaError_t tau_phase_cycles(unsigned long long *out16, int reset);
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream);

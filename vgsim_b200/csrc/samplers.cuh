@@ -40,6 +40,12 @@ __device__ __forceinline__ double log_factorial(long long k) {
     return (x + 0.5) * log(x) - x + 0.9189385332046728 + r * (1.0 / 12.0 - r2 * (1.0 / 360.0 - r2 * (1.0 / 1260.0)));
 }
 
+// 1/n for the pmf recurrence of the inversion sampler (a table look-up instead of an fp64 division per step)
+__device__ const double RCP32[32] = {
+    0.0, 1.0, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, 1.0 / 8, 1.0 / 9, 1.0 / 10, 1.0 / 11,
+    1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22,
+    1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31};
+
 static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCtx &ctx, int lane) {
     const double slam = sqrt(lam);
     const double b = 0.931 + 2.53 * slam;
@@ -74,7 +80,7 @@ static __device__ __noinline__ long long poisson_inversion(double lam, uint32_t 
     long long n = 0;
     while (U >= cdf && n < 256) {
         n++;
-        p *= lam / (double)n;
+        p *= lam * (n < 32 ? RCP32[n] : 1.0 / (double)n);  // lam < 10: the walk almost never passes 32
         cdf += p;
     }
     return n;

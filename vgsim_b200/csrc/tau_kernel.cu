@@ -178,7 +178,8 @@ struct Channel {
 // Channel l of infectious cell (p,h): l < E are the deme-block events RECOVERY, SAMPLING, MUTATION[u][k],
 // TRANSMISSION[s]; l >= E is out-migration of h from p to the (l-E)/S-th other deme, group (l-E)%S.
 // Returns the positional index c of the channel in the dense row.
-__device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, const TauShared &s, const double *eff,
+template <class SH>
+__device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, const SH &s, const double *eff,
                                             Channel &ch) {
     const int K = D.K, H = D.H, S = D.S;
     const int cell = p * H + h;
@@ -224,7 +225,8 @@ __device__ __forceinline__ int cell_channel(int p, int h, int l, const Dims &D, 
 }
 
 // SUSCCHANGE channel l of deme p: [ss][ts != ss]  (:2378)
-__device__ __forceinline__ int susc_channel(int p, int l, const Dims &D, const TauShared &s, Channel &ch) {
+template <class SH>
+__device__ __forceinline__ int susc_channel(int p, int l, const Dims &D, const SH &s, Channel &ch) {
     const int S = D.S;
     int ss = l / (S - 1), tsp = l - ss * (S - 1);
     int ts = tsp + (tsp >= ss ? 1 : 0);
@@ -373,43 +375,12 @@ __device__ __forceinline__ void q_pass(const Dims &D, const TauShared &s) {
     }
 }
 
-// Drifts and tau of the current shared-memory state (Propensities :2351-2417 summed per compartment, ChooseTau
-// :2432-2450).  Needs the lists and Qm; contains two barriers; returns tau (uniform).  Every sum runs over the
-// ordered cell list / set bits in ascending order, so the result does not depend on warp scheduling.
-__device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double *eff, int slot) {
-    const int K = D.K, H = D.H, S = D.S, U = D.U;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    // ---- A. per (deme, group): pressure B = sum_h sigma[s,h] b[h] I[p,h], return flow R = sum_{g[h]=s} (d + sr sm) I.
-    //         8 lanes share one (deme, group) sum (strided over the deme's cells) and combine in a fixed butterfly.
-    for (int t0 = 0; t0 < K * S; t0 += nt >> 3) {
-        const int task = t0 + (tid >> 3), j = tid & 7;
-        double Bv = 0.0, Rv = 0.0;
-        int p = 0, sn = 0;
-        if (task < K * S) {
-            p = task / S;
-            sn = task - p * S;
-            const int a1 = s.dstart[p + 1];
-            for (int a = s.dstart[p] + j; a < a1; a += 8) {
-                const int cell = s.act[a], h = cell & (H - 1);
-                const double Iv = s.I[cell];
-                Bv += s.sb[sn * H + h] * Iv;
-                if (s.g[h] == sn) Rv += (s.d[h] + s.sr[h] * s.sm[p]) * Iv;
-            }
-        }
-        for (int o = 4; o > 0; o >>= 1) {
-            Bv += __shfl_xor_sync(0xffffffffu, Bv, o);
-            Rv += __shfl_xor_sync(0xffffffffu, Rv, o);
-        }
-        if (task < K * S && j == 0) {
-            s.Bp[task] = Bv;
-            s.Rp[task] = Rv;
-        }
-    }
-    align_teams();  // generation barrier 3 of 5
-    double tmin = 1.0;
-    const float eps = 0.03f;
-    // ---- B1. infectious drifts, one thread per cell
-    for (int i = tid; i < K * H; i += nt) {
+// Net drift of infectious cell i = (p,h): force of infection (own deme + migration from every deme holding h),
+// removal, and mutation inflow from the haplotypes one substitution away that are present in the deme
+// (Propensities :2351-2417 summed per compartment).  Every sum runs in ascending index order.
+template <class SH>
+__device__ __forceinline__ double drift_I_cell(int i, const Dims &D, const SH &s, const double *eff) {
+    const int K = D.K, H = D.H, U = D.U;
         const int p = i >> D.hshift, h = i & (H - 1);
         const double Iv = s.I[i];
         double v = 0.0;
@@ -457,6 +428,63 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
                 }
             }
         }
+        return v;
+}
+
+// Net drift of susceptible compartment i = (p, sn)
+template <class SH>
+__device__ __forceinline__ double drift_S_cell(int i, const Dims &D, const SH &s, const double *eff) {
+    const int K = D.K, S = D.S;
+        const int p = i / S, sn = i - p * S;
+        double phi = s.c[p] * s.Bp[i];
+        for (int sp = 0; sp < K; sp++)
+            if (sp != p) phi += eff[p * K + sp] * s.mdiag[sp] * s.Bp[sp * S + sn];
+        const double Sv = s.Sx[i];
+        double v = -Sv * phi + s.Rp[i];
+        for (int s2 = 0; s2 < S; s2++)
+            if (s2 != sn) v += s.T[s2 * S + sn] * s.Sx[p * S + s2] - s.T[sn * S + s2] * Sv;
+        return v;
+}
+
+// Drifts and tau of the current shared-memory state (Propensities :2351-2417 summed per compartment, ChooseTau
+// :2432-2450).  Needs the lists and Qm; contains two barriers; returns tau (uniform).  Every sum runs over the
+// ordered cell list / set bits in ascending order, so the result does not depend on warp scheduling.
+__device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double *eff, int slot) {
+    const int K = D.K, H = D.H, S = D.S, U = D.U;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // ---- A. per (deme, group): pressure B = sum_h sigma[s,h] b[h] I[p,h], return flow R = sum_{g[h]=s} (d + sr sm) I.
+    //         8 lanes share one (deme, group) sum (strided over the deme's cells) and combine in a fixed butterfly.
+    for (int t0 = 0; t0 < K * S; t0 += nt >> 3) {
+        const int task = t0 + (tid >> 3), j = tid & 7;
+        double Bv = 0.0, Rv = 0.0;
+        int p = 0, sn = 0;
+        if (task < K * S) {
+            p = task / S;
+            sn = task - p * S;
+            const int a1 = s.dstart[p + 1];
+            for (int a = s.dstart[p] + j; a < a1; a += 8) {
+                const int cell = s.act[a], h = cell & (H - 1);
+                const double Iv = s.I[cell];
+                Bv += s.sb[sn * H + h] * Iv;
+                if (s.g[h] == sn) Rv += (s.d[h] + s.sr[h] * s.sm[p]) * Iv;
+            }
+        }
+        for (int o = 4; o > 0; o >>= 1) {
+            Bv += __shfl_xor_sync(0xffffffffu, Bv, o);
+            Rv += __shfl_xor_sync(0xffffffffu, Rv, o);
+        }
+        if (task < K * S && j == 0) {
+            s.Bp[task] = Bv;
+            s.Rp[task] = Rv;
+        }
+    }
+    align_teams();  // generation barrier 3 of 5
+    double tmin = 1.0;
+    const float eps = 0.03f;
+    // ---- B1. infectious drifts, one thread per cell
+    for (int i = tid; i < K * H; i += nt) {
+        const double Iv = s.I[i];
+        const double v = drift_I_cell(i, D, s, eff);
         if (s.store_drift) s.dI[i] = v;
         const double av = fabs(v);
         if (av >= 1e-8) {
@@ -468,14 +496,8 @@ __device__ double drifts_and_tau(const Dims &D, const TauShared &s, const double
     // ---- B2. susceptible drifts, one thread per (deme, group), taken from the END of the CTA (those threads
     //          own one cell fewer in B1)
     for (int i = nt - 1 - tid; i < K * S; i += nt) {
-        const int p = i / S, sn = i - p * S;
-        double phi = s.c[p] * s.Bp[i];
-        for (int sp = 0; sp < K; sp++)
-            if (sp != p) phi += eff[p * K + sp] * s.mdiag[sp] * s.Bp[sp * S + sn];
         const double Sv = s.Sx[i];
-        double v = -Sv * phi + s.Rp[i];
-        for (int s2 = 0; s2 < S; s2++)
-            if (s2 != sn) v += s.T[s2 * S + sn] * s.Sx[p * S + s2] - s.T[sn * S + s2] * Sv;
+        const double v = drift_S_cell(i, D, s, eff);
         if (s.store_drift) s.dS[i] = v;
         const double av = fabs(v);
         if (av >= 1e-8) {
@@ -587,7 +609,8 @@ struct LeapTally {
 };
 
 // book n events of channel ch into the shared-memory deltas and the per-thread tallies
-__device__ __forceinline__ void book(const Channel &ch, int n, const TauShared &s, LeapTally &t) {
+template <class SH>
+__device__ __forceinline__ void book(const Channel &ch, int n, const SH &s, LeapTally &t) {
     if (ch.i_dec >= 0) {
         atomicSub(&s.chkI[ch.i_dec], n);
         atomicSub(&s.updI[ch.i_dec], n);
@@ -672,7 +695,8 @@ __device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
 
 // total out-migration propensity of cell (p,h): sum over targets and groups of the channel propensities,
 // factorised through Q[tp,h] = sum_s Sx[tp,s] sigma[s,h]
-__device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims &D, const TauShared &s, const double *eff) {
+template <class SH>
+__device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims &D, const SH &s, const double *eff) {
     double acc = 0.0;
     for (int tp = 0; tp < D.K; tp++)
         if (tp != p) acc += eff[tp * D.K + p] * s.Qm[tp * D.H + h];
@@ -683,7 +707,8 @@ __device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims 
 // count that the top 32 bits of the uniform already prove to be 0 is settled here; everything else goes to
 // the slow-path queue (inversion entries from the bottom, PTRS entries from the top) or, for group totals
 // that are too large to aggregate, to the expansion queues.
-__device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner, int code, const TauShared &s, int *qn) {
+template <class SH>
+__device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner, int code, const SH &s, int *qn) {
     int e;
     if (lam < 10.0) {
         if ((double)hi + 1.0 <= (1.0 - lam) * 4294967296.0) return;  // U < 1-lam <= exp(-lam)  =>  0
@@ -697,7 +722,8 @@ __device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner,
 
 // multinomial split of an aggregated total: n events of cell (p,h), each assigned to one channel of the
 // group with probability prop_channel / prop_total (exact: independent Poissons conditioned on their sum)
-static __device__ __noinline__ void split_total(int n, int p, int h, int code, int *row, const Dims &D, const TauShared &s,
+template <class SH>
+static __device__ __noinline__ void split_total(int n, int p, int h, int code, int *row, const Dims &D, const SH &s,
                                                 const double *eff, const DrawGeom &g, PhiloxCtx ctx, LeapTally &tr) {
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     const int cell = p * H + h;
@@ -761,7 +787,8 @@ static __device__ __noinline__ void split_total(int n, int p, int h, int code, i
 
 // one slow-path queue entry: recompute its lambda (same expression as the primary pass), finish the Poisson
 // draw, then write / split the count
-__device__ __forceinline__ void process_entry(int e, double tau, int *row, const Dims &D, const TauShared &s,
+template <class SH>
+__device__ __forceinline__ void process_entry(int e, double tau, int *row, const Dims &D, const SH &s,
                                               const double *eff, const DrawGeom &g, PhiloxCtx &ctx, LeapTally &tr) {
     const uint32_t hi = (uint32_t)s.qhi[e];
     const int oc = s.qoc[e];
@@ -1152,6 +1179,10 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
     if (threadIdx.x == 0) *tau_out = tau;
 }
 
+}  // namespace vg
+#include "tau_warp.cuh"
+namespace vg {
+
 // host launchers ---------------------------------------------------------------------------------
 template <int TEAMS>
 static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant,
@@ -1173,10 +1204,32 @@ static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStre
     return cudaGetLastError();
 }
 
-// Teams per CTA: as many 256-thread teams as the shared memory of one SM holds (at most 4 = 1024 threads), one
-// CTA per SM.  VGSIM_TAU_CFG = "<teams>x<ctas per SM>" overrides the choice for A/B measurements.
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant) {
+// Default: the warp-per-replicate kernel (tau_warp.cuh), one CTA per SM with as many warps as the shared memory
+// holds (<= 16).  The team kernel (256-thread teams, CTA-wide generations) stays available as a parity tap:
+// variant bit 2, or VGSIM_TAU_KERNEL=team; VGSIM_TAU_CFG = "<teams>x<ctas per SM>" then overrides its shape.
+// VGSIM_TAU_WARPS caps the warps per CTA of the warp kernel (A/B measurements).
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp) {
     if ((long long)st.D.K * st.D.H + st.D.K >= (1 << 20)) return cudaErrorInvalidValue;  // owner id is packed in 20 bits
+    bool team = (variant & 4) != 0;
+    if (const char *e = getenv("VGSIM_TAU_KERNEL")) team = team || e[0] == 't';
+    if (!team) {
+        int max_warps = 16;
+        if (const char *e = getenv("VGSIM_TAU_WARPS")) max_warps = atoi(e);
+        if (max_warps < 1) max_warps = 1;
+        WarpLayout L = warp_layout(st.D, uniform_pp >= 0, uniform_pp >= 0 ? uniform_pp : 0, 227 * 1024, max_warps);
+        if (const char *e = getenv("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
+        if (L.nwarps >= 1 && st.D.K * st.D.H < 65536) {  // cell ids are held as uint16
+            const WS ws = make_ws(L, st.D);
+            auto kern = (variant & 2) ? tau_warp_kernel<true> : tau_warp_kernel<false>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+            if (e != cudaSuccess) return e;
+            int grid = (st.R + L.nwarps - 1) / L.nwarps;
+            if (grid > num_sms) grid = num_sms;
+            kern<<<grid, L.nwarps * 32, L.total_bytes, stream>>>(st, a, L, ws, variant);
+            return cudaGetLastError();
+        }
+        // a single replicate's state does not fit one warp slice: fall through to the team kernel
+    }
     const size_t stride = ((size_t)tau_layout(st.D, false, TAU_TEAM).bytes + 15) & ~(size_t)15;
     int teams = (int)((227 * 1024 - TAU_CTA_TAIL) / stride), cap = 0;
     if (teams > 4) teams = 4;

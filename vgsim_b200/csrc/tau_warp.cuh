@@ -1,0 +1,804 @@
+// Warp-per-replicate tau-leaping kernel (included by tau_kernel.cu; shares its channel / draw helpers).
+//
+// Why a second mapping: ncu of the team kernel (profiles/r1_e_*) shows 66 % of all warp samples parked on
+// barriers -- every phase of a leap lasts as long as its slowest warp (a handful of Poisson slow paths, a
+// 1-lane multinomial split) while the other 31 warps of the SM idle, and the 64-register cap of a
+// 1024-thread CTA spills.  At T3 a leap touches ~70 infectious cells and ~200 real Poisson draws: that is
+// warp-sized work.  Here ONE WARP owns a replicate: no named barriers, no CTA-wide generations, every phase
+// is a lane-strided loop closed by __syncwarp(), and 14-16 independent replicates per SM keep the issue
+// slots busy while any one of them waits on a dependent chain.
+//
+// Per-replicate state lives in the warp's slice of dynamic shared memory: I as int32 (converted on use),
+// per-leap deltas, the ordered list of infectious cells, presence masks, the slow-path queue.  Q[p,h] is
+// recomputed where needed instead of stored.  The parameter point is staged ONCE per CTA when every
+// replicate of the launch uses the same point (the common case), else once per warp.
+//
+// The arithmetic is the team kernel's: same drift / propensity expressions (shared template functions),
+// same summation orders, same Philox addressing (owner, leap, retry|epoch, block), same samplers -- a leap
+// is a pure function of (state, seed), so the two kernels produce the same log.  The team kernel stays as a
+// parity tap (variant bit 2 / VGSIM_TAU_KERNEL=team).
+#pragma once
+
+namespace vg {
+
+#define TW_ZB 8192  // CTA zero buffer: source of the TMA row wipes
+
+struct WarpLayout {
+    int nwarps;        // warps (= replicates in flight) per CTA
+    int par_shared;    // 1: one parameter block per CTA (all replicates use point pp0); 0: one per warp
+    int pp0;
+    int o_par, o_nbr, o_warp0, warp_bytes;
+    // inside the parameter block (bytes)
+    int p_b, p_d, p_sr, p_tmq, p_q, p_sigT, p_sb, p_T, p_sm, p_mdiag, p_sizeD, p_startN, p_endN, p_g, par_bytes;
+    // inside a warp slice (bytes)
+    int w_par, w_cd, w_c, w_maxEBM, w_eff, w_Sx, w_Bp, w_Rp, w_I, w_chk, w_upd, w_act, w_dSx, w_lock, w_tot, w_dstart,
+        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qhi, w_qoc, w_xq, w_cnt, w_tally;
+    int qcap, xcap;
+    int has_eff, use_masks;
+    int o_done, gsync;
+    int total_bytes;
+};
+
+inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_bytes, int max_warps) {
+    WarpLayout L;
+    L.gsync = 0;
+    const int K = D.K, H = D.H, S = D.S, U = D.U, KH = K * H, KS = K * S;
+    L.par_shared = par_shared ? 1 : 0;
+    L.pp0 = pp0;
+    L.use_masks = (H <= 64 && K <= 32) ? 1 : 0;
+    L.has_eff = tau_eff_in_smem(D) ? 1 : 0;
+    L.qcap = 256;
+    L.xcap = 64;
+    int o = 0;
+    auto take = [&](int &f, int bytes, int align) {
+        o = (o + align - 1) & ~(align - 1);
+        f = o;
+        o += bytes;
+    };
+    // parameter block
+    take(L.p_b, H * 8, 8); take(L.p_d, H * 8, 8); take(L.p_sr, H * 8, 8); take(L.p_tmq, H * 8, 8);
+    take(L.p_q, H * U * 3 * 8, 8); take(L.p_sigT, S * H * 8, 8); take(L.p_sb, S * H * 8, 8); take(L.p_T, S * S * 8, 8);
+    take(L.p_sm, K * 8, 8); take(L.p_mdiag, K * 8, 8); take(L.p_sizeD, K * 8, 8); take(L.p_startN, K * 8, 8);
+    take(L.p_endN, K * 8, 8); take(L.p_g, H * 4, 8);
+    L.par_bytes = (o + 15) & ~15;
+    // warp slice
+    o = 0;
+    L.w_par = 0;
+    if (!par_shared) o = L.par_bytes;
+    take(L.w_cd, K * 8, 8); take(L.w_c, K * 8, 8); take(L.w_maxEBM, K * 8, 8);
+    take(L.w_eff, L.has_eff ? K * K * 8 : 0, 8);
+    take(L.w_Sx, KS * 8, 8); take(L.w_Bp, KS * 8, 8); take(L.w_Rp, KS * 8, 8);
+    take(L.w_rowmask, L.use_masks ? K * 8 : 0, 8);
+    take(L.w_tally, 8 * 8, 8);
+    take(L.w_I, KH * 4, 16);
+    take(L.w_chk, KH * 4, 16);   // chk and upd are wiped together: keep them adjacent
+    take(L.w_upd, KH * 4, 16);
+    take(L.w_act, KH * 2, 16);  // uint16 cell ids (KH < 65536); 16-aligned: the int4 wipe of chk/upd may round up into the padding before it
+    take(L.w_dSx, KS * 4, 4); take(L.w_lock, K * 4, 4); take(L.w_tot, K * 4, 4); take(L.w_dstart, (K + 1) * 4, 4);
+    take(L.w_colmask, L.use_masks ? H * 4 : 0, 4);
+    if (L.use_masks) L.w_colcnt = L.w_colmask;  // "present anywhere" is colmask != 0 on the mask path
+    else take(L.w_colcnt, H * 4, 4);
+    take(L.w_hlist, H * 4, 4);
+    take(L.w_qhi, L.qcap * 4, 4); take(L.w_qoc, L.qcap * 4, 4); take(L.w_xq, 2 * L.xcap * 4, 4);
+    take(L.w_cnt, 8 * 4, 4);
+    L.warp_bytes = (o + 15) & ~15;
+    // CTA
+    o = TW_ZB;
+    L.o_done = o;
+    o += 16;
+    L.o_par = o;
+    if (par_shared) o += L.par_bytes;
+    L.o_nbr = o;
+    if (L.use_masks) o += H * 8;
+    o = (o + 15) & ~15;
+    L.o_warp0 = o;
+    int nw = (max_bytes - o) / L.warp_bytes;
+    if (nw > max_warps) nw = max_warps;
+    if (nw > 14) nw = 14;  // 448 threads: 144 registers per thread; 148 x 14 = 2072 replicates in flight
+    L.nwarps = nw;
+    L.total_bytes = o + (nw > 0 ? nw : 0) * L.warp_bytes;
+    return L;
+}
+
+// ---- shared-memory views handed to the channel / draw helpers (same member names as TauShared) ---------
+// A view is (byte offset, per-warp stride): address = smem + off + scale * warp index.  CTA-shared arrays have
+// scale 0.  The whole WS is a __grid_constant__ kernel parameter, so the ~50 pairs sit in the constant bank
+// (one IMAD per address) and helpers can take it by reference without a local-memory copy.
+__device__ __forceinline__ unsigned w_index() { return threadIdx.x >> 5; }
+template <class T>
+struct WArr {
+    int off, scale;
+    __device__ __forceinline__ T *ptr() const { return reinterpret_cast<T *>(smem_raw + (unsigned)(off + scale * (int)w_index())); }
+    __device__ __forceinline__ T &operator[](int i) const { return ptr()[i]; }
+    __device__ __forceinline__ operator T *() const { return ptr(); }
+};
+struct WIval {  // infectious counts: int32 in shared memory, fp64 to the arithmetic
+    WArr<int> raw;
+    __device__ __forceinline__ double operator[](int i) const { return (double)raw.ptr()[i]; }
+};
+struct WQval {  // Q[p,h] = sum_s Sx[p,s] sigma[s,h], recomputed on use (same order as the team kernel's q_pass)
+    WArr<double> Sx, sg;
+    int H, S, hshift;
+    __device__ __forceinline__ double operator[](int i) const {
+        const double *sx = Sx.ptr(), *sig = sg.ptr();
+        const int p = i >> hshift, h = i & (H - 1);
+        double Q = 0.0;
+#pragma unroll 1
+        for (int sn = 0; sn < S; sn++) Q += sx[p * S + sn] * sig[sn * H + h];
+        return Q;
+    }
+};
+struct WS {
+    WArr<double> b, d, sr, q, tmq, sigT, sb, T, sm, mdiag, sizeD, startN, endN;
+    WArr<int> g;
+    WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp;
+    WIval I;
+    WQval Qm;
+    WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, xq, cnt;
+    WArr<unsigned short> act;
+    WArr<long long> tally64;
+    WArr<unsigned long long> rowmask, nbrmask;
+    int qcap;
+    bool use_masks, has_effS;
+};
+
+inline WS make_ws(const WarpLayout &L, const Dims &D) {
+    WS s;
+    const int wb = L.o_warp0, ws = L.warp_bytes;
+    const int pb = L.par_shared ? L.o_par : wb + L.w_par, ps = L.par_shared ? 0 : ws;
+    auto P = [&](int o) { WArr<double> a; a.off = pb + o; a.scale = ps; return a; };
+    auto Wd = [&](int o) { WArr<double> a; a.off = wb + o; a.scale = ws; return a; };
+    auto Wi = [&](int o) { WArr<int> a; a.off = wb + o; a.scale = ws; return a; };
+    s.b = P(L.p_b); s.d = P(L.p_d); s.sr = P(L.p_sr); s.tmq = P(L.p_tmq); s.q = P(L.p_q); s.sigT = P(L.p_sigT);
+    s.sb = P(L.p_sb); s.T = P(L.p_T); s.sm = P(L.p_sm); s.mdiag = P(L.p_mdiag); s.sizeD = P(L.p_sizeD);
+    s.startN = P(L.p_startN); s.endN = P(L.p_endN);
+    s.g.off = pb + L.p_g; s.g.scale = ps;
+    s.cd = Wd(L.w_cd); s.c = Wd(L.w_c); s.maxEBM = Wd(L.w_maxEBM); s.effS = Wd(L.w_eff);
+    s.Sx = Wd(L.w_Sx); s.Bp = Wd(L.w_Bp); s.Rp = Wd(L.w_Rp);
+    s.Iraw = Wi(L.w_I); s.I.raw = s.Iraw;
+    s.Qm.Sx = s.Sx; s.Qm.sg = s.sigT; s.Qm.H = D.H; s.Qm.S = D.S; s.Qm.hshift = D.hshift;
+    s.chkI = Wi(L.w_chk); s.updI = Wi(L.w_upd); s.act.off = wb + L.w_act; s.act.scale = ws; s.dSx = Wi(L.w_dSx); s.lock = Wi(L.w_lock);
+    s.tot = Wi(L.w_tot); s.dstart = Wi(L.w_dstart); s.colcnt = Wi(L.w_colcnt); s.colmask = Wi(L.w_colmask);
+    s.hlist = Wi(L.w_hlist); s.qhi = Wi(L.w_qhi); s.qoc = Wi(L.w_qoc); s.xq = Wi(L.w_xq); s.cnt = Wi(L.w_cnt);
+    s.tally64.off = wb + L.w_tally; s.tally64.scale = ws;
+    s.rowmask.off = wb + L.w_rowmask; s.rowmask.scale = ws;
+    s.nbrmask.off = L.o_nbr; s.nbrmask.scale = 0;
+    s.qcap = L.qcap;
+    s.use_masks = L.use_masks != 0;
+    s.has_effS = L.has_eff != 0;
+    return s;
+}
+
+// TMA zero-fill of a dense log row out of the CTA zero buffer at shared-memory offset 0 (issued by one lane)
+__device__ __forceinline__ void w_wipe_row_async(int *row, int bytes) {
+    const unsigned src = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned long long dst = (unsigned long long)(uintptr_t)row;
+    asm volatile("fence.proxy.async;" ::: "memory");  // earlier generic-proxy stores to this row (a failed draw) stay before the wipe
+#pragma unroll 1
+    for (int off = 0; off < bytes; off += TW_ZB) {
+        const int n = bytes - off < TW_ZB ? bytes - off : TW_ZB;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src), "r"(n) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+struct LaneGroup {  // rates.cuh group interface for one warp
+    __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int size() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+// CheckLockdown for every deme (:2328-2329 / :449-450 / :736-737): the lanes vote whether any deme crosses a
+// threshold; only then lane 0 runs the sequential reference pass and the warp refreshes the contact-density
+// dependent rates.  Returns the number of flips.
+static __device__ __noinline__ int w_lockdown_slow(const DevState &st, int r, const Dims &D, const WS &s, const double *pp,
+                                                   double *eff_g, double now) {
+    const int lane = threadIdx.x & 31, K = D.K;
+    int flips = 0;
+    if (lane == 0)
+        for (int p = 0; p < K; p++)
+            flips += check_lockdown(D, pp, p, (long long)s.tot[p], s.cd, s.lock, now, &st.loc_n[r],
+                                    st.loc_sp + (size_t)r * st.loc_cap, st.loc_t + (size_t)r * st.loc_cap, st.loc_cap,
+                                    &st.err[r]);
+    flips = __shfl_sync(0xffffffffu, flips, 0);
+    __syncwarp();
+    if (flips) {
+        update_contact_rates(LaneGroup(), D, pp, s.cd, eff_g, s.c, s.maxEBM);
+        if (s.has_effS) {
+            for (int i = lane; i < K * K; i += 32) s.effS[i] = eff_g[i];
+            __syncwarp();
+        }
+    }
+    return flips;
+}
+__device__ __forceinline__ int w_lockdown(const DevState &st, int r, const Dims &D, const WS &s, const double *pp,
+                                          double *eff_g, double now) {
+    int pred = 0;
+#pragma unroll 1
+    for (int p = threadIdx.x & 31; p < D.K; p += 32) {
+        const double ti = (double)s.tot[p];
+        if ((ti > s.startN[p] && s.lock[p] == 0) || (ti < s.endN[p] && s.lock[p] == 1)) pred = 1;
+    }
+    if (!__any_sync(0xffffffffu, pred)) return 0;
+    return w_lockdown_slow(st, r, D, s, pp, eff_g, now);
+}
+
+// stage one parameter point (blob layout of common.cuh) into a shared-memory parameter block
+__device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const double *pp, int t, int n) {
+    const int K = D.K, H = D.H, S = D.S, U = D.U;
+#pragma unroll 1
+    for (int i = t; i < H; i += n) {
+        s.b[i] = pp[D.o_b + i];
+        s.d[i] = pp[D.o_d + i];
+        s.sr[i] = pp[D.o_sr + i];
+        s.tmq[i] = pp[D.o_tmq + i];
+        s.g[i] = (int)pp[D.o_g + i];
+    }
+#pragma unroll 1
+    for (int i = t; i < H * U * 3; i += n) s.q[i] = pp[D.o_q + i];
+#pragma unroll 1
+    for (int i = t; i < S * H; i += n) {
+        s.sigT[i] = pp[D.o_sigT + i];
+        s.sb[i] = pp[D.o_sigT + i] * pp[D.o_b + (i % H)];
+    }
+#pragma unroll 1
+    for (int i = t; i < S * S; i += n) s.T[i] = pp[D.o_T + i];
+#pragma unroll 1
+    for (int i = t; i < K; i += n) {
+        s.sm[i] = pp[D.o_sm + i];
+        s.mdiag[i] = pp[D.o_m + i * K + i];
+        s.sizeD[i] = pp[D.o_size + i];
+        s.startN[i] = pp[D.o_startN + i];
+        s.endN[i] = pp[D.o_endN + i];
+    }
+}
+
+// Ordered compaction of the infectious cells of the CURRENT counts (+ upd when APPLY): act[] ascending, dstart[],
+// presence masks / counts, per-deme totals, the ascending list of haplotypes present anywhere.  Returns the
+// number of infectious cells; nhap gets the number of present haplotypes.  One warp, ends with __syncwarp().
+template <bool APPLY>
+__device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap) {
+    const int lane = threadIdx.x & 31, K = D.K, H = D.H, KH = K * H;
+#pragma unroll 1
+    for (int i = lane; i < H; i += 32) s.colcnt[i] = 0;  // (= colmask on the mask path)
+#pragma unroll 1
+    for (int i = lane; i < K; i += 32) {
+        s.tot[i] = 0;
+        if (s.use_masks) s.rowmask[i] = 0ull;
+    }
+    __syncwarp();
+    int cnt = 0;
+    int *I = s.Iraw;
+#pragma unroll 1
+    for (int base = 0; base < KH; base += 32) {
+        const int i = base + lane;
+        int v = 0;
+        if (i < KH) {
+            v = I[i];
+            if (APPLY) {
+                v += s.updI[i];
+                I[i] = v;
+            }
+        }
+        const bool on = v != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (i < KH) {
+            const int p = i >> D.hshift, h = i & (H - 1);
+            if (h == 0) s.dstart[p] = pos;
+            if (on) {
+                s.act[pos] = (unsigned short)i;
+                atomicAdd(&s.tot[p], v);
+                if (s.use_masks) {
+                    atomicOr(&s.colmask[h], 1 << p);
+                    atomicOr(&s.rowmask[p], 1ull << h);
+                } else {
+                    atomicAdd(&s.colcnt[h], 1);
+                }
+            }
+        }
+        cnt += __popc(m);
+    }
+    if (lane == 0) s.dstart[K] = cnt;
+    __syncwarp();
+    int nh = 0;
+#pragma unroll 1
+    for (int base = 0; base < H; base += 32) {
+        const int h = base + lane;
+        const bool on = h < H && s.colcnt[h] != 0;
+        const unsigned m = __ballot_sync(0xffffffffu, on);
+        if (on) s.hlist[nh + __popc(m & ((1u << lane) - 1u))] = h;
+        nh += __popc(m);
+    }
+    nhap = nh;
+    __syncwarp();
+    return cnt;
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Drifts and tau (ChooseTau :2432-2450) of the warp's state; same sums as the team kernel's drifts_and_tau.
+__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, const double *eff, int nhap) {
+    const int K = D.K, H = D.H, S = D.S, KS = K * S;
+    const int lane = threadIdx.x & 31;
+    // ---- A. pressure / return-flow sums per (deme, group): 8 lanes per sum, fixed butterfly
+#pragma unroll 1
+    for (int t0 = 0; t0 < KS; t0 += 4) {
+        const int task = t0 + (lane >> 3), j = lane & 7;
+        double Bv = 0.0, Rv = 0.0;
+        int p = 0, sn = 0;
+        if (task < KS) {
+            p = task / S;
+            sn = task - p * S;
+            const int a1 = s.dstart[p + 1];
+            for (int a = s.dstart[p] + j; a < a1; a += 8) {
+                const int cell = s.act[a], h = cell & (H - 1);
+                const double Iv = s.I[cell];
+                Bv += s.sb[sn * H + h] * Iv;
+                if (s.g[h] == sn) Rv += (s.d[h] + s.sr[h] * s.sm[p]) * Iv;
+            }
+        }
+        for (int o = 4; o > 0; o >>= 1) {
+            Bv += __shfl_xor_sync(0xffffffffu, Bv, o);
+            Rv += __shfl_xor_sync(0xffffffffu, Rv, o);
+        }
+        if (task < KS && j == 0) {
+            s.Bp[task] = Bv;
+            s.Rp[task] = Rv;
+        }
+    }
+    __syncwarp();
+    double tmin = 1.0;
+    const float eps = 0.03f;
+    auto candidate = [&](double v, double cnt) {
+        const double av = fabs(v);
+        if (av >= 1e-8) {
+            double x = (double)(eps * (float)cnt) / 2.0;  // float product, like the reference's generated C
+            x = 1.0 > x ? 1.0 : x;
+            if (x < tmin * av) tmin = fmin(tmin, x / av);
+        }
+    };
+    // ---- B1a. cells whose haplotype is present somewhere: force of infection + removal + mutation inflow.
+    //           Walks (present haplotype, deme) pairs: every lane has the long sum to do, and neighbouring lanes
+    //           share the haplotype, i.e. the trip count of the presence loop.
+    const int n1 = K * nhap;
+#pragma unroll 1
+    for (int i = lane; i < n1; i += 32) {
+        const int hi = i / K, p = i - hi * K, h = s.hlist[hi];
+        const int cell = p * H + h;
+        candidate(drift_I_cell(cell, D, s, eff), s.I[cell]);
+    }
+    // ---- B1b. every other cell: mutation inflow only (its count is 0)
+#pragma unroll 1
+    for (int i = lane; i < K * H; i += 32) {
+        if (s.colcnt[i & (H - 1)] != 0) continue;
+        candidate(drift_I_cell(i, D, s, eff), 0.0);
+    }
+    // ---- B2. susceptible drifts
+#pragma unroll 1
+    for (int i = lane; i < KS; i += 32) candidate(drift_S_cell(i, D, s, eff), s.Sx[i]);
+    return warp_min_d(tmin);
+}
+
+__device__ __forceinline__ int warp_sum32(int v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// drain the slow-path queue and the expansion queues of the warp (team kernel step 3b), then reset them
+__device__ __forceinline__ void w_drain(double tau, int *row, const Dims &D, const WS &s, const double *eff,
+                                        const DrawGeom &g, PhiloxCtx &ctx, LeapTally &tr) {
+    const int lane = threadIdx.x & 31, K = D.K, H = D.H, S = D.S;
+    int *qn = s.cnt;
+    const int ninv = qn[0], nptr = qn[1], nxm = qn[2], nxg = qn[3];
+    __syncwarp();
+    if (lane < 4) qn[lane] = 0;
+    // inversion entries sit at the bottom of the queue, PTRS entries at the top: one loop, at most one mixed round
+#pragma unroll 1
+    for (int k = lane; k < ninv + nptr; k += 32)
+        process_entry(k < ninv ? k : s.qcap - 1 - (k - ninv), tau, row, D, s, eff, g, ctx, tr);
+    const int nchM = 3 * D.U, nchG = (K - 1) * S;
+    const int itM = nxm * nchM, itX = itM + nxg * nchG;
+#pragma unroll 1
+    for (int it = lane; it < itX; it += 32) {
+        int owner, lc, lbase, domb;
+        if (it < itM) {
+            const int xi = it / nchM;
+            lc = it - xi * nchM;
+            owner = s.xq[xi];
+            lbase = 2;
+            domb = g.NBP;
+        } else {
+            const int it2 = it - itM, xi = it2 / nchG;
+            lc = it2 - xi * nchG;
+            owner = s.xq[64 + xi];
+            lbase = D.E;
+            domb = g.NBP + g.nbm;
+        }
+        const int p = owner >> D.hshift, h = owner & (H - 1);
+        Channel ch;
+        const int c = cell_channel(p, h, lbase + lc, D, s, eff, ch);
+        const double lam = ch.prop * tau;
+        if (lam > 0.0) {
+            ctx.c0 = (uint32_t)owner;
+            ctx.dom0 = (uint32_t)(domb + (lc >> 2));
+            const uint4 w = ctx.draw(0u);
+            const int n = (int)poisson_draw(lam, pick_word(w, lc & 3), ctx, lc & 3);
+            if (n != 0) {
+                row[c] = n;
+                book(ch, n, s, tr);
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(448, 1)
+    tau_warp_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
+                    const __grid_constant__ WarpLayout L, const __grid_constant__ WS s, const int variant) {
+    const Dims &D = st.D;
+    const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const DrawGeom g = draw_geom(D);
+    const bool prof = PROF;
+    unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tmark = 0;
+#define TW_MARK(k)                                    \
+    if (prof && lane == 0) {                          \
+        const long long now_ = clock64();             \
+        pc[k] += (unsigned long long)(now_ - tmark);  \
+        tmark = now_;                                 \
+    }
+
+    // Optional lockstep ("generations"): with a bit of `gsync` set every warp of the CTA meets at a CTA-wide barrier
+    // at that point of every leap (1: leap start, 2: before the draws, 4: before the apply pass), so the warps of
+    // an SM walk the same phase at the same time and share its instruction fetch.  A warp that ran out of
+    // replicates keeps answering the barriers until all are done (see the end of the kernel).
+    const int gsync = L.gsync;
+#define TW_GEN_SYNC() asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory")
+    int *done_warps = reinterpret_cast<int *>(smem_raw + L.o_done);
+    if (threadIdx.x == 0) *done_warps = 0;
+    // ---- CTA prologue: zero buffer, neighbour masks, the shared parameter point
+#pragma unroll 1
+    for (int i = threadIdx.x; i < TW_ZB / 16; i += blockDim.x) reinterpret_cast<int4 *>(smem_raw)[i] = make_int4(0, 0, 0, 0);
+    if (s.use_masks)
+#pragma unroll 1
+        for (int i = threadIdx.x; i < H; i += blockDim.x) {
+            unsigned long long m = 0ull;
+            for (int u = 0; u < D.U; u++)
+                for (int al = 1; al < 4; al++) m |= 1ull << (i ^ (al << (2 * u)));
+            s.nbrmask[i] = m;
+        }
+    if (L.par_shared) w_load_params(D, s, st.params + (size_t)L.pp0 * D.blob, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
+
+    for (int r = blockIdx.x * nw + wid; r < st.R; r += gridDim.x * nw) {
+        const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
+        double *eff_g = st.eff + (size_t)r * K * K;
+        long long *ctr = st.counters + (size_t)r * NCOUNT;
+        const uint64_t seed = st.seeds[r];
+        __syncwarp();
+        // ---- load the replicate
+        if (!L.par_shared) w_load_params(D, s, pp, lane, 32);
+#pragma unroll 1
+        for (int i = lane; i < K; i += 32) {
+            s.cd[i] = st.cd[(size_t)r * K + i];
+            s.c[i] = st.ceff[(size_t)r * K + i];
+            s.maxEBM[i] = st.maxEBM[(size_t)r * K + i];
+            s.lock[i] = st.lock[(size_t)r * K + i];
+        }
+        if (s.has_effS)
+#pragma unroll 1
+            for (int i = lane; i < K * K; i += 32) s.effS[i] = eff_g[i];
+        int ovf = 0;
+#pragma unroll 1
+        for (int i = lane; i < KH; i += 32) {
+            const long long v = st.I[(size_t)r * KH + i];
+            if (v > 2147483647LL || v < 0) ovf = 1;
+            s.Iraw[i] = (int)v;
+        }
+#pragma unroll 1
+        for (int i = lane; i < K; i += 32)
+            if (s.sizeD[i] > 2147483647.0) ovf = 1;  // counts are held as int32 and bounded by the deme size
+#pragma unroll 1
+        for (int i = lane; i < KS; i += 32) {
+            const long long v = st.Sx[(size_t)r * KS + i];
+            if (v > 2147483647LL || v < 0) ovf = 1;
+            s.Sx[i] = (double)v;
+        }
+        if (lane < 8) s.cnt[lane] = 0;
+        __syncwarp();
+        if (__any_sync(0xffffffffu, ovf)) {
+            if (lane == 0) st.err[r] |= ERR_COUNT_OVERFLOW;
+            continue;
+        }
+        const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
+        int nhap = 0;
+        int nAct = w_lists<false>(D, s, nhap);
+
+        bool restarted = false;
+        if (lane < 8) s.tally64[lane] = 0;
+        int flips_total = 0;
+        long long sC = ctr[C_S];
+        long long evptr = ctr[C_EVPTR], leaps = ctr[C_LEAPS];
+        double t = st.time[r];
+        unsigned epoch = st.epoch[r];
+        long long good_attempt = ctr[C_GOOD];
+        const long long ev_limit = evptr + a.iterations;
+        int *tau_counts = st.tau_counts + (size_t)r * st.leap_cap * D.Pp;
+
+        for (long long attempt = 0; attempt < a.attempts; attempt++) {
+            epoch++;
+            if (nAct != 0) {
+                while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
+                       (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
+                    int *row = tau_counts + (size_t)leaps * D.Pp;
+                    if (gsync) {
+                        TW_GEN_SYNC();
+                        if (gsync == 1) TW_GEN_SYNC();  // the end-of-kernel protocol needs two barriers per generation
+                    }
+                    if (prof && lane == 0) tmark = clock64();
+                    // ---- 0. zero-fill the dense row (TMA, asynchronous); 1-2. drifts and tau
+                    if (lane == 0) w_wipe_row_async(row, D.Pp * 4);
+                    double tau = w_drifts_and_tau(D, s, eff, nhap);
+                    TW_MARK(1)
+                    if (gsync & 2) TW_GEN_SYNC();
+                    if (prof && lane == 0) tmark = clock64();
+                    // ---- 3. draw; halve tau and redraw on an infeasible leap (:2316-2321)
+                    int tB = 0, tD = 0, tS = 0, tM = 0, tI = 0, tG = 0;
+                    for (unsigned retry = 0;; retry++) {
+                        // clear the per-leap deltas (chk and upd are adjacent)
+                        {
+                            int4 *z = reinterpret_cast<int4 *>(s.chkI.ptr());
+                            const int n16 = (int)((s.updI.off - s.chkI.off) + KH * 4 + 15) >> 4;
+#pragma unroll 1
+                            for (int i = lane; i < n16; i += 32) z[i] = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+                            for (int i = lane; i < KS; i += 32) s.dSx[i] = 0;
+                        }
+                        __syncwarp();
+                        LeapTally tr;
+                        tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
+                        PhiloxCtx ctx;
+                        ctx.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+                        ctx.c1 = (uint32_t)leaps;
+                        ctx.c2 = (retry & 0xffu) | (epoch << 8);
+                        ctx.dstride = (uint32_t)g.GS;
+                        const int n1 = nAct * g.NB1, nItems = n1 + K * g.G2;
+                        int *qn = s.cnt;  // [0] inversion [1] PTRS [2] expand-mut [3] expand-mig
+                        bool wiped = false;
+#pragma unroll 1
+                        for (int base = 0; base < nItems; base += 32) {
+                            const int item = base + lane;
+                            // ---- 3a. primary draws (identical to the team kernel's)
+                            if (item < n1) {
+                                // block 0 of every cell first (the lanes of a round then do the same kind of work)
+                                int ai = item, blk = 0;
+                                if (item >= nAct) {
+                                    const int it2 = item - nAct;
+                                    ai = it2 / (g.NB1 - 1);
+                                    blk = 1 + it2 - ai * (g.NB1 - 1);
+                                }
+                                const int cell = s.act[ai];
+                                const int p = cell >> D.hshift, h = cell & (H - 1);
+                                const double Ii = s.I[cell];
+                                double lam[4];
+                                if (blk == 0) {
+                                    lam[0] = s.d[h] * Ii * tau;
+                                    lam[1] = s.sr[h] * Ii * s.sm[p] * tau;
+                                    lam[2] = s.tmq[h] * Ii * tau;
+                                    lam[3] = K > 1 ? mig_total(p, h, Ii, D, s, eff) * tau : 0.0;
+                                    if (lam[2] > 0.0 && ((variant & 1) || lam[2] > TAU_THETA)) {
+                                        s.xq[atomicAdd(&qn[2], 1)] = cell;
+                                        lam[2] = 0.0;
+                                    }
+                                    if (lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA)) {
+                                        s.xq[64 + atomicAdd(&qn[3], 1)] = cell;
+                                        lam[3] = 0.0;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int q = 0; q < 4; q++) {
+                                        const int sn = (blk - 1) * 4 + q;
+                                        lam[q] = sn < S ? s.b[h] * s.sigT[sn * H + h] * s.c[p] * s.Sx[p * S + sn] * Ii * tau
+                                                        : 0.0;
+                                    }
+                                }
+                                if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
+                                    ctx.c0 = (uint32_t)cell;
+                                    ctx.dom0 = (uint32_t)blk;
+                                    const uint4 w = ctx.draw(0u);
+                                    const int code0 = blk == 0 ? 0 : 4 + (blk - 1) * 4;
+                                    if (lam[0] > 0.0) primary_draw(lam[0], w.x, cell, code0, s, qn);
+                                    if (lam[1] > 0.0) primary_draw(lam[1], w.y, cell, code0 + 1, s, qn);
+                                    if (lam[2] > 0.0) primary_draw(lam[2], w.z, cell, code0 + 2, s, qn);
+                                    if (lam[3] > 0.0) primary_draw(lam[3], w.w, cell, code0 + 3, s, qn);
+                                }
+                            } else if (item < nItems) {
+                                const int it = item - n1;
+                                const int p = it / g.G2, j = it - p * g.G2;
+                                double lam[4];
+                                Channel ch;
+#pragma unroll
+                                for (int q = 0; q < 4; q++) {
+                                    const int l = j * 4 + q;
+                                    lam[q] = 0.0;
+                                    if (l < D.SS1) {
+                                        susc_channel(p, l, D, s, ch);
+                                        lam[q] = ch.prop * tau;
+                                    }
+                                }
+                                if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
+                                    ctx.c0 = (uint32_t)(K * H + p);
+                                    ctx.dom0 = (uint32_t)j;
+                                    const uint4 w = ctx.draw(0u);
+                                    if (lam[0] > 0.0) primary_draw(lam[0], w.x, K * H + p, j * 4, s, qn);
+                                    if (lam[1] > 0.0) primary_draw(lam[1], w.y, K * H + p, j * 4 + 1, s, qn);
+                                    if (lam[2] > 0.0) primary_draw(lam[2], w.z, K * H + p, j * 4 + 2, s, qn);
+                                    if (lam[3] > 0.0) primary_draw(lam[3], w.w, K * H + p, j * 4 + 3, s, qn);
+                                }
+                            }
+                            __syncwarp();
+                            // ---- 3b. drain when the next round could overflow a queue, and after the last round
+                            const bool last = base + 32 >= nItems;
+                            if (last || qn[0] + qn[1] + 128 > s.qcap || qn[2] + 32 > 64 || qn[3] + 32 > 64) {
+                                if (!wiped) {
+                                    if (lane == 0) wipe_wait();  // the row is zero before any count is scattered into it
+                                    wiped = true;
+                                }
+                                w_drain(tau, row, D, s, eff, g, ctx, tr);
+                            }
+                        }
+                        TW_MARK(2)
+                        // ---- 4. feasibility (:2522-2528, quirk Q8) -- see the team kernel for the extra state test
+                        int bad = 0;
+#pragma unroll 1
+                        for (int i = lane; i < KH; i += 32) {
+                            const double sz = s.sizeD[i >> D.hshift];
+                            const double Iv = s.I[i];
+                            const double v = Iv + (double)s.chkI[i];
+                            const double u = Iv + (double)s.updI[i];
+                            if (v < 0.0 || v > sz || u < 0.0 || u > sz) bad = 1;
+                        }
+#pragma unroll 1
+                        for (int i = lane; i < KS; i += 32) {
+                            const double v = s.Sx[i] + (double)s.dSx[i];
+                            if (v < 0.0 || v > s.sizeD[i / S]) bad = 1;
+                        }
+                        bad = __any_sync(0xffffffffu, bad);
+                        tB = __reduce_add_sync(0xffffffffu, tr.B); tD = __reduce_add_sync(0xffffffffu, tr.Dd);
+                        tS = __reduce_add_sync(0xffffffffu, tr.Sm); tM = __reduce_add_sync(0xffffffffu, tr.M);
+                        tI = __reduce_add_sync(0xffffffffu, tr.I); tG = __reduce_add_sync(0xffffffffu, tr.G);
+                        TW_MARK(3)
+                        if (!bad) break;
+                        tau *= 0.5;
+                        if (lane == 0) w_wipe_row_async(row, D.Pp * 4);  // rare path
+                        if (retry >= 80) {  // tau * 2^-80: nothing can fire any more, yet the state fails the test
+                            if (lane == 0) st.err[r] |= ERR_TAU_STUCK;
+                            tau = 0.0;
+                            tB = tD = tS = tM = tI = tG = 0;
+                            {
+                                int4 *z = reinterpret_cast<int4 *>(s.chkI.ptr());
+                                const int n16 = (int)((s.updI.off - s.chkI.off) + KH * 4 + 15) >> 4;
+#pragma unroll 1
+                                for (int i = lane; i < n16; i += 32) z[i] = make_int4(0, 0, 0, 0);
+#pragma unroll 1
+                                for (int i = lane; i < KS; i += 32) s.dSx[i] = 0;
+                            }
+                            if (lane == 0) wipe_wait();
+                            __syncwarp();
+                            break;
+                        }
+                    }
+                    if (gsync & 4) TW_GEN_SYNC();
+                    if (prof && lane == 0) tmark = clock64();
+                    // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) fused with the list rebuild
+#pragma unroll 1
+                    for (int i = lane; i < KS; i += 32) s.Sx[i] += (double)s.dSx[i];
+                    nAct = w_lists<true>(D, s, nhap);
+                    t += tau;
+                    sC += tS;
+                    if (lane == 0) {
+                        long long *ty = s.tally64;
+                        ty[EV_BIRTH] += tB; ty[EV_DEATH] += tD; ty[EV_SAMPLING] += tS;
+                        ty[EV_MUTATION] += tM; ty[EV_SUSCCHANGE] += tI; ty[EV_MIGRATION] += tG;
+                        double *tau_tt = st.tau_tt + ((size_t)r * st.leap_cap + leaps) * 2;
+                        tau_tt[0] = t;
+                        tau_tt[1] = tau;
+                        st.ev_time[(size_t)r * st.ev_cap + evptr] = t;
+                        st.ev_desc[(size_t)r * st.ev_cap + evptr] = pack_multi((uint32_t)leaps);
+                    }
+                    leaps++;
+                    evptr++;
+                    TW_MARK(4)
+                    if (prof && lane == 0) pc[7] += 1;
+                    // ---- extinction test and CheckLockdown for every deme (:2326-2329)
+                    if (nAct == 0) break;
+                    flips_total += w_lockdown(st, r, D, s, pp, eff_g, t);
+                }
+            }
+            // ---- extinction-retry (:2331-2335): <= 100 log rows with iterations > 100 => Restart (:714-738)
+            if (evptr <= 100 && a.iterations > 100) {
+                evptr = 0;
+                leaps = 0;
+                sC = 0;
+                t = 0.0;
+                restarted = true;
+                if (lane < 8) s.tally64[lane] = 0;
+                __syncwarp();
+#pragma unroll 1
+                for (int i = lane; i < KH; i += 32) s.Iraw[i] = (int)st.initI[(size_t)r * KH + i];
+#pragma unroll 1
+                for (int i = lane; i < KS; i += 32) s.Sx[i] = (double)st.initSx[(size_t)r * KS + i];
+                __syncwarp();
+                nAct = w_lists<false>(D, s, nhap);
+                flips_total += w_lockdown(st, r, D, s, pp, eff_g, t);
+                good_attempt = 0;
+                if (lane == 0) ctr[C_MIGN] = 0;
+            } else {
+                good_attempt = attempt + 1;
+                break;
+            }
+        }
+
+        // ---- commit the replicate back to HBM
+        if (lane == 0) wipe_wait();
+        __syncwarp();
+        long long ginf = 0;
+#pragma unroll 1
+        for (int i = lane; i < KH; i += 32) {
+            const int v = s.Iraw[i];
+            st.I[(size_t)r * KH + i] = (long long)v;
+            ginf += v;
+        }
+        for (int o = 16; o > 0; o >>= 1) ginf += __shfl_xor_sync(0xffffffffu, ginf, o);
+#pragma unroll 1
+        for (int i = lane; i < KS; i += 32) st.Sx[(size_t)r * KS + i] = (long long)s.Sx[i];
+#pragma unroll 1
+        for (int i = lane; i < K; i += 32) {
+            st.cd[(size_t)r * K + i] = s.cd[i];
+            st.ceff[(size_t)r * K + i] = s.c[i];
+            st.maxEBM[(size_t)r * K + i] = s.maxEBM[i];
+            st.lock[(size_t)r * K + i] = s.lock[i];
+        }
+        if (lane == 0) {
+            for (int j = 0; j < 6; j++) ctr[j] = (restarted ? 0 : ctr[j]) + s.tally64[j];
+            ctr[C_S] = sC;
+            ctr[C_SWAP] += flips_total;
+            ctr[C_GOOD] = good_attempt;
+            ctr[C_EVPTR] = evptr;
+            ctr[C_LEAPS] = leaps;
+            ctr[C_GINF] = ginf;
+            st.time[r] = t;
+            st.epoch[r] = epoch;
+        }
+        __syncwarp();
+    }
+    if (prof && lane == 0)
+        for (int k = 0; k < 8; k++) atomicAdd(&g_tau_phase_cycles[k], pc[k]);
+    // ---- lockstep tail: this warp is out of replicates; keep answering the generation barriers until every
+    // warp is.  A warp announces itself after the last barrier of its last generation and before the first
+    // barrier of the next; the counter is read between the first and the second barrier of a generation, where
+    // no announcement can be in flight, so all idle warps take the same decision.
+    if (gsync) {
+        __syncwarp();
+        if (lane == 0) atomicAdd(done_warps, 1);
+        for (;;) {
+            TW_GEN_SYNC();
+            const bool all = *(volatile int *)done_warps >= nw;
+            if (gsync == 1) TW_GEN_SYNC();
+            if (gsync & 2) TW_GEN_SYNC();
+            if (gsync & 4) TW_GEN_SYNC();
+            if (all) break;
+        }
+    }
+#undef TW_GEN_SYNC
+#undef TW_MARK
+}
+
+}  // namespace vg
