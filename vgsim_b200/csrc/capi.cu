@@ -107,7 +107,7 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
     st.seeds = seeds;
     st.loc_cap = 64;
     if (dalloc(h, &st.loc_sp, R * st.loc_cap) || dalloc(h, &st.loc_t, R * st.loc_cap) ||
-        dalloc(h, &h->summaries, R * VGSIM_NSUMMARY)) {
+        dalloc(h, &h->summaries, R * VGSIM_NSUMMARY) || dalloc(h, &h->tau_order, 2 * R)) {
         vgsim_destroy(h);
         return 1;
     }
@@ -439,7 +439,7 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
     int uniform_pp = h->rep_pp_host.empty() ? 0 : h->rep_pp_host[0];  // every replicate on one parameter point?
     for (int v : h->rep_pp_host)
         if (v != uniform_pp) uniform_pp = -1;
-    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms, h->tau_variant, uniform_pp);
+    cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms, h->tau_variant, uniform_pp, h->tau_order);
     if (e != cudaSuccess) return fail(std::string("tau kernel: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(h->ev_k1, h->stream));
     h->ev_valid = true;

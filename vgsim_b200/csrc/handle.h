@@ -51,6 +51,7 @@ struct Handle {
     bool state_set = false;
     GenealogyBuffers gen;
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
+    int *tau_order = nullptr;      // [2R] scratch of the tau kernel's size-sorted schedule (weights, order)
     std::vector<int> rep_pp_host;  // host copy of the replicate -> parameter point map
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the last hot kernel on the handle's stream
     bool ev_valid = false;
@@ -58,7 +59,8 @@ struct Handle {
 };
 
 // kernels' host launchers (defined in the .cu files)
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp);
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp,
+                       int *order_buf);
 cudaError_t tau_phase_cycles(unsigned long long *out16, int reset);
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream);

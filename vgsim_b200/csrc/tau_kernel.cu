@@ -93,6 +93,7 @@ struct SArr {
 };
 
 struct TauShared {
+    static constexpr bool has_qin = false;
     // fp64 parameters
     SArr<double> b, d, sr, q, tmq, sigT, sb, T, sm, cd, c, mdiag, sizeD, maxEBM, startN, endN, effS;
     bool has_effS;
@@ -404,6 +405,20 @@ __device__ __forceinline__ double drift_I_cell(int i, const Dims &D, const SH &s
             v = Q * F + s.c[p] * s.b[h] * Iv * Q - (s.d[h] + s.sr[h] * s.sm[p] + s.tmq[h]) * Iv;
         }
         // mutation inflow from the haplotypes one substitution away that are present in this deme (:2400-2401)
+        if constexpr (SH::has_qin) {
+            if (s.use_masks) {  // same terms in the same order, rates read from the inflow table qin[h][neighbour slot]
+                const unsigned long long nb = s.nbrmask[h];
+                unsigned long long nm = s.rowmask[p] & nb;
+                const int n3 = 3 * U;
+                while (nm) {
+                    const int src = __ffsll((long long)nm) - 1;
+                    nm &= nm - 1;
+                    const int slot = __popcll(nb & ((1ull << src) - 1ull));
+                    v += s.qin[h * n3 + slot] * s.I[p * H + src];
+                }
+                return v;
+            }
+        }
         if (s.use_masks) {
             unsigned long long nm = s.rowmask[p] & s.nbrmask[h];
             while (nm) {
@@ -1208,7 +1223,8 @@ static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStre
 // holds (<= 16).  The team kernel (256-thread teams, CTA-wide generations) stays available as a parity tap:
 // variant bit 2, or VGSIM_TAU_KERNEL=team; VGSIM_TAU_CFG = "<teams>x<ctas per SM>" then overrides its shape.
 // VGSIM_TAU_WARPS caps the warps per CTA of the warp kernel (A/B measurements).
-cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp) {
+cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp,
+                       int *order_buf) {
     if ((long long)st.D.K * st.D.H + st.D.K >= (1 << 20)) return cudaErrorInvalidValue;  // owner id is packed in 20 bits
     bool team = (variant & 4) != 0;
     if (const char *e = getenv("VGSIM_TAU_KERNEL")) team = team || e[0] == 't';
@@ -1217,6 +1233,7 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
         if (const char *e = getenv("VGSIM_TAU_WARPS")) max_warps = atoi(e);
         if (max_warps < 1) max_warps = 1;
         WarpLayout L = warp_layout(st.D, uniform_pp >= 0, uniform_pp >= 0 ? uniform_pp : 0, 227 * 1024, max_warps);
+        L.gsync = 7;  // lockstep generations on by default (A/B: VGSIM_TAU_SYNC=0)
         if (const char *e = getenv("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
         if (L.nwarps >= 1 && st.D.K * st.D.H < 65536) {  // cell ids are held as uint16
             const WS ws = make_ws(L, st.D);
@@ -1225,7 +1242,14 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
             if (e != cudaSuccess) return e;
             int grid = (st.R + L.nwarps - 1) / L.nwarps;
             if (grid > num_sms) grid = num_sms;
-            kern<<<grid, L.nwarps * 32, L.total_bytes, stream>>>(st, a, L, ws, variant);
+            // size-sorted schedule (only useful with lockstep generations and more than one visit per CTA)
+            int sorted = L.gsync != 0 && order_buf != nullptr && st.R > grid * L.nwarps;
+            if (const char *e2 = getenv("VGSIM_TAU_SORT")) sorted = sorted && atoi(e2) != 0;
+            if (sorted) {
+                tau_weight_kernel<<<(st.R * 32 + 255) / 256, 256, 0, stream>>>(st, order_buf);
+                tau_order_kernel<<<1, 1024, 0, stream>>>(st.R, st.D.K * st.D.H, order_buf, order_buf + st.R);
+            }
+            kern<<<grid, L.nwarps * 32, L.total_bytes, stream>>>(st, a, L, ws, variant, sorted ? order_buf + st.R : nullptr);
             return cudaGetLastError();
         }
         // a single replicate's state does not fit one warp slice: fall through to the team kernel

@@ -21,7 +21,6 @@
 
 namespace vg {
 
-#define TW_ZB 8192  // CTA zero buffer: source of the TMA row wipes
 
 struct WarpLayout {
     int nwarps;        // warps (= replicates in flight) per CTA
@@ -32,7 +31,8 @@ struct WarpLayout {
     int p_b, p_d, p_sr, p_tmq, p_q, p_sigT, p_sb, p_T, p_sm, p_mdiag, p_sizeD, p_startN, p_endN, p_g, par_bytes;
     // inside a warp slice (bytes)
     int w_par, w_cd, w_c, w_maxEBM, w_eff, w_Sx, w_Bp, w_Rp, w_I, w_chk, w_upd, w_act, w_dSx, w_lock, w_tot, w_dstart,
-        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qhi, w_qoc, w_xq, w_cnt, w_tally;
+        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qhi, w_qoc, w_xq, w_cnt, w_tally, w_hidx, w_qtab;
+    int qtab_cap;      // doubles in the per-leap Q table (0: always recompute)
     int qcap, xcap;
     int has_eff, use_masks;
     int o_done, gsync;
@@ -57,7 +57,7 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     };
     // parameter block
     take(L.p_b, H * 8, 8); take(L.p_d, H * 8, 8); take(L.p_sr, H * 8, 8); take(L.p_tmq, H * 8, 8);
-    take(L.p_q, H * U * 3 * 8, 8); take(L.p_sigT, S * H * 8, 8); take(L.p_sb, S * H * 8, 8); take(L.p_T, S * S * 8, 8);
+    take(L.p_q, L.use_masks ? H * U * 3 * 8 : 0, 8);  /* qin: inflow rates by (target haplotype, neighbour slot) */ take(L.p_sigT, S * H * 8, 8); take(L.p_sb, S * H * 8, 8); take(L.p_T, S * S * 8, 8);
     take(L.p_sm, K * 8, 8); take(L.p_mdiag, K * 8, 8); take(L.p_sizeD, K * 8, 8); take(L.p_startN, K * 8, 8);
     take(L.p_endN, K * 8, 8); take(L.p_g, H * 4, 8);
     L.par_bytes = (o + 15) & ~15;
@@ -81,9 +81,13 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     take(L.w_hlist, H * 4, 4);
     take(L.w_qhi, L.qcap * 4, 4); take(L.w_qoc, L.qcap * 4, 4); take(L.w_xq, 2 * L.xcap * 4, 4);
     take(L.w_cnt, 8 * 4, 4);
-    L.warp_bytes = (o + 15) & ~15;
+    take(L.w_hidx, H * 2, 2);
+    const int fixed_bytes = (o + 15) & ~15;
+    L.w_qtab = fixed_bytes;
+    L.qtab_cap = 0;
+    L.warp_bytes = fixed_bytes;
     // CTA
-    o = TW_ZB;
+    o = 0;
     L.o_done = o;
     o += 16;
     L.o_par = o;
@@ -96,6 +100,12 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     if (nw > max_warps) nw = max_warps;
     if (nw > 14) nw = 14;  // 448 threads: 144 registers per thread; 148 x 14 = 2072 replicates in flight
     L.nwarps = nw;
+    if (nw >= 1) {  // what is left of the shared memory holds the per-leap table of Q[p, present h]
+        int spare = ((max_bytes - o) / nw - L.warp_bytes) & ~15;
+        if (spare > KH * 8) spare = (KH * 8 + 15) & ~15;
+        L.qtab_cap = spare / 8;
+        L.warp_bytes += spare;
+    }
     L.total_bytes = o + (nw > 0 ? nw : 0) * L.warp_bytes;
     return L;
 }
@@ -116,26 +126,43 @@ struct WIval {  // infectious counts: int32 in shared memory, fp64 to the arithm
     WArr<int> raw;
     __device__ __forceinline__ double operator[](int i) const { return (double)raw.ptr()[i]; }
 };
-struct WQval {  // Q[p,h] = sum_s Sx[p,s] sigma[s,h], recomputed on use (same order as the team kernel's q_pass)
-    WArr<double> Sx, sg;
+struct WQval {  // Q[p,h] = sum_s Sx[p,s] sigma[s,h] (same order as the team kernel's q_pass): read from the per-leap
+                // table of (deme, present haplotype) pairs when it fits (cnt[4] = its row stride), else recomputed
+    WArr<double> Sx, sg, tab;
+    WArr<unsigned short> hidx;
+    WArr<int> cnt;
     int H, S, hshift;
     __device__ __forceinline__ double operator[](int i) const {
-        const double *sx = Sx.ptr(), *sig = sg.ptr();
         const int p = i >> hshift, h = i & (H - 1);
+        const int stride = cnt.ptr()[4];
+        if (stride > 0) return tab.ptr()[p * stride + hidx.ptr()[h]];
+        const double *sx = Sx.ptr(), *sig = sg.ptr();
         double Q = 0.0;
 #pragma unroll 1
         for (int sn = 0; sn < S; sn++) Q += sx[p * S + sn] * sig[sn * H + h];
         return Q;
     }
 };
+struct WGq {  // mutation channel rates q[h][u][k]: read from the parameter blob in global memory (cold: a mutation
+              // event or an expanded group); the hot drift sums use the shared-memory inflow table qin instead
+    WArr<long long> slot;  // tally64: entry 7 holds the replicate's blob pointer
+    int o_q;
+    __device__ __forceinline__ double operator[](int i) const {
+        return __ldg(reinterpret_cast<const double *>(slot.ptr()[7]) + o_q + i);
+    }
+};
 struct WS {
-    WArr<double> b, d, sr, q, tmq, sigT, sb, T, sm, mdiag, sizeD, startN, endN;
+    static constexpr bool has_qin = true;
+    WArr<double> b, d, sr, qin, tmq, sigT, sb, T, sm, mdiag, sizeD, startN, endN;
+    WGq q;
     WArr<int> g;
     WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp;
     WIval I;
     WQval Qm;
     WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, xq, cnt;
-    WArr<unsigned short> act;
+    WArr<unsigned short> act, hidx;
+    WArr<double> qtab;
+    int qtab_cap;
     WArr<long long> tally64;
     WArr<unsigned long long> rowmask, nbrmask;
     int qcap;
@@ -149,18 +176,23 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     auto P = [&](int o) { WArr<double> a; a.off = pb + o; a.scale = ps; return a; };
     auto Wd = [&](int o) { WArr<double> a; a.off = wb + o; a.scale = ws; return a; };
     auto Wi = [&](int o) { WArr<int> a; a.off = wb + o; a.scale = ws; return a; };
-    s.b = P(L.p_b); s.d = P(L.p_d); s.sr = P(L.p_sr); s.tmq = P(L.p_tmq); s.q = P(L.p_q); s.sigT = P(L.p_sigT);
+    s.b = P(L.p_b); s.d = P(L.p_d); s.sr = P(L.p_sr); s.tmq = P(L.p_tmq); s.qin = P(L.p_q); s.sigT = P(L.p_sigT);
     s.sb = P(L.p_sb); s.T = P(L.p_T); s.sm = P(L.p_sm); s.mdiag = P(L.p_mdiag); s.sizeD = P(L.p_sizeD);
     s.startN = P(L.p_startN); s.endN = P(L.p_endN);
     s.g.off = pb + L.p_g; s.g.scale = ps;
     s.cd = Wd(L.w_cd); s.c = Wd(L.w_c); s.maxEBM = Wd(L.w_maxEBM); s.effS = Wd(L.w_eff);
     s.Sx = Wd(L.w_Sx); s.Bp = Wd(L.w_Bp); s.Rp = Wd(L.w_Rp);
     s.Iraw = Wi(L.w_I); s.I.raw = s.Iraw;
-    s.Qm.Sx = s.Sx; s.Qm.sg = s.sigT; s.Qm.H = D.H; s.Qm.S = D.S; s.Qm.hshift = D.hshift;
     s.chkI = Wi(L.w_chk); s.updI = Wi(L.w_upd); s.act.off = wb + L.w_act; s.act.scale = ws; s.dSx = Wi(L.w_dSx); s.lock = Wi(L.w_lock);
     s.tot = Wi(L.w_tot); s.dstart = Wi(L.w_dstart); s.colcnt = Wi(L.w_colcnt); s.colmask = Wi(L.w_colmask);
     s.hlist = Wi(L.w_hlist); s.qhi = Wi(L.w_qhi); s.qoc = Wi(L.w_qoc); s.xq = Wi(L.w_xq); s.cnt = Wi(L.w_cnt);
     s.tally64.off = wb + L.w_tally; s.tally64.scale = ws;
+    s.q.slot = s.tally64; s.q.o_q = D.o_q;
+    s.hidx.off = wb + L.w_hidx; s.hidx.scale = ws;
+    s.qtab = Wd(L.w_qtab);
+    s.qtab_cap = L.qtab_cap;
+    s.Qm.Sx = s.Sx; s.Qm.sg = s.sigT; s.Qm.H = D.H; s.Qm.S = D.S; s.Qm.hshift = D.hshift;
+    s.Qm.tab = s.qtab; s.Qm.hidx = s.hidx; s.Qm.cnt = s.cnt;
     s.rowmask.off = wb + L.w_rowmask; s.rowmask.scale = ws;
     s.nbrmask.off = L.o_nbr; s.nbrmask.scale = 0;
     s.qcap = L.qcap;
@@ -169,17 +201,14 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     return s;
 }
 
-// TMA zero-fill of a dense log row out of the CTA zero buffer at shared-memory offset 0 (issued by one lane)
-__device__ __forceinline__ void w_wipe_row_async(int *row, int bytes) {
-    const unsigned src = (unsigned)__cvta_generic_to_shared(smem_raw);
-    const unsigned long long dst = (unsigned long long)(uintptr_t)row;
-    asm volatile("fence.proxy.async;" ::: "memory");  // earlier generic-proxy stores to this row (a failed draw) stay before the wipe
-#pragma unroll 1
-    for (int off = 0; off < bytes; off += TW_ZB) {
-        const int n = bytes - off < TW_ZB ? bytes - off : TW_ZB;
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(src), "r"(n) : "memory");
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+// Zero-fill of a dense log row: 16-byte stores, one 512-byte line group per warp instruction (206 instructions
+// for a T3 row).  The TMA bulk-copy wipe of the team kernel stalled its issuing lane for 14 % of all warp
+// samples here (ncu, profiles/r1_f_*): with one warp per replicate nobody else hides that, plain stores do.
+// The later scatter into the row is ordered behind these stores by the __syncwarp()s in between.
+__device__ __forceinline__ void w_wipe_row(int *row, int n16) {
+    int4 *z = reinterpret_cast<int4 *>(row);
+#pragma unroll 4
+    for (int i = threadIdx.x & 31; i < n16; i += 32) z[i] = make_int4(0, 0, 0, 0);
 }
 
 struct LaneGroup {  // rates.cuh group interface for one warp
@@ -234,8 +263,23 @@ __device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const 
         s.tmq[i] = pp[D.o_tmq + i];
         s.g[i] = (int)pp[D.o_g + i];
     }
+    // qin[h][j]: rate of the mutation channel that turns the j-th (ascending) one-substitution neighbour of h into h
+    // (mask path only; nbrmask is complete by now)
+    if (s.use_masks) {
 #pragma unroll 1
-    for (int i = t; i < H * U * 3; i += n) s.q[i] = pp[D.o_q + i];
+        for (int i = t; i < H * U * 3; i += n) {
+            const int h = i / (3 * U), j = i - h * 3 * U;
+            unsigned long long m = s.nbrmask[h];
+            for (int c = 0; c < j; c++) m &= m - 1;
+            const int src = __ffsll((long long)m) - 1;
+            const int x = src ^ h;
+            const int sh = (31 - __clz(x)) & ~1;
+            const int u = U - 1 - (sh >> 1);
+            const int as = (src >> sh) & 3, hu = (h >> sh) & 3;
+            const int k = hu - (hu > as ? 1 : 0);
+            s.qin[i] = pp[D.o_q + (src * U + u) * 3 + k];
+        }
+    }
 #pragma unroll 1
     for (int i = t; i < S * H; i += n) {
         s.sigT[i] = pp[D.o_sigT + i];
@@ -307,10 +351,29 @@ __device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap) {
         const int h = base + lane;
         const bool on = h < H && s.colcnt[h] != 0;
         const unsigned m = __ballot_sync(0xffffffffu, on);
-        if (on) s.hlist[nh + __popc(m & ((1u << lane) - 1u))] = h;
+        if (on) {
+            const int pos = nh + __popc(m & ((1u << lane) - 1u));
+            s.hlist[pos] = h;
+            s.hidx[h] = (unsigned short)pos;
+        }
         nh += __popc(m);
     }
     nhap = nh;
+    __syncwarp();
+    // per-leap table Q[p, j] for the present haplotypes hlist[j] (the susceptible counts are final for this leap)
+    const bool tab = K * nh <= s.qtab_cap;
+    if (tab) {
+        const int S = D.S;
+#pragma unroll 1
+        for (int i = lane; i < K * nh; i += 32) {
+            const int p = i / nh, h = s.hlist[i - p * nh];
+            double Q = 0.0;
+#pragma unroll 1
+            for (int sn = 0; sn < S; sn++) Q += s.Sx[p * S + sn] * s.sigT[sn * H + h];
+            s.qtab[i] = Q;
+        }
+    }
+    if (lane == 0) s.cnt[4] = tab ? nh : 0;
     __syncwarp();
     return cnt;
 }
@@ -436,10 +499,46 @@ __device__ __forceinline__ void w_drain(double tau, int *row, const Dims &D, con
     __syncwarp();
 }
 
+// ---- size-sorted schedule -----------------------------------------------------------------------------
+// With lockstep generations a leap costs every warp of the CTA as much as it costs the slowest one, and a
+// leap's cost grows with the number of infectious cells of the replicate.  So replicates of similar size share
+// a CTA: weight = #infectious cells, sorted descending, consecutive groups of `nwarps` go to one CTA visit, and
+// the CTAs walk the groups boustrophedon (b, 2G-1-b, 2G+b, ...) so that every CTA gets the same mix of heavy and
+// light groups.  Scheduling only: every replicate's result is a function of its own state and seed.
+__global__ void tau_weight_kernel(const DevState st, int *weight) {
+    const int lane = threadIdx.x & 31, KH = st.D.K * st.D.H;
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= st.R) return;
+    int n = 0;
+    for (int i = lane; i < KH; i += 32) n += st.I[(size_t)r * KH + i] != 0;
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) weight[r] = n;
+}
+// one CTA: counting sort by weight (descending) into order[]
+__global__ void __launch_bounds__(1024) tau_order_kernel(int R, int KH, const int *weight, int *order) {
+    __shared__ int bins[2049];
+    const int NB = 2048;
+    for (int i = threadIdx.x; i <= NB; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int b = NB - 1 - (int)(((long long)weight[r] * (NB - 1)) / (KH > 0 ? KH : 1));  // heavy first
+        atomicAdd(&bins[b + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int i = 0; i < NB; i++) bins[i + 1] += bins[i];
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int b = NB - 1 - (int)(((long long)weight[r] * (NB - 1)) / (KH > 0 ? KH : 1));
+        order[atomicAdd(&bins[b], 1)] = r;
+    }
+}
+
 template <bool PROF>
 __global__ void __launch_bounds__(448, 1)
     tau_warp_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
-                    const __grid_constant__ WarpLayout L, const __grid_constant__ WS s, const int variant) {
+                    const __grid_constant__ WarpLayout L, const __grid_constant__ WS s, const int variant,
+                    const int *__restrict__ order) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -462,9 +561,7 @@ __global__ void __launch_bounds__(448, 1)
 #define TW_GEN_SYNC() asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory")
     int *done_warps = reinterpret_cast<int *>(smem_raw + L.o_done);
     if (threadIdx.x == 0) *done_warps = 0;
-    // ---- CTA prologue: zero buffer, neighbour masks, the shared parameter point
-#pragma unroll 1
-    for (int i = threadIdx.x; i < TW_ZB / 16; i += blockDim.x) reinterpret_cast<int4 *>(smem_raw)[i] = make_int4(0, 0, 0, 0);
+    // ---- CTA prologue: neighbour masks, the shared parameter point
     if (s.use_masks)
 #pragma unroll 1
         for (int i = threadIdx.x; i < H; i += blockDim.x) {
@@ -473,11 +570,23 @@ __global__ void __launch_bounds__(448, 1)
                 for (int al = 1; al < 4; al++) m |= 1ull << (i ^ (al << (2 * u)));
             s.nbrmask[i] = m;
         }
+    __syncthreads();  // nbrmask is read by the parameter staging
     if (L.par_shared) w_load_params(D, s, st.params + (size_t)L.pp0 * D.blob, threadIdx.x, blockDim.x);
     __syncthreads();
-    if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async-proxy reads
 
-    for (int r = blockIdx.x * nw + wid; r < st.R; r += gridDim.x * nw) {
+    for (int visit = 0;; visit++) {
+        int r;
+        if (order) {  // boustrophedon walk over the size-sorted groups
+            const int G = gridDim.x;
+            const int grp = (visit & 1) ? (visit + 1) * G - 1 - (int)blockIdx.x : visit * G + (int)blockIdx.x;
+            if ((long long)(visit & ~1) * G * nw >= st.R) break;  // both groups of this pair of visits are past the end
+            const int pos = grp * nw + wid;
+            if (pos >= st.R) continue;
+            r = order[pos];
+        } else {
+            r = (visit * (int)gridDim.x + (int)blockIdx.x) * nw + wid;
+            if (r >= st.R) break;
+        }
         const double *pp = st.params + (size_t)st.rep_pp[r] * D.blob;
         double *eff_g = st.eff + (size_t)r * K * K;
         long long *ctr = st.counters + (size_t)r * NCOUNT;
@@ -522,7 +631,8 @@ __global__ void __launch_bounds__(448, 1)
         int nAct = w_lists<false>(D, s, nhap);
 
         bool restarted = false;
-        if (lane < 8) s.tally64[lane] = 0;
+        if (lane < 6) s.tally64[lane] = 0;
+        if (lane == 7) s.tally64[7] = (long long)(uintptr_t)pp;
         int flips_total = 0;
         long long sC = ctr[C_S];
         long long evptr = ctr[C_EVPTR], leaps = ctr[C_LEAPS];
@@ -543,8 +653,8 @@ __global__ void __launch_bounds__(448, 1)
                         if (gsync == 1) TW_GEN_SYNC();  // the end-of-kernel protocol needs two barriers per generation
                     }
                     if (prof && lane == 0) tmark = clock64();
-                    // ---- 0. zero-fill the dense row (TMA, asynchronous); 1-2. drifts and tau
-                    if (lane == 0) w_wipe_row_async(row, D.Pp * 4);
+                    // ---- 0. zero-fill the dense row; 1-2. drifts and tau
+                    w_wipe_row(row, D.Pp >> 2);
                     double tau = w_drifts_and_tau(D, s, eff, nhap);
                     TW_MARK(1)
                     if (gsync & 2) TW_GEN_SYNC();
@@ -571,7 +681,6 @@ __global__ void __launch_bounds__(448, 1)
                         ctx.dstride = (uint32_t)g.GS;
                         const int n1 = nAct * g.NB1, nItems = n1 + K * g.G2;
                         int *qn = s.cnt;  // [0] inversion [1] PTRS [2] expand-mut [3] expand-mig
-                        bool wiped = false;
 #pragma unroll 1
                         for (int base = 0; base < nItems; base += 32) {
                             const int item = base + lane;
@@ -647,10 +756,6 @@ __global__ void __launch_bounds__(448, 1)
                             // ---- 3b. drain when the next round could overflow a queue, and after the last round
                             const bool last = base + 32 >= nItems;
                             if (last || qn[0] + qn[1] + 128 > s.qcap || qn[2] + 32 > 64 || qn[3] + 32 > 64) {
-                                if (!wiped) {
-                                    if (lane == 0) wipe_wait();  // the row is zero before any count is scattered into it
-                                    wiped = true;
-                                }
                                 w_drain(tau, row, D, s, eff, g, ctx, tr);
                             }
                         }
@@ -677,7 +782,7 @@ __global__ void __launch_bounds__(448, 1)
                         TW_MARK(3)
                         if (!bad) break;
                         tau *= 0.5;
-                        if (lane == 0) w_wipe_row_async(row, D.Pp * 4);  // rare path
+                        w_wipe_row(row, D.Pp >> 2);  // rare path
                         if (retry >= 80) {  // tau * 2^-80: nothing can fire any more, yet the state fails the test
                             if (lane == 0) st.err[r] |= ERR_TAU_STUCK;
                             tau = 0.0;
@@ -690,7 +795,6 @@ __global__ void __launch_bounds__(448, 1)
 #pragma unroll 1
                                 for (int i = lane; i < KS; i += 32) s.dSx[i] = 0;
                             }
-                            if (lane == 0) wipe_wait();
                             __syncwarp();
                             break;
                         }
@@ -729,7 +833,7 @@ __global__ void __launch_bounds__(448, 1)
                 sC = 0;
                 t = 0.0;
                 restarted = true;
-                if (lane < 8) s.tally64[lane] = 0;
+                if (lane < 6) s.tally64[lane] = 0;
                 __syncwarp();
 #pragma unroll 1
                 for (int i = lane; i < KH; i += 32) s.Iraw[i] = (int)st.initI[(size_t)r * KH + i];
@@ -747,7 +851,6 @@ __global__ void __launch_bounds__(448, 1)
         }
 
         // ---- commit the replicate back to HBM
-        if (lane == 0) wipe_wait();
         __syncwarp();
         long long ginf = 0;
 #pragma unroll 1
