@@ -738,8 +738,11 @@ __device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner,
 // multinomial split of an aggregated total: n events of cell (p,h), each assigned to one channel of the
 // group with probability prop_channel / prop_total (exact: independent Poissons conditioned on their sum)
 template <class SH>
-static __device__ __noinline__ void split_total(int n, int p, int h, int code, int *row, const Dims &D, const SH &s,
-                                                const double *eff, const DrawGeom &g, PhiloxCtx ctx, LeapTally &tr) {
+static __device__ __noinline__ int split_total(int n, int p, int h, int code, int *row, const Dims &D, const SH &s,
+                                                const double *eff, const DrawGeom &g, PhiloxCtx ctx) {
+    LeapTally tr;  // the events are all of one type: the caller tallies the returned count
+    tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
+    int booked = 0;
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     const int cell = p * H + h;
     const double Ii = s.I[cell];
@@ -796,8 +799,10 @@ static __device__ __noinline__ void split_total(int n, int p, int h, int code, i
             int c = cell_channel(p, h, l, D, s, eff, ch);
             atomicAdd(&row[c], 1);
             book(ch, 1, s, tr);
+            booked++;
         }
     }
+    return booked;
 }
 
 // one slow-path queue entry: recompute its lambda (same expression as the primary pass), finish the Poisson
@@ -828,7 +833,11 @@ __device__ __forceinline__ void process_entry(int e, double tau, int *row, const
         const double lam = code == 2 ? s.tmq[h] * Ii * tau : mig_total(p, h, Ii, D, s, eff) * tau;
         ctx.dom0 = 0u;
         const int n = (int)poisson_inversion(lam, hi, ctx, code);
-        if (n != 0) split_total(n, p, h, code, row, D, s, eff, g, ctx, tr);
+        if (n != 0) {
+            const int nb = split_total(n, p, h, code, row, D, s, eff, g, ctx);
+            if (code == 2) tr.M += nb;
+            else tr.G += nb;
+        }
         return;
     }
     const int l = code == 0 ? 0 : code == 1 ? 1 : 2 + 3 * D.U + (code - 4);

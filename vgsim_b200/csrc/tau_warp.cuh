@@ -211,6 +211,30 @@ __device__ __forceinline__ void w_wipe_row(int *row, int n16) {
     for (int i = threadIdx.x & 31; i < n16; i += 32) z[i] = make_int4(0, 0, 0, 0);
 }
 
+// The wipe of the NEXT leap's row is spread over the dense loops of the current leap (a few stores per round):
+// issued in one burst at the top of a leap, the 14 lockstepped warps of every SM push 1.5 MB into the store path at
+// the same moment and sit on it (18 % of all warp samples, ncu profiles/r1_g_*).
+struct RowWiper {
+    int4 *z;   // row being wiped
+    int idx;   // this lane's next int4 index; >= n16 when there is nothing (left) to do
+    __device__ __forceinline__ void begin(int *row) {
+        z = reinterpret_cast<int4 *>(row);
+        idx = threadIdx.x & 31;
+    }
+    __device__ __forceinline__ void idle() { idx = 0x3fffffff; }
+    __device__ __forceinline__ void some(int k, int n16) {
+#pragma unroll 1
+        for (int j = 0; j < k; j++) {
+            if (idx < n16) z[idx] = make_int4(0, 0, 0, 0);
+            idx += 32;
+        }
+    }
+    __device__ __forceinline__ void finish(int n16) {
+#pragma unroll 4
+        for (; idx < n16; idx += 32) z[idx] = make_int4(0, 0, 0, 0);
+    }
+};
+
 struct LaneGroup {  // rates.cuh group interface for one warp
     __device__ __forceinline__ int tid() const { return threadIdx.x & 31; }
     __device__ __forceinline__ int size() const { return 32; }
@@ -301,7 +325,7 @@ __device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const 
 // presence masks / counts, per-deme totals, the ascending list of haplotypes present anywhere.  Returns the
 // number of infectious cells; nhap gets the number of present haplotypes.  One warp, ends with __syncwarp().
 template <bool APPLY>
-__device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap) {
+__device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, RowWiper &wp, int wk, int n16) {
     const int lane = threadIdx.x & 31, K = D.K, H = D.H, KH = K * H;
 #pragma unroll 1
     for (int i = lane; i < H; i += 32) s.colcnt[i] = 0;  // (= colmask on the mask path)
@@ -324,6 +348,7 @@ __device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap) {
                 I[i] = v;
             }
         }
+        if (APPLY) wp.some(wk, n16);
         const bool on = v != 0;
         const unsigned m = __ballot_sync(0xffffffffu, on);
         const int pos = cnt + __popc(m & ((1u << lane) - 1u));
@@ -384,7 +409,8 @@ __device__ __forceinline__ double warp_min_d(double v) {
 }
 
 // Drifts and tau (ChooseTau :2432-2450) of the warp's state; same sums as the team kernel's drifts_and_tau.
-__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, const double *eff, int nhap) {
+__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, const double *eff, int nhap, RowWiper &wp,
+                                                   int wk, int n16) {
     const int K = D.K, H = D.H, S = D.S, KS = K * S;
     const int lane = threadIdx.x & 31;
     // ---- A. pressure / return-flow sums per (deme, group): 8 lanes per sum, fixed butterfly
@@ -437,6 +463,7 @@ __device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, c
     // ---- B1b. every other cell: mutation inflow only (its count is 0)
 #pragma unroll 1
     for (int i = lane; i < K * H; i += 32) {
+        wp.some(wk, n16);
         if (s.colcnt[i & (H - 1)] != 0) continue;
         candidate(drift_I_cell(i, D, s, eff), 0.0);
     }
@@ -543,6 +570,9 @@ __global__ void __launch_bounds__(448, 1)
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const DrawGeom g = draw_geom(D);
+    const int n16 = D.Pp >> 2;  // int4 stores per log row
+    // stores per lane per dense-loop round so that three dense loops (drift, feasibility, apply) cover a row
+    const int wk = ((n16 + 31) / 32 + 3 * ((KH + 31) / 32) - 1) / (3 * ((KH + 31) / 32));
     const bool prof = PROF;
     unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark = 0;
@@ -628,7 +658,10 @@ __global__ void __launch_bounds__(448, 1)
         }
         const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
         int nhap = 0;
-        int nAct = w_lists<false>(D, s, nhap);
+        RowWiper wp;
+        wp.idle();
+        int pre_row = -1;  // leap whose row the wiper is working on / has finished
+        int nAct = w_lists<false>(D, s, nhap, wp, 0, n16);
 
         bool restarted = false;
         if (lane < 6) s.tally64[lane] = 0;
@@ -653,9 +686,18 @@ __global__ void __launch_bounds__(448, 1)
                         if (gsync == 1) TW_GEN_SYNC();  // the end-of-kernel protocol needs two barriers per generation
                     }
                     if (prof && lane == 0) tmark = clock64();
-                    // ---- 0. zero-fill the dense row; 1-2. drifts and tau
-                    w_wipe_row(row, D.Pp >> 2);
-                    double tau = w_drifts_and_tau(D, s, eff, nhap);
+                    // ---- 0. this leap's row: finish the wipe started during the previous leap (or do all of it: first
+                    //         leap of the call, Restart), then start on the next row; 1-2. drifts and tau
+                    if (pre_row != (int)leaps) wp.begin(row);
+                    wp.finish(n16);
+                    if (leaps + 1 < st.leap_cap && evptr + 1 < ev_limit && evptr + 1 < st.ev_cap) {
+                        wp.begin(row + D.Pp);
+                        pre_row = (int)leaps + 1;
+                    } else {
+                        wp.idle();
+                        pre_row = -1;
+                    }
+                    double tau = w_drifts_and_tau(D, s, eff, nhap, wp, wk, n16);
                     TW_MARK(1)
                     if (gsync & 2) TW_GEN_SYNC();
                     if (prof && lane == 0) tmark = clock64();
@@ -764,6 +806,7 @@ __global__ void __launch_bounds__(448, 1)
                         int bad = 0;
 #pragma unroll 1
                         for (int i = lane; i < KH; i += 32) {
+                            wp.some(wk, n16);
                             const double sz = s.sizeD[i >> D.hshift];
                             const double Iv = s.I[i];
                             const double v = Iv + (double)s.chkI[i];
@@ -804,7 +847,7 @@ __global__ void __launch_bounds__(448, 1)
                     // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) fused with the list rebuild
 #pragma unroll 1
                     for (int i = lane; i < KS; i += 32) s.Sx[i] += (double)s.dSx[i];
-                    nAct = w_lists<true>(D, s, nhap);
+                    nAct = w_lists<true>(D, s, nhap, wp, wk, n16);
                     t += tau;
                     sC += tS;
                     if (lane == 0) {
@@ -840,7 +883,7 @@ __global__ void __launch_bounds__(448, 1)
 #pragma unroll 1
                 for (int i = lane; i < KS; i += 32) s.Sx[i] = (double)st.initSx[(size_t)r * KS + i];
                 __syncwarp();
-                nAct = w_lists<false>(D, s, nhap);
+                nAct = w_lists<false>(D, s, nhap, wp, 0, n16);
                 flips_total += w_lockdown(st, r, D, s, pp, eff_g, t);
                 good_attempt = 0;
                 if (lane == 0) ctr[C_MIGN] = 0;
