@@ -713,6 +713,16 @@ __device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
 template <class SH>
 __device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims &D, const SH &s, const double *eff) {
     double acc = 0.0;
+    if constexpr (SH::has_qin) {  // warp kernel: the per-leap Q table, row stride and column hoisted out of the loop
+        const int stride = s.cnt[4];
+        if (stride > 0) {
+            const double *tab = s.qtab.ptr() + s.hidx[h];
+#pragma unroll 1
+            for (int tp = 0; tp < D.K; tp++)
+                if (tp != p) acc += eff[tp * D.K + p] * tab[tp * stride];
+            return Ii * s.b[h] * s.mdiag[p] * acc;
+        }
+    }
     for (int tp = 0; tp < D.K; tp++)
         if (tp != p) acc += eff[tp * D.K + p] * s.Qm[tp * D.H + h];
     return Ii * s.b[h] * s.mdiag[p] * acc;
@@ -1242,11 +1252,12 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
         if (const char *e = getenv("VGSIM_TAU_WARPS")) max_warps = atoi(e);
         if (max_warps < 1) max_warps = 1;
         WarpLayout L = warp_layout(st.D, uniform_pp >= 0, uniform_pp >= 0 ? uniform_pp : 0, 227 * 1024, max_warps);
-        L.gsync = 7;  // lockstep generations on by default (A/B: VGSIM_TAU_SYNC=0)
+        L.gsync = 3;  // lockstep generations on by default: leap start + before the draws (A/B: VGSIM_TAU_SYNC=0..7)
         if (const char *e = getenv("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
         if (L.nwarps >= 1 && st.D.K * st.D.H < 65536) {  // cell ids are held as uint16
             const WS ws = make_ws(L, st.D);
-            auto kern = (variant & 2) ? tau_warp_kernel<true> : tau_warp_kernel<false>;
+            auto kern = L.has_eff ? ((variant & 2) ? tau_warp_kernel<true, true> : tau_warp_kernel<false, true>)
+                                  : ((variant & 2) ? tau_warp_kernel<true, false> : tau_warp_kernel<false, false>);
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
             if (e != cudaSuccess) return e;
             int grid = (st.R + L.nwarps - 1) / L.nwarps;

@@ -222,11 +222,21 @@ struct RowWiper {
         idx = threadIdx.x & 31;
     }
     __device__ __forceinline__ void idle() { idx = 0x3fffffff; }
-    __device__ __forceinline__ void some(int k, int n16) {
+    // k4 groups of four stores per lane (2 KB per warp and group)
+    __device__ __forceinline__ void some(int k4, int n16) {
 #pragma unroll 1
-        for (int j = 0; j < k; j++) {
-            if (idx < n16) z[idx] = make_int4(0, 0, 0, 0);
-            idx += 32;
+        for (int j = 0; j < k4; j++) {
+            if (idx + 96 < n16) {
+                int4 *q = z + idx;
+                q[0] = make_int4(0, 0, 0, 0);
+                q[32] = make_int4(0, 0, 0, 0);
+                q[64] = make_int4(0, 0, 0, 0);
+                q[96] = make_int4(0, 0, 0, 0);
+            } else {
+#pragma unroll 1
+                for (int i = idx; i < n16 && i < idx + 128; i += 32) z[i] = make_int4(0, 0, 0, 0);
+            }
+            idx += 128;
         }
     }
     __device__ __forceinline__ void finish(int n16) {
@@ -561,7 +571,7 @@ __global__ void __launch_bounds__(1024) tau_order_kernel(int R, int KH, const in
     }
 }
 
-template <bool PROF>
+template <bool PROF, bool EFFS>
 __global__ void __launch_bounds__(448, 1)
     tau_warp_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
                     const __grid_constant__ WarpLayout L, const __grid_constant__ WS s, const int variant,
@@ -571,8 +581,8 @@ __global__ void __launch_bounds__(448, 1)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const DrawGeom g = draw_geom(D);
     const int n16 = D.Pp >> 2;  // int4 stores per log row
-    // stores per lane per dense-loop round so that three dense loops (drift, feasibility, apply) cover a row
-    const int wk = ((n16 + 31) / 32 + 3 * ((KH + 31) / 32) - 1) / (3 * ((KH + 31) / 32));
+    // groups of 4 stores per lane per dense-loop round so that three dense loops (drift, feasibility, apply) cover a row
+    const int wk = (((n16 + 31) / 32 + 3 * ((KH + 31) / 32) - 1) / (3 * ((KH + 31) / 32)) + 3) / 4;  // in groups of 4
     const bool prof = PROF;
     unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark = 0;
@@ -621,6 +631,7 @@ __global__ void __launch_bounds__(448, 1)
         double *eff_g = st.eff + (size_t)r * K * K;
         long long *ctr = st.counters + (size_t)r * NCOUNT;
         const uint64_t seed = st.seeds[r];
+        if (lane == 0) s.tally64[6] = (long long)seed;  // reread once per leap instead of living in two registers
         __syncwarp();
         // ---- load the replicate
         if (!L.par_shared) w_load_params(D, s, pp, lane, 32);
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(448, 1)
             s.maxEBM[i] = st.maxEBM[(size_t)r * K + i];
             s.lock[i] = st.lock[(size_t)r * K + i];
         }
-        if (s.has_effS)
+        if (EFFS)
 #pragma unroll 1
             for (int i = lane; i < K * K; i += 32) s.effS[i] = eff_g[i];
         int ovf = 0;
@@ -656,7 +667,9 @@ __global__ void __launch_bounds__(448, 1)
             if (lane == 0) st.err[r] |= ERR_COUNT_OVERFLOW;
             continue;
         }
-        const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
+        // EFFS (K <= 32): the effective-migration matrix sits in the warp slice -- a compile-time choice so that the
+        // pointer keeps its shared-memory address space (LDS, 32-bit addresses) through the inlined helpers
+        const double *eff = EFFS ? (const double *)s.effS.ptr() : (const double *)eff_g;
         int nhap = 0;
         RowWiper wp;
         wp.idle();
@@ -717,7 +730,10 @@ __global__ void __launch_bounds__(448, 1)
                         LeapTally tr;
                         tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
                         PhiloxCtx ctx;
-                        ctx.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+                        {
+                            const unsigned long long sd = (unsigned long long)s.tally64[6];
+                            ctx.key = make_uint2((uint32_t)sd, (uint32_t)(sd >> 32));
+                        }
                         ctx.c1 = (uint32_t)leaps;
                         ctx.c2 = (retry & 0xffu) | (epoch << 8);
                         ctx.dstride = (uint32_t)g.GS;
@@ -844,16 +860,18 @@ __global__ void __launch_bounds__(448, 1)
                     }
                     if (gsync & 4) TW_GEN_SYNC();
                     if (prof && lane == 0) tmark = clock64();
-                    // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) fused with the list rebuild
-#pragma unroll 1
-                    for (int i = lane; i < KS; i += 32) s.Sx[i] += (double)s.dSx[i];
-                    nAct = w_lists<true>(D, s, nhap, wp, wk, n16);
                     t += tau;
                     sC += tS;
                     if (lane == 0) {
                         long long *ty = s.tally64;
                         ty[EV_BIRTH] += tB; ty[EV_DEATH] += tD; ty[EV_SAMPLING] += tS;
                         ty[EV_MUTATION] += tM; ty[EV_SUSCCHANGE] += tI; ty[EV_MIGRATION] += tG;
+                    }
+                    // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) fused with the list rebuild
+#pragma unroll 1
+                    for (int i = lane; i < KS; i += 32) s.Sx[i] += (double)s.dSx[i];
+                    nAct = w_lists<true>(D, s, nhap, wp, wk, n16);
+                    if (lane == 0) {
                         double *tau_tt = st.tau_tt + ((size_t)r * st.leap_cap + leaps) * 2;
                         tau_tt[0] = t;
                         tau_tt[1] = tau;
