@@ -35,13 +35,14 @@ struct WarpLayout {
     int qtab_cap;      // doubles in the per-leap Q table (0: always recompute)
     int qcap, xcap;
     int has_eff, use_masks;
-    int o_done, gsync;
+    int o_done, gsync, gevery;  // gevery: the warps meet only every gevery-th leap of each warp
     int total_bytes;
 };
 
 inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_bytes, int max_warps) {
     WarpLayout L;
     L.gsync = 0;
+    L.gevery = 1;
     const int K = D.K, H = D.H, S = D.S, U = D.U, KH = K * H, KS = K * S;
     L.par_shared = par_shared ? 1 : 0;
     L.pp0 = pp0;
@@ -347,36 +348,66 @@ __device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, Ro
     __syncwarp();
     int cnt = 0;
     int *I = s.Iraw;
+    if ((H & 31) == 0) {
+        // a round of 32 cells lies inside one deme and lane l always meets the haplotypes l, l+32, ...: the presence
+        // word of the round is the ballot itself and no two lanes ever touch the same table entry -> no atomics
 #pragma unroll 1
-    for (int base = 0; base < KH; base += 32) {
-        const int i = base + lane;
-        int v = 0;
-        if (i < KH) {
-            v = I[i];
+        for (int base = 0; base < KH; base += 32) {
+            const int i = base + lane;
+            int v = I[i];
             if (APPLY) {
                 v += s.updI[i];
                 I[i] = v;
+                wp.some(wk, n16);
             }
-        }
-        if (APPLY) wp.some(wk, n16);
-        const bool on = v != 0;
-        const unsigned m = __ballot_sync(0xffffffffu, on);
-        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (i < KH) {
-            const int p = i >> D.hshift, h = i & (H - 1);
-            if (h == 0) s.dstart[p] = pos;
+            const bool on = v != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            const int p = base >> D.hshift, hb = base & (H - 1);
             if (on) {
-                s.act[pos] = (unsigned short)i;
-                atomicAdd(&s.tot[p], v);
-                if (s.use_masks) {
-                    atomicOr(&s.colmask[h], 1 << p);
-                    atomicOr(&s.rowmask[p], 1ull << h);
-                } else {
-                    atomicAdd(&s.colcnt[h], 1);
+                s.act[cnt + __popc(m & ((1u << lane) - 1u))] = (unsigned short)i;
+                if (s.use_masks) s.colmask[hb + lane] |= 1 << p;
+                else s.colcnt[hb + lane] += 1;
+            }
+            const int sum = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0) {
+                if (hb == 0) s.dstart[p] = cnt;
+                s.tot[p] += sum;
+                if (s.use_masks) reinterpret_cast<unsigned *>(s.rowmask.ptr() + p)[hb >> 5] = m;
+            }
+            cnt += __popc(m);
+        }
+    } else {
+#pragma unroll 1
+        for (int base = 0; base < KH; base += 32) {
+            const int i = base + lane;
+            int v = 0;
+            if (i < KH) {
+                v = I[i];
+                if (APPLY) {
+                    v += s.updI[i];
+                    I[i] = v;
                 }
             }
+            if (APPLY) wp.some(wk, n16);
+            const bool on = v != 0;
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+            if (i < KH) {
+                const int p = i >> D.hshift, h = i & (H - 1);
+                if (h == 0) s.dstart[p] = pos;
+                if (on) {
+                    s.act[pos] = (unsigned short)i;
+                    atomicAdd(&s.tot[p], v);
+                    if (s.use_masks) {
+                        atomicOr(&s.colmask[h], 1 << p);
+                        atomicOr(reinterpret_cast<unsigned *>(s.rowmask.ptr() + p) + (h >> 5), 1u << (h & 31));
+                    } else {
+                        atomicAdd(&s.colcnt[h], 1);
+                    }
+                }
+            }
+            cnt += __popc(m);
         }
-        cnt += __popc(m);
     }
     if (lane == 0) s.dstart[K] = cnt;
     __syncwarp();
@@ -598,6 +629,7 @@ __global__ void __launch_bounds__(448, 1)
     // an SM walk the same phase at the same time and share its instruction fetch.  A warp that ran out of
     // replicates keeps answering the barriers until all are done (see the end of the kernel).
     const int gsync = L.gsync;
+    int gen = 0;  // leaps this warp has walked; it joins the barriers of every gevery-th one
 #define TW_GEN_SYNC() asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory")
     int *done_warps = reinterpret_cast<int *>(smem_raw + L.o_done);
     if (threadIdx.x == 0) *done_warps = 0;
@@ -694,7 +726,9 @@ __global__ void __launch_bounds__(448, 1)
                 while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
                        (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
                     int *row = tau_counts + (size_t)leaps * D.Pp;
-                    if (gsync) {
+                    const bool meet = gsync && (L.gevery <= 1 || gen % L.gevery == 0);
+                    gen++;
+                    if (meet) {
                         TW_GEN_SYNC();
                         if (gsync == 1) TW_GEN_SYNC();  // the end-of-kernel protocol needs two barriers per generation
                     }
@@ -712,7 +746,7 @@ __global__ void __launch_bounds__(448, 1)
                     }
                     double tau = w_drifts_and_tau(D, s, eff, nhap, wp, wk, n16);
                     TW_MARK(1)
-                    if (gsync & 2) TW_GEN_SYNC();
+                    if (meet && (gsync & 2)) TW_GEN_SYNC();
                     if (prof && lane == 0) tmark = clock64();
                     // ---- 3. draw; halve tau and redraw on an infeasible leap (:2316-2321)
                     int tB = 0, tD = 0, tS = 0, tM = 0, tI = 0, tG = 0;
@@ -858,7 +892,7 @@ __global__ void __launch_bounds__(448, 1)
                             break;
                         }
                     }
-                    if (gsync & 4) TW_GEN_SYNC();
+                    if (meet && (gsync & 4)) TW_GEN_SYNC();
                     if (prof && lane == 0) tmark = clock64();
                     t += tau;
                     sC += tS;
