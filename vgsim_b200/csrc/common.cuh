@@ -31,7 +31,7 @@ struct Dims {
     int PD;       // per-deme block: SS1 + H*E
     int NA;       // migration section: K*(K-1)*S*H
     int P;        // total channels
-    int Pp;       // P rounded up to a multiple of 4 (row stride of the dense log, int32 units)
+    int Pp;       // P rounded up to a multiple of 8 (row stride of the dense log, int32 units: rows are 32-byte aligned)
     int hshift;   // log2(H)
     // parameter blob offsets (in doubles)
     int o_b, o_d, o_sr, o_q, o_tmq, o_sigT, o_T, o_Tc, o_m, o_A, o_sm, o_cdB, o_cdA, o_startN, o_endN,
@@ -50,7 +50,7 @@ __host__ __device__ inline Dims make_dims(int U, int K, int S) {
     D.PD = D.SS1 + H * D.E;
     D.NA = K * (K - 1) * S * H;
     D.P = D.NA + K * D.PD;
-    D.Pp = (D.P + 3) & ~3;
+    D.Pp = (D.P + 7) & ~7;
     int o = 0;
     D.o_b = o; o += H;
     D.o_d = o; o += H;

@@ -1255,6 +1255,7 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
         L.gsync = 3;  // lockstep generations on by default: leap start + before the draws (A/B: VGSIM_TAU_SYNC=0..7)
         if (const char *e = getenv("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
         if (const char *e = getenv("VGSIM_TAU_SYNC_EVERY")) L.gevery = atoi(e) < 1 ? 1 : atoi(e);
+        if (const char *e = getenv("VGSIM_TAU_GROUP")) L.ggroup = atoi(e) < 0 ? 0 : atoi(e);
         if (L.nwarps >= 1 && st.D.K * st.D.H < 65536) {  // cell ids are held as uint16
             const WS ws = make_ws(L, st.D);
             auto kern = L.has_eff ? ((variant & 2) ? tau_warp_kernel<true, true> : tau_warp_kernel<false, true>)

@@ -28,7 +28,7 @@ struct WarpLayout {
     int pp0;
     int o_par, o_nbr, o_warp0, warp_bytes;
     // inside the parameter block (bytes)
-    int p_b, p_d, p_sr, p_tmq, p_q, p_sigT, p_sb, p_T, p_sm, p_mdiag, p_sizeD, p_startN, p_endN, p_g, par_bytes;
+    int p_b, p_d, p_sr, p_tmq, p_q, p_sigT, p_sb, p_T, p_sm, p_mdiag, p_sizeD, p_startN, p_endN, p_g, p_qmax, par_bytes;
     // inside a warp slice (bytes)
     int w_par, w_cd, w_c, w_maxEBM, w_eff, w_Sx, w_Bp, w_Rp, w_I, w_chk, w_upd, w_act, w_dSx, w_lock, w_tot, w_dstart,
         w_colcnt, w_colmask, w_rowmask, w_hlist, w_qhi, w_qoc, w_xq, w_cnt, w_tally, w_hidx, w_qtab;
@@ -36,6 +36,7 @@ struct WarpLayout {
     int qcap, xcap;
     int has_eff, use_masks;
     int o_done, gsync, gevery;  // gevery: the warps meet only every gevery-th leap of each warp
+    int ggroup;                  // warps per lockstep group (0: the whole CTA); every group has its own named barrier
     int total_bytes;
 };
 
@@ -43,6 +44,7 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     WarpLayout L;
     L.gsync = 0;
     L.gevery = 1;
+    L.ggroup = 0;
     const int K = D.K, H = D.H, S = D.S, U = D.U, KH = K * H, KS = K * S;
     L.par_shared = par_shared ? 1 : 0;
     L.pp0 = pp0;
@@ -60,7 +62,7 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     take(L.p_b, H * 8, 8); take(L.p_d, H * 8, 8); take(L.p_sr, H * 8, 8); take(L.p_tmq, H * 8, 8);
     take(L.p_q, L.use_masks ? H * U * 3 * 8 : 0, 8);  /* qin: inflow rates by (target haplotype, neighbour slot) */ take(L.p_sigT, S * H * 8, 8); take(L.p_sb, S * H * 8, 8); take(L.p_T, S * S * 8, 8);
     take(L.p_sm, K * 8, 8); take(L.p_mdiag, K * 8, 8); take(L.p_sizeD, K * 8, 8); take(L.p_startN, K * 8, 8);
-    take(L.p_endN, K * 8, 8); take(L.p_g, H * 4, 8);
+    take(L.p_endN, K * 8, 8); take(L.p_g, H * 4, 8); take(L.p_qmax, 8, 8);
     L.par_bytes = (o + 15) & ~15;
     // warp slice
     o = 0;
@@ -90,7 +92,7 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     // CTA
     o = 0;
     L.o_done = o;
-    o += 16;
+    o += 64;  // one counter per lockstep group (<= 15 groups)
     L.o_par = o;
     if (par_shared) o += L.par_bytes;
     L.o_nbr = o;
@@ -155,6 +157,7 @@ struct WGq {  // mutation channel rates q[h][u][k]: read from the parameter blob
 struct WS {
     static constexpr bool has_qin = true;
     WArr<double> b, d, sr, qin, tmq, sigT, sb, T, sm, mdiag, sizeD, startN, endN;
+    WArr<double> qmax;  // [0]: largest mutation channel rate of the parameter point (bounds the inflow into empty cells)
     WGq q;
     WArr<int> g;
     WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp;
@@ -179,7 +182,7 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     auto Wi = [&](int o) { WArr<int> a; a.off = wb + o; a.scale = ws; return a; };
     s.b = P(L.p_b); s.d = P(L.p_d); s.sr = P(L.p_sr); s.tmq = P(L.p_tmq); s.qin = P(L.p_q); s.sigT = P(L.p_sigT);
     s.sb = P(L.p_sb); s.T = P(L.p_T); s.sm = P(L.p_sm); s.mdiag = P(L.p_mdiag); s.sizeD = P(L.p_sizeD);
-    s.startN = P(L.p_startN); s.endN = P(L.p_endN);
+    s.startN = P(L.p_startN); s.endN = P(L.p_endN); s.qmax = P(L.p_qmax);
     s.g.off = pb + L.p_g; s.g.scale = ps;
     s.cd = Wd(L.w_cd); s.c = Wd(L.w_c); s.maxEBM = Wd(L.w_maxEBM); s.effS = Wd(L.w_eff);
     s.Sx = Wd(L.w_Sx); s.Bp = Wd(L.w_Bp); s.Rp = Wd(L.w_Rp);
@@ -202,47 +205,50 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     return s;
 }
 
-// Zero-fill of a dense log row: 16-byte stores, one 512-byte line group per warp instruction (206 instructions
-// for a T3 row).  The TMA bulk-copy wipe of the team kernel stalled its issuing lane for 14 % of all warp
-// samples here (ncu, profiles/r1_f_*): with one warp per replicate nobody else hides that, plain stores do.
-// The later scatter into the row is ordered behind these stores by the __syncwarp()s in between.
-__device__ __forceinline__ void w_wipe_row(int *row, int n16) {
-    int4 *z = reinterpret_cast<int4 *>(row);
+// Zero-fill of a dense log row with 256-bit stores (STG.E.256 of RZ: no data registers; rows are 32-byte aligned
+// because Dims::Pp is a multiple of 8): one 1 KB line group per warp instruction, 103 instructions for a T3 row.
+// The TMA bulk-copy wipe of the team kernel stalled its issuing lane for 14 % of all warp samples here (ncu,
+// profiles/r1_f_*): with one warp per replicate nobody else hides that, plain stores do.  The later scatter into
+// the row is ordered behind these stores by the __syncwarp()s in between.
+struct alignas(32) Row32 {
+    int v[8];
+};
+__device__ __forceinline__ void st_zero32(Row32 *p) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"l"(p), "r"(0) : "memory");
+}
+__device__ __forceinline__ void w_wipe_row(int *row, int n32) {
+    Row32 *z = reinterpret_cast<Row32 *>(row);
 #pragma unroll 4
-    for (int i = threadIdx.x & 31; i < n16; i += 32) z[i] = make_int4(0, 0, 0, 0);
+    for (int i = threadIdx.x & 31; i < n32; i += 32) st_zero32(z + i);
 }
 
 // The wipe of the NEXT leap's row is spread over the dense loops of the current leap (a few stores per round):
 // issued in one burst at the top of a leap, the 14 lockstepped warps of every SM push 1.5 MB into the store path at
 // the same moment and sit on it (18 % of all warp samples, ncu profiles/r1_g_*).
 struct RowWiper {
-    int4 *z;   // row being wiped
-    int idx;   // this lane's next int4 index; >= n16 when there is nothing (left) to do
+    Row32 *z;  // row being wiped
+    int idx;   // this lane's next 32-byte index; >= n32 when there is nothing (left) to do
     __device__ __forceinline__ void begin(int *row) {
-        z = reinterpret_cast<int4 *>(row);
+        z = reinterpret_cast<Row32 *>(row);
         idx = threadIdx.x & 31;
     }
     __device__ __forceinline__ void idle() { idx = 0x3fffffff; }
-    // k4 groups of four stores per lane (2 KB per warp and group)
-    __device__ __forceinline__ void some(int k4, int n16) {
+    // k2 groups of two stores per lane (2 KB per warp and group)
+    __device__ __forceinline__ void some(int k2, int n32) {
 #pragma unroll 1
-        for (int j = 0; j < k4; j++) {
-            if (idx + 96 < n16) {
-                int4 *q = z + idx;
-                q[0] = make_int4(0, 0, 0, 0);
-                q[32] = make_int4(0, 0, 0, 0);
-                q[64] = make_int4(0, 0, 0, 0);
-                q[96] = make_int4(0, 0, 0, 0);
-            } else {
-#pragma unroll 1
-                for (int i = idx; i < n16 && i < idx + 128; i += 32) z[i] = make_int4(0, 0, 0, 0);
+        for (int j = 0; j < k2; j++) {
+            if (idx + 32 < n32) {
+                st_zero32(z + idx);
+                st_zero32(z + idx + 32);
+            } else if (idx < n32) {
+                st_zero32(z + idx);
             }
-            idx += 128;
+            idx += 64;
         }
     }
-    __device__ __forceinline__ void finish(int n16) {
+    __device__ __forceinline__ void finish(int n32) {
 #pragma unroll 4
-        for (; idx < n16; idx += 32) z[idx] = make_int4(0, 0, 0, 0);
+        for (; idx < n32; idx += 32) st_zero32(z + idx);
     }
 };
 
@@ -322,6 +328,12 @@ __device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const 
     }
 #pragma unroll 1
     for (int i = t; i < S * S; i += n) s.T[i] = pp[D.o_T + i];
+    {  // qmax (the caller zeroed it before its last barrier): non-negative doubles order like their bit patterns
+        double m = 0.0;
+#pragma unroll 1
+        for (int i = t; i < H * U * 3; i += n) m = fmax(m, pp[D.o_q + i]);
+        if (m > 0.0) atomicMax(reinterpret_cast<unsigned long long *>(s.qmax.ptr()), (unsigned long long)__double_as_longlong(m));
+    }
 #pragma unroll 1
     for (int i = t; i < K; i += n) {
         s.sm[i] = pp[D.o_sm + i];
@@ -336,7 +348,7 @@ __device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const 
 // presence masks / counts, per-deme totals, the ascending list of haplotypes present anywhere.  Returns the
 // number of infectious cells; nhap gets the number of present haplotypes.  One warp, ends with __syncwarp().
 template <bool APPLY>
-__device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, RowWiper &wp, int wk, int n16) {
+__device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, RowWiper &wp, int wk, int n32) {
     const int lane = threadIdx.x & 31, K = D.K, H = D.H, KH = K * H;
 #pragma unroll 1
     for (int i = lane; i < H; i += 32) s.colcnt[i] = 0;  // (= colmask on the mask path)
@@ -358,7 +370,7 @@ __device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, Ro
             if (APPLY) {
                 v += s.updI[i];
                 I[i] = v;
-                wp.some(wk, n16);
+                wp.some(wk, n32);
             }
             const bool on = v != 0;
             const unsigned m = __ballot_sync(0xffffffffu, on);
@@ -388,7 +400,7 @@ __device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, Ro
                     I[i] = v;
                 }
             }
-            if (APPLY) wp.some(wk, n16);
+            if (APPLY) wp.some(wk, n32);
             const bool on = v != 0;
             const unsigned m = __ballot_sync(0xffffffffu, on);
             const int pos = cnt + __popc(m & ((1u << lane) - 1u));
@@ -451,7 +463,7 @@ __device__ __forceinline__ double warp_min_d(double v) {
 
 // Drifts and tau (ChooseTau :2432-2450) of the warp's state; same sums as the team kernel's drifts_and_tau.
 __device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, const double *eff, int nhap, RowWiper &wp,
-                                                   int wk, int n16) {
+                                                   int wk, int n32, bool &dense_pass) {
     const int K = D.K, H = D.H, S = D.S, KS = K * S;
     const int lane = threadIdx.x & 31;
     // ---- A. pressure / return-flow sums per (deme, group): 8 lanes per sum, fixed butterfly
@@ -501,12 +513,21 @@ __device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, c
         const int cell = p * H + h;
         candidate(drift_I_cell(cell, D, s, eff), s.I[cell]);
     }
-    // ---- B1b. every other cell: mutation inflow only (its count is 0)
+    // ---- B1b. every other cell: mutation inflow only (its count is 0).  Such a cell proposes tau = 1 / inflow, which
+    //           can only undercut tmin <= 1 when inflow > 1; inflow <= qmax * (infectious total of the deme), so when that
+    //           bound is below 1 in every deme the whole pass cannot change tau and is skipped (the usual case: per-site
+    //           mutation rates are orders of magnitude below 1 / deme prevalence).
+    int need = 0;
 #pragma unroll 1
-    for (int i = lane; i < K * H; i += 32) {
-        wp.some(wk, n16);
-        if (s.colcnt[i & (H - 1)] != 0) continue;
-        candidate(drift_I_cell(i, D, s, eff), 0.0);
+    for (int p = lane; p < K; p += 32) need |= s.qmax[0] * (double)s.tot[p] >= 0.999;
+    dense_pass = __any_sync(0xffffffffu, need) != 0;
+    if (dense_pass) {
+#pragma unroll 1
+        for (int i = lane; i < K * H; i += 32) {
+            wp.some(wk, n32);
+            if (s.colcnt[i & (H - 1)] != 0) continue;
+            candidate(drift_I_cell(i, D, s, eff), 0.0);
+        }
     }
     // ---- B2. susceptible drifts
 #pragma unroll 1
@@ -603,7 +624,11 @@ __global__ void __launch_bounds__(1024) tau_order_kernel(int R, int KH, const in
 }
 
 template <bool PROF, bool EFFS>
+#ifdef VGSIM_TW_MAXNREG
+__global__ void __maxnreg__(VGSIM_TW_MAXNREG)
+#else
 __global__ void __launch_bounds__(448, 1)
+#endif
     tau_warp_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
                     const __grid_constant__ WarpLayout L, const __grid_constant__ WS s, const int variant,
                     const int *__restrict__ order) {
@@ -611,9 +636,10 @@ __global__ void __launch_bounds__(448, 1)
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const DrawGeom g = draw_geom(D);
-    const int n16 = D.Pp >> 2;  // int4 stores per log row
-    // groups of 4 stores per lane per dense-loop round so that three dense loops (drift, feasibility, apply) cover a row
-    const int wk = (((n16 + 31) / 32 + 3 * ((KH + 31) / 32) - 1) / (3 * ((KH + 31) / 32)) + 3) / 4;  // in groups of 4
+    const int n32 = D.Pp >> 3;  // 256-bit stores per log row
+    // groups of 2 stores per lane per dense-loop round so that three dense loops (drift, feasibility, apply) cover a row
+    const int wk = (((n32 + 31) / 32 + 3 * ((KH + 31) / 32) - 1) / (3 * ((KH + 31) / 32)) + 1) / 2;  // in groups of 2
+    const int wk2 = (((n32 + 31) / 32 + 2 * ((KH + 31) / 32) - 1) / (2 * ((KH + 31) / 32)) + 1) / 2;  // ... over two dense loops
     const bool prof = PROF;
     unsigned long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tmark = 0;
@@ -630,9 +656,12 @@ __global__ void __launch_bounds__(448, 1)
     // replicates keeps answering the barriers until all are done (see the end of the kernel).
     const int gsync = L.gsync;
     int gen = 0;  // leaps this warp has walked; it joins the barriers of every gevery-th one
-#define TW_GEN_SYNC() asm volatile("bar.sync 1, %0;" ::"r"((int)blockDim.x) : "memory")
-    int *done_warps = reinterpret_cast<int *>(smem_raw + L.o_done);
-    if (threadIdx.x == 0) *done_warps = 0;
+    const int gsz = (L.ggroup > 0 && L.ggroup < nw && (nw + L.ggroup - 1) / L.ggroup <= 15) ? L.ggroup : nw;
+    const int grp = wid / gsz;
+    const int gmembers = (nw - grp * gsz < gsz) ? nw - grp * gsz : gsz;  // warps in this warp's group
+#define TW_GEN_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gmembers * 32) : "memory")
+    int *done_warps = reinterpret_cast<int *>(smem_raw + L.o_done) + grp;
+    if (threadIdx.x < 16) reinterpret_cast<int *>(smem_raw + L.o_done)[threadIdx.x] = 0;
     // ---- CTA prologue: neighbour masks, the shared parameter point
     if (s.use_masks)
 #pragma unroll 1
@@ -642,6 +671,7 @@ __global__ void __launch_bounds__(448, 1)
                 for (int al = 1; al < 4; al++) m |= 1ull << (i ^ (al << (2 * u)));
             s.nbrmask[i] = m;
         }
+    if (L.par_shared && threadIdx.x == 0) s.qmax[0] = 0.0;
     __syncthreads();  // nbrmask is read by the parameter staging
     if (L.par_shared) w_load_params(D, s, st.params + (size_t)L.pp0 * D.blob, threadIdx.x, blockDim.x);
     __syncthreads();
@@ -664,6 +694,7 @@ __global__ void __launch_bounds__(448, 1)
         long long *ctr = st.counters + (size_t)r * NCOUNT;
         const uint64_t seed = st.seeds[r];
         if (lane == 0) s.tally64[6] = (long long)seed;  // reread once per leap instead of living in two registers
+        if (!L.par_shared && lane == 0) s.qmax[0] = 0.0;
         __syncwarp();
         // ---- load the replicate
         if (!L.par_shared) w_load_params(D, s, pp, lane, 32);
@@ -706,7 +737,7 @@ __global__ void __launch_bounds__(448, 1)
         RowWiper wp;
         wp.idle();
         int pre_row = -1;  // leap whose row the wiper is working on / has finished
-        int nAct = w_lists<false>(D, s, nhap, wp, 0, n16);
+        int nAct = w_lists<false>(D, s, nhap, wp, 0, n32);
 
         bool restarted = false;
         if (lane < 6) s.tally64[lane] = 0;
@@ -736,7 +767,7 @@ __global__ void __launch_bounds__(448, 1)
                     // ---- 0. this leap's row: finish the wipe started during the previous leap (or do all of it: first
                     //         leap of the call, Restart), then start on the next row; 1-2. drifts and tau
                     if (pre_row != (int)leaps) wp.begin(row);
-                    wp.finish(n16);
+                    wp.finish(n32);
                     if (leaps + 1 < st.leap_cap && evptr + 1 < ev_limit && evptr + 1 < st.ev_cap) {
                         wp.begin(row + D.Pp);
                         pre_row = (int)leaps + 1;
@@ -744,7 +775,9 @@ __global__ void __launch_bounds__(448, 1)
                         wp.idle();
                         pre_row = -1;
                     }
-                    double tau = w_drifts_and_tau(D, s, eff, nhap, wp, wk, n16);
+                    bool dense_pass;
+                    double tau = w_drifts_and_tau(D, s, eff, nhap, wp, wk, n32, dense_pass);
+                    const int wkl = dense_pass ? wk : wk2;  // the empty-cell drift pass was skipped: its share of the wipe moves on
                     TW_MARK(1)
                     if (meet && (gsync & 2)) TW_GEN_SYNC();
                     if (prof && lane == 0) tmark = clock64();
@@ -856,7 +889,7 @@ __global__ void __launch_bounds__(448, 1)
                         int bad = 0;
 #pragma unroll 1
                         for (int i = lane; i < KH; i += 32) {
-                            wp.some(wk, n16);
+                            wp.some(wkl, n32);
                             const double sz = s.sizeD[i >> D.hshift];
                             const double Iv = s.I[i];
                             const double v = Iv + (double)s.chkI[i];
@@ -875,7 +908,7 @@ __global__ void __launch_bounds__(448, 1)
                         TW_MARK(3)
                         if (!bad) break;
                         tau *= 0.5;
-                        w_wipe_row(row, D.Pp >> 2);  // rare path
+                        w_wipe_row(row, D.Pp >> 3);  // rare path
                         if (retry >= 80) {  // tau * 2^-80: nothing can fire any more, yet the state fails the test
                             if (lane == 0) st.err[r] |= ERR_TAU_STUCK;
                             tau = 0.0;
@@ -904,7 +937,7 @@ __global__ void __launch_bounds__(448, 1)
                     // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) fused with the list rebuild
 #pragma unroll 1
                     for (int i = lane; i < KS; i += 32) s.Sx[i] += (double)s.dSx[i];
-                    nAct = w_lists<true>(D, s, nhap, wp, wk, n16);
+                    nAct = w_lists<true>(D, s, nhap, wp, wkl, n32);
                     if (lane == 0) {
                         double *tau_tt = st.tau_tt + ((size_t)r * st.leap_cap + leaps) * 2;
                         tau_tt[0] = t;
@@ -935,7 +968,7 @@ __global__ void __launch_bounds__(448, 1)
 #pragma unroll 1
                 for (int i = lane; i < KS; i += 32) s.Sx[i] = (double)st.initSx[(size_t)r * KS + i];
                 __syncwarp();
-                nAct = w_lists<false>(D, s, nhap, wp, 0, n16);
+                nAct = w_lists<false>(D, s, nhap, wp, 0, n32);
                 flips_total += w_lockdown(st, r, D, s, pp, eff_g, t);
                 good_attempt = 0;
                 if (lane == 0) ctr[C_MIGN] = 0;
@@ -988,7 +1021,7 @@ __global__ void __launch_bounds__(448, 1)
         if (lane == 0) atomicAdd(done_warps, 1);
         for (;;) {
             TW_GEN_SYNC();
-            const bool all = *(volatile int *)done_warps >= nw;
+            const bool all = *(volatile int *)done_warps >= gmembers;
             if (gsync == 1) TW_GEN_SYNC();
             if (gsync & 2) TW_GEN_SYNC();
             if (gsync & 4) TW_GEN_SYNC();
