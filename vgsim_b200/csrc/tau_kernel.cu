@@ -1268,8 +1268,10 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
             int sorted = L.gsync != 0 && order_buf != nullptr && st.R > grid * L.nwarps;
             if (const char *e2 = getenv("VGSIM_TAU_SORT")) sorted = sorted && atoi(e2) != 0;
             if (sorted) {
-                tau_weight_kernel<<<(st.R * 32 + 255) / 256, 256, 0, stream>>>(st, order_buf);
-                tau_order_kernel<<<1, 1024, 0, stream>>>(st.R, st.D.K * st.D.H, order_buf, order_buf + st.R);
+                int wmode = 0;  // A/B: VGSIM_TAU_WEIGHT=1 sorts by loop items (cells and present haplotypes) instead of cells
+                if (const char *e3 = getenv("VGSIM_TAU_WEIGHT")) wmode = atoi(e3);
+                tau_weight_kernel<<<(st.R * 32 + 255) / 256, 256, 0, stream>>>(st, order_buf, wmode);
+                tau_order_kernel<<<1, 1024, 0, stream>>>(st.R, (wmode == 1 ? 3 : 1) * st.D.K * st.D.H, order_buf, order_buf + st.R);
             }
             kern<<<grid, L.nwarps * 32, L.total_bytes, stream>>>(st, a, L, ws, variant, sorted ? order_buf + st.R : nullptr);
             return cudaGetLastError();

@@ -593,14 +593,22 @@ __device__ __forceinline__ void w_drain(double tau, int *row, const Dims &D, con
 // leap's cost grows with the number of infectious cells of the replicate.  So replicates of similar size share
 // a CTA: weight = #infectious cells, sorted descending, consecutive groups of `nwarps` go to one CTA visit, and
 // the CTAs walk the groups boustrophedon (b, 2G-1-b, 2G+b, ...) so that every CTA gets the same mix of heavy and
-// light groups.  Scheduling only: every replicate's result is a function of its own state and seed.
-__global__ void tau_weight_kernel(const DevState st, int *weight) {
-    const int lane = threadIdx.x & 31, KH = st.D.K * st.D.H;
+// light groups.  (KH below is the largest possible weight.)  Scheduling only: every replicate's result is a function of its own state and seed.
+__global__ void tau_weight_kernel(const DevState st, int *weight, int mode) {
+    const int lane = threadIdx.x & 31, K = st.D.K, H = st.D.H, KH = K * H;
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= st.R) return;
     int n = 0;
-    for (int i = lane; i < KH; i += 32) n += st.I[(size_t)r * KH + i] != 0;
+    unsigned long long present = 0ull;  // haplotypes present anywhere (H <= 64)
+    for (int i = lane; i < KH; i += 32) {
+        const bool on = st.I[(size_t)r * KH + i] != 0;
+        n += on;
+        if (on) present |= 1ull << (i & (H - 1) & 63);
+    }
     n = __reduce_add_sync(0xffffffffu, n);
+    unsigned lo = __reduce_or_sync(0xffffffffu, (unsigned)present), hi = __reduce_or_sync(0xffffffffu, (unsigned)(present >> 32));
+    // mode 1: items of the two long loops of a leap -- 2 draw blocks per cell + K drift sums per present haplotype
+    if (mode == 1 && H <= 64) n = 2 * n + K * (__popc(lo) + __popc(hi));
     if (lane == 0) weight[r] = n;
 }
 // one CTA: counting sort by weight (descending) into order[]
