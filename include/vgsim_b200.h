@@ -165,6 +165,21 @@ int vgsim_get_migrations(vgsim_handle h, int replicate, int64_t *node, double *t
 int vgsim_summaries(vgsim_handle h, double *out);
 int vgsim_summaries_dev(vgsim_handle h, void **dev_ptr);
 
+/* Epidemic curves of EVERY compartment of replicates [rep_first, rep_first + rep_count) in one pass over their
+ * event logs (direct rows and MULTITYPE leaps); replaces get_data_infectious / get_data_susceptible
+ * (src/_BirthDeath.pyx:1967-2045), which walk the whole log once per (deme, haplotype) query.
+ * Grid: time_points[q][j] = j * currentTime / step_num, j = 0..step_num (:1968); the value at j is the state
+ * after every log row with time <= time_points[j] (:1975-1978).  Host outputs, any may be NULL:
+ *   infectious[rep_count][step_num+1][K*H], susceptible[..][K*S] : compartment counts;
+ *   removed[..][K*H], sampled[..][K*H] : cumulative recoveries+samplings / samplings per infectious cell (the
+ *   reference's Data / Sample arrays mix these in through an operator-precedence quirk; the Python wrapper rebuilds
+ *   its exact output from them);
+ *   last_point[rep_count] : index of the grid point that holds the last log row (the reference leaves later points
+ *   zero, here they repeat the final state). */
+int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step_num, int64_t *infectious,
+                          int64_t *susceptible, int64_t *removed, int64_t *sampled, double *time_points,
+                          int32_t *last_point);
+
 /* Parity tap.  Variant 0 (default, product): per infectious cell the kernel draws ONE Poisson for the total of
  * its mutation channels and ONE for the total of its out-migration channels whenever that total's lambda is
  * <= 1, and splits a non-zero total multinomially over the group's channels (independent Poissons

@@ -286,3 +286,89 @@ def make_reference(sites=0, K=1, S=1, seed=0):
     return BD(number_of_sites=sites, populations_number=K, number_of_susceptible_groups=S, seed=seed,
               sampling_probability=False, memory_optimization=False, genome_length=int(1e6),
               recombination_probability=0.0)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Epidemic curves: literal restatement of get_data_infectious / get_data_susceptible
+# (reference src/_BirthDeath.pyx:1967-2005 and :2008-2045), including the operator-precedence quirk of the DEATH /
+# SAMPLING branch (`a or b or c and d and e` -> every DEATH / SAMPLING of ANY cell decrements Data and, for
+# SAMPLING, increments Sample) and the multi-event MIGRATION branch of the susceptible curve comparing
+# `haplotypes` (not `newHaplotypes`) with the group index.  chain = 6 x N export_chain_events layout (used rows
+# only); multi = dict of the multiEvents SoA (num, type, hap, pop, nhap, npop) or None.  TEST INFRASTRUCTURE.
+BIRTH, DEATH, SAMPLING, MUTATION, SUSCCHANGE, MIGRATION, MULTITYPE = range(7)
+
+
+def ref_data_infectious(chain, multi, initial, current_time, pop, hap, step_num):
+    tp = [i * current_time / step_num for i in range(step_num + 1)]
+    Data = np.zeros(step_num + 1)
+    Sample = np.zeros(step_num + 1)
+    Data[0] = initial
+    t_, ty_, h_, p_, nh_, np_ = (chain[k] for k in range(6))
+    point = 0
+    for i in range(chain.shape[1]):
+        while point != step_num and tp[point] < t_[i]:
+            Data[point + 1] = Data[point]
+            Sample[point + 1] = Sample[point]
+            point += 1
+        ty = int(ty_[i])
+        if ty == BIRTH and p_[i] == pop and h_[i] == hap:
+            Data[point] += 1
+        elif ty == DEATH or ty == SAMPLING or ty == MUTATION and p_[i] == pop and h_[i] == hap:
+            Data[point] -= 1
+            if ty == SAMPLING:
+                Sample[point] += 1
+        elif ty == MUTATION and nh_[i] == hap and p_[i] == pop:
+            Data[point] += 1
+        elif ty == MIGRATION and np_[i] == pop and h_[i] == hap:
+            Data[point] += 1
+        elif ty == MULTITYPE:
+            lo, hi = int(h_[i]), int(p_[i])
+            nz = lo + np.nonzero(multi["num"][lo:hi])[0]  # records with num == 0 add nothing
+            for j in nz:
+                mt, n = int(multi["type"][j]), int(multi["num"][j])
+                if mt == BIRTH and multi["hap"][j] == hap and multi["pop"][j] == pop:
+                    Data[point] += n
+                elif mt == DEATH or mt == SAMPLING or mt == MUTATION and multi["hap"][j] == hap and multi["pop"][j] == pop:
+                    Data[point] -= n
+                    if mt == SAMPLING:
+                        Sample[point] += n
+                elif mt == MUTATION and multi["nhap"][j] == hap and multi["pop"][j] == pop:
+                    Data[point] += n
+                elif mt == MIGRATION and multi["npop"][j] == pop and multi["hap"][j] == hap:
+                    Data[point] += n
+    return Data, Sample, tp
+
+
+def ref_data_susceptible(chain, multi, initial, current_time, pop, sus, step_num):
+    tp = [i * current_time / step_num for i in range(step_num + 1)]
+    Data = np.zeros(step_num + 1)
+    Data[0] = initial
+    t_, ty_, h_, p_, nh_, np_ = (chain[k] for k in range(6))
+    point = 0
+    for i in range(chain.shape[1]):
+        while point != step_num and tp[point] < t_[i]:
+            Data[point + 1] = Data[point]
+            point += 1
+        ty = int(ty_[i])
+        if ty == BIRTH and p_[i] == pop and nh_[i] == sus:
+            Data[point] -= 1
+        elif (ty == DEATH or ty == SAMPLING or ty == SUSCCHANGE) and p_[i] == pop and nh_[i] == sus:
+            Data[point] += 1
+        elif ty == SUSCCHANGE and h_[i] == sus and p_[i] == pop:
+            Data[point] -= 1
+        elif ty == MIGRATION and np_[i] == pop and nh_[i] == sus:
+            Data[point] -= 1
+        elif ty == MULTITYPE:
+            lo, hi = int(h_[i]), int(p_[i])
+            nz = lo + np.nonzero(multi["num"][lo:hi])[0]
+            for j in nz:
+                mt, n = int(multi["type"][j]), int(multi["num"][j])
+                if mt == BIRTH and multi["nhap"][j] == sus and multi["pop"][j] == pop:
+                    Data[point] -= n
+                elif (mt == DEATH or mt == SAMPLING or mt == SUSCCHANGE) and multi["nhap"][j] == sus and multi["pop"][j] == pop:
+                    Data[point] += n
+                elif mt == SUSCCHANGE and multi["hap"][j] == sus and multi["pop"][j] == pop:
+                    Data[point] -= n
+                elif mt == MIGRATION and multi["npop"][j] == pop and multi["hap"][j] == sus:
+                    Data[point] -= n
+    return Data, tp

@@ -16,7 +16,11 @@ are absent from the mount (.MISSING_LARGE_BLOBS) and tests/test_interface.py pin
   prop_<scn>.npz     PrintPropensities (src/_BirthDeath.pyx:2615-2649) of a mid-epidemic state, parsed
                      from its repr(float) prints: the P propensities in positional channel order.
 
+  curves_<kind>_<scn>.npz  get_data_infectious / get_data_susceptible (src/_BirthDeath.pyx:1967-2045) of the
+                     direct_<scn> / tau_<scn> runs for a few compartments, 37 grid steps.
+
 Run:  python tests/golden/make_golden.py        (needs oracle/_ref; ~1 min)
+      python tests/golden/make_golden.py curves (only the curves fixtures)
 """
 import contextlib
 import hashlib
@@ -157,15 +161,57 @@ def gen_prop(name, seed, t_warm):
     print("prop", name, "P", P, "nonzero", int((out["prop"] != 0).sum()))
 
 
+CURVE_STEPS = 37
+# (kind, scenario): the direct run of gen_direct / the mixed run of gen_tau (same seeds and arguments), then
+# get_data_infectious / get_data_susceptible of the reference for a handful of compartments
+CURVES = [("direct", "s4"), ("direct", "s7"), ("direct", "s9"), ("tau", "example"), ("tau", "t3small"), ("tau", "s5")]
+
+
+def gen_curves(kind, name):
+    (U, K, S), _ = SCENARIOS[name]
+    H = 4 ** U
+    if kind == "direct":
+        ref = make_ref(name, SEED)
+        _quiet(ref.SimulatePopulation, 100000, 100000, -1, 200)
+    else:
+        _, seed, t_warm, t_end, iters = [a for a in TAU if a[0] == name][0]
+        ref = make_ref(name, seed)
+        _quiet(ref.SimulatePopulation, WARM_ROWS, 10 ** 9, t_warm, 200)
+        n_direct = used_rows(chain_of(ref))
+        ref = make_ref(name, seed)
+        _quiet(ref.SimulatePopulation, n_direct, 10 ** 9, t_warm, 200)
+        _quiet(ref.SimulatePopulation_tau, iters, 10 ** 9, t_end, 200)
+    I_end = np.asarray(ref.infectious)
+    cells = sorted({(p, h) for p in (0, K - 1) for h in (0, int(np.argmax(I_end.sum(axis=0))), H - 1)})
+    groups = sorted({(p, s) for p in (0, K - 1) for s in (0, S - 1)})
+    out = dict(cells=np.array(cells), groups=np.array(groups), steps=CURVE_STEPS)
+    for k, (p, h) in enumerate(cells):
+        Data, Sample, tp, _ld = ref.get_data_infectious(p, h, CURVE_STEPS)
+        out["inf_%d" % k] = np.asarray(Data, np.float64)
+        out["smp_%d" % k] = np.asarray(Sample, np.float64)
+        out["tp"] = np.asarray(tp, np.float64)
+    for k, (p, s) in enumerate(groups):
+        Data, tp, _ld = ref.get_data_susceptible(p, s, CURVE_STEPS)
+        out["sus_%d" % k] = np.asarray(Data, np.float64)
+    np.savez_compressed(os.path.join(HERE, "curves_%s_%s.npz" % (kind, name)), **out)
+    print("curves", kind, name, "cells", cells, "groups", groups, "final Data", [float(out["inf_%d" % k][-1]) for k in range(len(cells))])
+
+
 def main():
     if not O.reference_available():
         sys.exit("oracle/_ref is not built: run python oracle/build_ref.py (needs /root/reference)")
+    if sys.argv[1:] == ["curves"]:
+        for args in CURVES:
+            gen_curves(*args)
+        return
     for name in DIRECT:
         gen_direct(name)
     for args in TAU:
         gen_tau(*args)
     for args in PROP:
         gen_prop(*args)
+    for args in CURVES:
+        gen_curves(*args)
 
 
 if __name__ == "__main__":

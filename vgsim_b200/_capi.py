@@ -63,6 +63,7 @@ def _load():
         "vgsim_get_mutations": (c_int, [P, c_int, P, P, P, P, P]),
         "vgsim_num_migrations": (c_int64, [P, c_int]),
         "vgsim_get_migrations": (c_int, [P, c_int, P, P, P, P]),
+        "vgsim_epidemic_curves": (c_int, [P, c_int, c_int, c_int, P, P, P, P, P, P]),
         "vgsim_summaries": (c_int, [P, P]),
         "vgsim_summaries_dev": (c_int, [P, ctypes.POINTER(c_void_p)]),
         "vgsim_launch_count": (c_int64, [P]),
@@ -248,6 +249,23 @@ class Handle:
         n = int(self.get_counters()["events"][replicate])
         out = np.zeros((6, n), np.float64)
         _ck(lib.vgsim_get_event_log(self._h, replicate, _p(out), n))
+        return out
+
+    def epidemic_curves(self, step_num, rep_first=0, rep_count=None,
+                        want=("infectious", "susceptible", "removed", "sampled")):
+        """One pass over the logs of replicates [rep_first, rep_first + rep_count): dict of int64 arrays
+        infectious [n, T+1, K, H], susceptible [n, T+1, K, S], removed / sampled [n, T+1, K, H] (those named in
+        `want`), time_points [n, T+1] and last_point [n]."""
+        n = self.R - rep_first if rep_count is None else int(rep_count)
+        T1 = int(step_num) + 1
+        shapes = {"infectious": (n, T1, self.K, self.H), "susceptible": (n, T1, self.K, self.S),
+                  "removed": (n, T1, self.K, self.H), "sampled": (n, T1, self.K, self.H)}
+        out = {k: np.zeros(shapes[k], np.int64) for k in shapes if k in want}
+        out["time_points"] = np.zeros((n, T1), np.float64)
+        out["last_point"] = np.zeros(n, np.int32)
+        _ck(lib.vgsim_epidemic_curves(self._h, int(rep_first), n, int(step_num), _p(out.get("infectious")),
+                                      _p(out.get("susceptible")), _p(out.get("removed")), _p(out.get("sampled")),
+                                      _p(out["time_points"]), _p(out["last_point"])))
         return out
 
     def get_tau_log(self, replicate=0):

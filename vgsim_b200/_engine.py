@@ -725,6 +725,64 @@ class BirthDeathModel:
         sel = ev[1] == SAMPLING
         return list(ev[0][sel]), [int(x) for x in ev[3][sel]], [int(x) for x in ev[2][sel]]
 
+    # ---- epidemic curves (reference :1967-2045), computed for every compartment in one device pass over the log
+    def epidemic_curves(self, step_num, rep_first=0, rep_count=None,
+                        want=("infectious", "susceptible", "removed", "sampled")):
+        """True compartment counts on the reference's time grid for a range of replicates (see
+        include/vgsim_b200.h: vgsim_epidemic_curves)."""
+        return self._handle.epidemic_curves(step_num, rep_first, rep_count, want)
+
+    def _lockdown_rows(self, pop, replicate):
+        state, lp, lt = self._handle.get_lockdowns(replicate)
+        return [[int(state[i]), float(lt[i])] for i in range(len(state)) if int(lp[i]) == pop]
+
+    def _tau_migration_in(self, pop, replicate):
+        """Per leap: counts[leap][S][H] of MIGRATION multi-events into deme `pop`, and the leap times."""
+        K, H, S = self.popNum, self.hapNum, self.susNum
+        counts, tt = self._handle.get_tau_log(replicate)
+        if counts.shape[0] == 0 or K < 2:
+            return np.zeros((0, S, H), np.int64), np.zeros(0)
+        mig = counts[:, :K * (K - 1) * S * H].reshape(-1, K, K - 1, S, H).astype(np.int64)  # [leap][source][target'][s][h]
+        tot = np.zeros((counts.shape[0], S, H), np.int64)
+        for sp in range(K):
+            if sp != pop:
+                tot += mig[:, sp, pop - (1 if pop > sp else 0)]
+        return tot, tt[:, 0]
+
+    def get_data_infectious(self, pop, hap, step_num, replicate=0):
+        """(Data, Sample, time_points, Lockdowns) exactly as the reference returns them (:1967-2005).  Its DEATH /
+        SAMPLING branch reads `DEATH or SAMPLING or MUTATION and <this cell>`, so EVERY recovery and sampling of the
+        replicate is subtracted from Data and every sampling is counted in Sample, and grid points after the one
+        holding the last log row stay zero; both are rebuilt here from the true counts of `epidemic_curves`."""
+        c = self._handle.epidemic_curves(step_num, replicate, 1, ("infectious", "removed", "sampled"))
+        last = int(c["last_point"][0])
+        removed_all = c["removed"][0].sum(axis=(1, 2))
+        Data = (c["infectious"][0, :, pop, hap] + c["removed"][0, :, pop, hap] - removed_all).astype(np.float64)
+        Sample = c["sampled"][0].sum(axis=(1, 2)).astype(np.float64)
+        Data[last + 1:] = 0.0
+        Sample[last + 1:] = 0.0
+        return Data, Sample, [float(x) for x in c["time_points"][0]], self._lockdown_rows(pop, replicate)
+
+    def get_data_susceptible(self, pop, sus, step_num, replicate=0):
+        """(Data, time_points, Lockdowns) exactly as the reference returns them (:2008-2045).  Direct-method rows give
+        the true count; for MULTITYPE rows the reference matches MIGRATION records on `haplotypes == sus` instead of
+        `newHaplotypes == sus` (:2037): that difference is rebuilt from the migration block of the dense tau log."""
+        c = self._handle.epidemic_curves(step_num, replicate, 1, ("susceptible",))
+        last = int(c["last_point"][0])
+        tp = c["time_points"][0]
+        Data = c["susceptible"][0, :, pop, sus].astype(np.float64)
+        mig, lt = self._tau_migration_in(pop, replicate)
+        if mig.shape[0]:
+            by_group = mig[:, sus, :].sum(axis=1)
+            by_hap = mig[:, :, sus].sum(axis=1) if sus < self.hapNum else np.zeros(len(lt), np.int64)
+            # a leap lands on the first grid point that is not before it (:2016-2018), capped at the last point
+            pt = np.minimum(np.searchsorted(tp, lt, side="left"), step_num)
+            corr = np.zeros(step_num + 1)
+            np.add.at(corr, pt, (by_group - by_hap).astype(np.float64))
+            Data += np.cumsum(corr)
+        Data[last + 1:] = 0.0
+        return Data, [float(x) for x in tp], self._lockdown_rows(pop, replicate)
+
     def get_lockdowns(self, replicate=0):
         return self._handle.get_lockdowns(replicate)
 

@@ -269,6 +269,18 @@ class Simulator:
     def get_chain_events(self, replicate=0):
         return self.simulation.get_chain_events(replicate)
 
+    def get_data_susceptible(self, population, susceptibility_type, step_num, replicate=0):
+        """susceptible, time_points, lockdowns (reference src/_interface.py:599-615)."""
+        return self.simulation.get_data_susceptible(population, susceptibility_type, step_num, replicate)
+
+    def get_data_infectious(self, population, haplotype, step_num, replicate=0):
+        """infections, sample, time_points, lockdowns (reference src/_interface.py:617-633)."""
+        return self.simulation.get_data_infectious(population, haplotype, step_num, replicate)
+
+    def epidemic_curves(self, step_num, rep_first=0, rep_count=None):
+        """Every compartment of a range of replicates on the reference's time grid, one device pass over the logs."""
+        return self.simulation.epidemic_curves(step_num, rep_first, rep_count)
+
     def get_tree(self, replicate=0):
         return self.simulation.get_tree(replicate)
 

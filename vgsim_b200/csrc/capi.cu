@@ -690,6 +690,47 @@ int vgsim_get_lockdowns(vgsim_handle h, int r, int64_t *state, int64_t *pop, dou
     return 0;
 }
 
+int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step_num, int64_t *infectious,
+                          int64_t *susceptible, int64_t *removed, int64_t *sampled, double *time_points,
+                          int32_t *last_point) {
+    CK(cudaSetDevice(h->device));
+    if (rep_first < 0 || rep_count < 1 || rep_first + rep_count > h->R) return fail("epidemic curves: replicate range out of bounds");
+    if (step_num < 1) return fail("epidemic curves: step_num must be >= 1");
+    const Dims &D = h->D;
+    const size_t np = (size_t)rep_count * (step_num + 1), KH = (size_t)D.K * D.H, KS = (size_t)D.K * D.S;
+    long long *d_inf = nullptr, *d_sus = nullptr, *d_rem = nullptr, *d_smp = nullptr;
+    double *d_tp = nullptr;
+    int *d_lp = nullptr;
+    int rc = 0;
+    if (infectious && !rc) rc = dalloc(h, &d_inf, np * KH);
+    if (susceptible && !rc) rc = dalloc(h, &d_sus, np * KS);
+    if (removed && !rc) rc = dalloc(h, &d_rem, np * KH);
+    if (sampled && !rc) rc = dalloc(h, &d_smp, np * KH);
+    if (time_points && !rc) rc = dalloc(h, &d_tp, np);
+    if (last_point && !rc) rc = dalloc(h, &d_lp, (size_t)rep_count);
+    cudaError_t e = cudaSuccess;
+    if (!rc) {
+        e = launch_curves(h->st, rep_first, rep_count, step_num, d_inf, d_sus, d_rem, d_smp, d_tp, d_lp, h->stream, h->num_sms);
+        h->launches++;
+    }
+    auto back = [&](void *dst, const void *src, size_t bytes) {
+        if (dst && e == cudaSuccess) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream);
+    };
+    if (!rc) {
+        back(infectious, d_inf, np * KH * 8);
+        back(susceptible, d_sus, np * KS * 8);
+        back(removed, d_rem, np * KH * 8);
+        back(sampled, d_smp, np * KH * 8);
+        back(time_points, d_tp, np * 8);
+        back(last_point, d_lp, (size_t)rep_count * 4);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    }
+    dfree(h, d_inf); dfree(h, d_sus); dfree(h, d_rem); dfree(h, d_smp); dfree(h, d_tp); dfree(h, d_lp);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(std::string("epidemic curves: ") + cudaGetErrorString(e));
+    return 0;
+}
+
 int64_t vgsim_launch_count(vgsim_handle h) { return h->launches; }
 
 int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset) {

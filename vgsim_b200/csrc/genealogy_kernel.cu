@@ -24,6 +24,7 @@
 #include <vector>
 #include "../../include/vgsim_b200.h"
 #include "common.cuh"
+#include "logrec.cuh"
 #include "handle.h"
 #include "genrng.cuh"
 
@@ -165,51 +166,6 @@ struct Out {
         mig_n++;
     }
 };
-
-// decode a tau-log channel index into a multi-event record (type, hap, pop, nhap, npop)
-__device__ __forceinline__ void decode_record(int c, const Dims &D, const double *__restrict__ pp, int &type, int &hap,
-                                              int &pop, int &nhap, int &npop) {
-    const int K = D.K, H = D.H, S = D.S;
-    if (c < D.NA) {
-        int row = c >> D.hshift;
-        hap = c & (H - 1);
-        int pair = row / S;
-        nhap = row - pair * S;
-        pop = pair / (K - 1);
-        int tpp = pair - pop * (K - 1);
-        npop = tpp + (tpp >= pop ? 1 : 0);
-        type = EV_MIGRATION;
-        return;
-    }
-    int c2 = c - D.NA;
-    pop = c2 / D.PD;
-    int r = c2 - pop * D.PD;
-    npop = 0;
-    if (r < D.SS1) {
-        hap = r / (S - 1);
-        int tsp = r - hap * (S - 1);
-        nhap = tsp + (tsp >= hap ? 1 : 0);
-        type = EV_SUSCCHANGE;
-        return;
-    }
-    int r2 = r - D.SS1;
-    hap = r2 / D.E;
-    int e = r2 - hap * D.E;
-    if (e == 0) {
-        type = EV_DEATH;
-        nhap = (int)pp[D.o_g + hap];
-    } else if (e == 1) {
-        type = EV_SAMPLING;
-        nhap = (int)pp[D.o_g + hap];
-    } else if (e < 2 + 3 * D.U) {
-        int uk = e - 2, u = uk / 3, k = uk - u * 3;
-        type = EV_MUTATION;
-        nhap = mutate_hap(hap, u, k, D.U);
-    } else {
-        type = EV_BIRTH;
-        nhap = e - 2 - 3 * D.U;
-    }
-}
 
 __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga) {
     const Dims D = st.D;

@@ -67,6 +67,9 @@ cudaError_t launch_propensities(const DevState &st, int r, double *out, double *
 cudaError_t launch_prepare(const DevState &st, int first, int tau_mode, cudaStream_t stream);
 cudaError_t launch_refresh(const DevState &st, cudaStream_t stream);
 cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms);
+cudaError_t launch_curves(const DevState &st, int rep_first, int rep_count, int step_num, long long *inf, long long *sus,
+                          long long *removed, long long *sampled, double *time_points, int *last_point,
+                          cudaStream_t stream, int num_sms);
 cudaError_t launch_rates_tap(const DevState &st, int r, double *ev, double *hp, double *popRate, double *migPop,
                              double *totals, cudaStream_t stream);
 
