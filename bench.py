@@ -58,6 +58,7 @@ def parse_args():
     ap.add_argument("--leaps", type=int, default=32, help="tau leaps per replicate per step")
     ap.add_argument("--scenario", default="t3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-curves", action="store_true", help="skip the (untimed) epidemic-curves pass reported beside the metric")
     ap.add_argument("--phases", action="store_true", help="add the tau kernel's per-phase critical-path cycles (timing tap)")
     ap.add_argument("--cpu-seconds", type=float, default=4.0, help="target timed CPU seconds per worker")
     ap.add_argument("--cpu-worker", nargs=4, metavar=("SEED", "REPS", "LEAPS", "SCENARIO"), default=None)
@@ -385,6 +386,24 @@ def gpu_arm(args, rank, world, local_rank):
     ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - w0))
     clk = clocks.stop() if rank == 0 else None
 
+    # ---- (reported beside the metric, outside the timed regions) epidemic curves of every replicate over the log the
+    #      last step left in HBM: one read of R*L dense rows (B_leap each) by curves_kernel
+    curves = None
+    if rank == 0 and not args.no_curves:
+        try:
+            t_c = []
+            for _ in range(3):
+                cv = h.epidemic_curves(8, want=("infectious",))
+                t_c.append(h.last_kernel_ms())
+            Sx_l, I_l = h.get_state()
+            assert np.array_equal(cv["infectious"][:, -1], I_l), "curves: last grid point != final state"
+            log_bytes = float(R) * L * (4 * P + 16)
+            curves = {"kernel": "curves_kernel", "kernel_ms": min(t_c), "log_bytes_read": log_bytes,
+                      "achieved_GBps": log_bytes / (min(t_c) * 1e-3) / 1e9, "grid_points": 9,
+                      "check": "last grid point equals the final state of all %d replicates" % R}
+        except Exception as ex:
+            curves = {"error": str(ex)}
+
     # ---- final all-gather of per-replicate summaries (the only collective of the path)
     sptr = h.summaries_dev_ptr()
     summ = torch.as_tensor(_DevArray(sptr, (R, _capi.NSUMMARY), "<f8"), device=dev)
@@ -439,6 +458,10 @@ def gpu_arm(args, rank, world, local_rank):
             "phase_a": {"mean_events": float(np.mean(cA["events"])), "mean_time": float(np.mean(cA["time"])),
                         "mean_infectious": float(I0.sum() / R)},
         }
+        if curves is not None:
+            line["epidemic_curves"] = curves
+            if "achieved_GBps" in curves:
+                curves["frac_of_hbm_peak"] = curves["achieved_GBps"] / peak
         if phase_cycles is not None:
             names = (["wipe+lists+Q", "drifts+tau", "primary draws", "slow-path drain", "feasibility", "apply", "lockdown vote"]
                      if KERNEL == "tau_kernel" else

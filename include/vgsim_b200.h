@@ -195,7 +195,7 @@ int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset);
 
 /* Launch accounting: kernels launched by this handle since creation. */
 int64_t vgsim_launch_count(vgsim_handle h);
-/* Device time of the LAST forward kernel (tau / direct), bracketed by CUDA events on the handle's
+/* Device time of the LAST hot kernel (tau / direct / epidemic curves), bracketed by CUDA events on the handle's
  * stream inside vgsim_simulate_* (replaces the reference's time.time() pair, src/_interface.py:821-827).
  * Blocks until that kernel has finished. */
 int vgsim_last_kernel_ms(vgsim_handle h, float *ms);

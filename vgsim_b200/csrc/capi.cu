@@ -710,7 +710,10 @@ int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step
     if (last_point && !rc) rc = dalloc(h, &d_lp, (size_t)rep_count);
     cudaError_t e = cudaSuccess;
     if (!rc) {
+        cudaEventRecord(h->ev_k0, h->stream);  // vgsim_last_kernel_ms then reports this kernel
         e = launch_curves(h->st, rep_first, rep_count, step_num, d_inf, d_sus, d_rem, d_smp, d_tp, d_lp, h->stream, h->num_sms);
+        cudaEventRecord(h->ev_k1, h->stream);
+        h->ev_valid = true;
         h->launches++;
     }
     auto back = [&](void *dst, const void *src, size_t bytes) {

@@ -10,7 +10,7 @@
 // _engine.py get_data_infectious).  The log is read forward exactly once:
 //   * direct-method rows: 16 B each (fp64 time + packed descriptor), 32 rows per warp load; rows are applied in
 //     order by the lanes that hold them (the updates commute, only the grid crossings are ordered);
-//   * MULTITYPE rows: the leap's dense row int32[P] is scanned with 16-byte loads, 4 in flight per lane (2 KB per
+//   * MULTITYPE rows: the leap's dense row int32[P] is scanned with 16-byte loads, 8 in flight per lane (4 KB per
 //     warp), and only non-zero counts are decoded (logrec.cuh) and applied with shared-memory atomics.
 // Grid: t_j = j * currentTime / step_num, j = 0..step_num (the reference's time_points).  The value at j is the
 // state after every log row with time <= t_j; whenever the next row's time exceeds t_j the warp writes the
@@ -61,7 +61,7 @@ __device__ __forceinline__ void curve_apply(int type, int hap, int pop, int nhap
     }
 }
 
-__global__ void __launch_bounds__(256) curves_kernel(const DevState st, const CurveArgs a, int slice_bytes) {
+__global__ void __launch_bounds__(512) curves_kernel(const DevState st, const CurveArgs a, int slice_bytes) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -142,15 +142,15 @@ __global__ void __launch_bounds__(256) curves_kernel(const DevState st, const Cu
                 }
                 const int4 *row = reinterpret_cast<const int4 *>(st.tau_counts + ((size_t)r * st.leap_cap + unpack_multi(dk)) * D.Pp);
                 const int n16 = D.Pp >> 2;
-                for (int b4 = 0; b4 < n16; b4 += 128) {
-                    int4 v[4];
+                for (int b4 = 0; b4 < n16; b4 += 256) {
+                    int4 v[8];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < 8; u++) {
                         const int j = b4 + u * 32 + lane;
                         v[u] = j < n16 ? __ldcs(row + j) : make_int4(0, 0, 0, 0);  // streamed once: evict first
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < 8; u++) {
                         if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0) continue;
                         const int c0 = (b4 + u * 32 + lane) * 4;
                         const int vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
@@ -182,7 +182,7 @@ cudaError_t launch_curves(const DevState &st, int rep_first, int rep_count, int 
     const int slice = ((3 * st.D.K * st.D.H + st.D.K * st.D.S) * 8 + 15) & ~15;
     int nw = (227 * 1024) / slice;
     if (nw < 1) return cudaErrorInvalidValue;  // the state of one replicate does not fit one SM's shared memory
-    if (nw > 8) nw = 8;
+    if (nw > 16) nw = 16;
     cudaError_t e = cudaFuncSetAttribute(curves_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nw * slice);
     if (e != cudaSuccess) return e;
     int per_sm = 1;

@@ -112,3 +112,107 @@ def writeMutations(mut, len_prufer, name_file, file_path):
     fn = (file_path + '/' if file_path is not None else '') + name_file + ".tsv"
     with open(fn, 'w') as f:
         f.writelines(mutation_lines(mut, len_prufer))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Text parameter formats of the command-line tool (reference src/IO.py:4-142,
+# testing/cmd_example/example.{rt,su,pp,mg,st}).  Same function names and return values as the reference's
+# readers.  Deliberate differences: '#' comment lines and blank lines after the two header lines are skipped (the
+# reference's `next` there is a no-op, so a comment line crashes it), and malformed input raises ValueError
+# instead of calling sys.exit.
+
+def _rows(fn, header_lines):
+    with open(fn) as f:
+        lines = f.read().splitlines()
+    head = [l.rstrip().split(" ") for l in lines[:header_lines]]
+    body = [l.rstrip().split(" ") for l in lines[header_lines:] if l.strip() and not l.startswith("#")]
+    return head, body
+
+
+def _site_allele(haplotype, site, sites):
+    """Base-4 digit of `haplotype` at `site` (site 0 = most significant), reference calculate_allele (src/IO.py:64-68)."""
+    return (haplotype // 4 ** (sites - site - 1)) % 4
+
+
+def read_rates(fn):
+    """*.rt -> (bRate[H], dRate[H], sRate[H], mRate[H][U][5]).  Columns `[H] B D S M0 M1 ...`; with `SP` in place of
+    `S` the third column is a sampling PROBABILITY (d = D*(1-SP), s = D*SP, src/IO.py:32-37).  A mutation field is
+    `rate` or `rate,p1,p2,p3`; the returned entry is [rate, w0..w3] with a 0 inserted at the haplotype's own allele
+    (src/IO.py:53-62)."""
+    head, body = _rows(fn, 2)
+    cols = head[1]
+    shift = 1 if cols[0] == "H" else 0
+    if len(cols) - shift < 3:
+        raise ValueError("At least three rates (B, D, S) are expected")
+    sp = cols[2 + shift] == "SP"
+    b, d, s, m = [], [], [], []
+    for row in body:
+        row = row[shift:]
+        b.append(float(row[0]))
+        if sp:
+            d.append(float(row[1]) * (1 - float(row[2])))
+            s.append(float(row[1]) * float(row[2]))
+        else:
+            d.append(float(row[1]))
+            s.append(float(row[2]))
+        muts = []
+        for field in row[3:]:
+            parts = field.split(",")
+            if len(parts) == 1:
+                muts.append([float(parts[0]), 1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0])
+            elif len(parts) == 4:
+                muts.append([float(x) for x in parts])
+            else:
+                raise ValueError("Error in mutations!!!")
+        m.append(muts)
+    H = len(m)
+    sites = 0
+    while 4 ** sites < H:
+        sites += 1
+    if 4 ** sites != H:
+        raise ValueError("the number of haplotype rows must be a power of 4")
+    for h in range(H):
+        for u in range(len(m[0])):
+            m[h][u].insert(_site_allele(h, u, len(m[0])) + 1, 0)
+    return b, d, s, m
+
+
+def read_susceptibility(fn):
+    """*.su -> (susceptibility[H][S] as the file's strings, susceptibility type[H]); columns `[H] T S0 S1 ...`."""
+    head, body = _rows(fn, 2)
+    shift = 1 if head[1][0] == "H" else 0
+    sus, typ = [], []
+    for row in body:
+        row = row[shift:]
+        typ.append(int(row[0]))
+        sus.append(row[1:])
+    return sus, typ
+
+
+def read_populations(fn):
+    """*.pp -> (sizes, contactDensity, contactAfter, startLD, endLD, samplingMultiplier); columns
+    `id size contactDensity [conDenAfterLD,startLD,endLD] [samplingMultiplier]`, the two optional fields in either
+    order (src/IO.py:88-129)."""
+    _, body = _rows(fn, 2)
+    sizes, cd, after, start, end, mult = [], [], [], [], [], []
+    for row in body:
+        sizes.append(int(row[1]))
+        cd.append(float(row[2]))
+        extra = [f.split(",") for f in row[3:5]]
+        npi = [e for e in extra if len(e) == 3]
+        sm = [e for e in extra if len(e) == 1]
+        if len(row) == 4:
+            if sm:
+                after.append(0); start.append(1.0); end.append(1.0); mult.append(float(sm[0][0]))
+            elif npi:
+                after.append(float(npi[0][0])); start.append(float(npi[0][1])); end.append(float(npi[0][2])); mult.append(1)
+        elif len(row) == 5 and npi and sm:
+            after.append(float(npi[0][0])); start.append(float(npi[0][1])); end.append(float(npi[0][2]))
+            mult.append(float(sm[0][0]))
+    return sizes, cd, after, start, end, mult
+
+
+def read_matrix(fn):
+    """*.mg / *.st -> list of rows of floats (one header line)."""
+    _, body = _rows(fn, 1)
+    return [[float(v) for v in row] for row in body]
