@@ -11,7 +11,8 @@
 //   * direct-method rows: 16 B each (fp64 time + packed descriptor), 32 rows per warp load; rows are applied in
 //     order by the lanes that hold them (the updates commute, only the grid crossings are ordered);
 //   * MULTITYPE rows: the leap's dense row int32[P] is scanned with 16-byte loads, 8 in flight per lane (4 KB per
-//     warp), and only non-zero counts are decoded (logrec.cuh) and applied with shared-memory atomics.
+//     warp); the ~1 % non-zero counts are compacted into a per-warp queue (three ballots per round) and decoded
+//     (logrec.cuh) and applied with shared-memory atomics 32 at a time, every lane busy.
 // Grid: t_j = j * currentTime / step_num, j = 0..step_num (the reference's time_points).  The value at j is the
 // state after every log row with time <= t_j; whenever the next row's time exceeds t_j the warp writes the
 // snapshot of point j with coalesced 8-byte stores.  Points after the last row repeat the final state; the index
@@ -27,6 +28,8 @@
 namespace vg {
 
 extern __shared__ __align__(16) unsigned char curves_smem[];
+
+#define CURVE_QCAP 256  // >= 128 (one round of 32 int4 can add that many) 
 
 struct CurveArgs {
     int rep_first, rep_count, step_num;
@@ -61,12 +64,13 @@ __device__ __forceinline__ void curve_apply(int type, int hap, int pop, int nhap
     }
 }
 
-__global__ void __launch_bounds__(512) curves_kernel(const DevState st, const CurveArgs a, int slice_bytes) {
+__global__ void __launch_bounds__(512, 1) curves_kernel(const DevState st, const CurveArgs a, int slice_bytes) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned long long *I = reinterpret_cast<unsigned long long *>(curves_smem + (size_t)wid * slice_bytes);
     unsigned long long *Sx = I + KH, *rem = Sx + KS, *smp = rem + KH;
+    int2 *queue = reinterpret_cast<int2 *>(smp + KH);  // (channel, count) of the non-zero counts of the row being scanned
     const int T = a.step_num;
     for (int q = blockIdx.x * nw + wid; q < a.rep_count; q += gridDim.x * nw) {
         const int r = a.rep_first + q;
@@ -142,6 +146,19 @@ __global__ void __launch_bounds__(512) curves_kernel(const DevState st, const Cu
                 }
                 const int4 *row = reinterpret_cast<const int4 *>(st.tau_counts + ((size_t)r * st.leap_cap + unpack_multi(dk)) * D.Pp);
                 const int n16 = D.Pp >> 2;
+                int qn = 0;  // entries in the warp's queue (uniform)
+                auto flush = [&]() {  // decode + apply the queued non-zero counts, 32 at a time with every lane busy
+                    __syncwarp();
+                    for (int e = lane; e < qn; e += 32) {
+                        const int2 en = queue[e];
+                        int mty, mh, mp, mnh, mnp;
+                        decode_record(en.x, D, pp, mty, mh, mp, mnh, mnp);
+                        curve_apply(mty, mh, mp, mnh, mnp, (long long)en.y, H, S, I, Sx, rem, smp);
+                    }
+                    __syncwarp();
+                    qn = 0;
+                };
+                const unsigned lt = (1u << lane) - 1u;
                 for (int b4 = 0; b4 < n16; b4 += 256) {
                     int4 v[8];
 #pragma unroll
@@ -151,18 +168,24 @@ __global__ void __launch_bounds__(512) curves_kernel(const DevState st, const Cu
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        if ((v[u].x | v[u].y | v[u].z | v[u].w) == 0) continue;
+                        // compaction: a dense row holds ~1 % non-zero counts, decoding them where they lie would run the
+                        // (division-heavy) decoder with one or two live lanes per pass
                         const int c0 = (b4 + u * 32 + lane) * 4;
-                        const int vals[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            if (vals[e] == 0 || c0 + e >= D.P) continue;
-                            int mty, mh, mp, mnh, mnp;
-                            decode_record(c0 + e, D, pp, mty, mh, mp, mnh, mnp);
-                            curve_apply(mty, mh, mp, mnh, mnp, (long long)vals[e], H, S, I, Sx, rem, smp);
-                        }
+                        const int cl = (v[u].x != 0) + (v[u].y != 0) + (v[u].z != 0) + (v[u].w != 0);
+                        const unsigned b0 = __ballot_sync(0xffffffffu, cl & 1), b1 = __ballot_sync(0xffffffffu, cl & 2),
+                                       b2 = __ballot_sync(0xffffffffu, cl & 4);
+                        if ((b0 | b1 | b2) == 0u) continue;
+                        const int tot = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                        if (qn + tot > CURVE_QCAP) flush();
+                        int pos = qn + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+                        if (v[u].x != 0) queue[pos++] = make_int2(c0, v[u].x);
+                        if (v[u].y != 0) queue[pos++] = make_int2(c0 + 1, v[u].y);
+                        if (v[u].z != 0) queue[pos++] = make_int2(c0 + 2, v[u].z);
+                        if (v[u].w != 0) queue[pos++] = make_int2(c0 + 3, v[u].w);
+                        qn += tot;
                     }
                 }
+                flush();
             }
         }
         __syncwarp();
@@ -179,7 +202,7 @@ cudaError_t launch_curves(const DevState &st, int rep_first, int rep_count, int 
     a.rep_first = rep_first; a.rep_count = rep_count; a.step_num = step_num;
     a.inf = inf; a.sus = sus; a.removed = removed; a.sampled = sampled;
     a.time_points = time_points; a.last_point = last_point;
-    const int slice = ((3 * st.D.K * st.D.H + st.D.K * st.D.S) * 8 + 15) & ~15;
+    const int slice = ((3 * st.D.K * st.D.H + st.D.K * st.D.S) * 8 + CURVE_QCAP * 8 + 15) & ~15;
     int nw = (227 * 1024) / slice;
     if (nw < 1) return cudaErrorInvalidValue;  // the state of one replicate does not fit one SM's shared memory
     if (nw > 16) nw = 16;
