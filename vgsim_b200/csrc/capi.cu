@@ -105,7 +105,7 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
     st.params = params;
     st.rep_pp = rep_pp;
     st.seeds = seeds;
-    st.loc_cap = 64;
+    st.loc_cap = 64 + 16 * K;  // a deme flips its lockdown on and off a few times per wave; overflow sets a sticky error bit
     if (dalloc(h, &st.loc_sp, R * st.loc_cap) || dalloc(h, &st.loc_t, R * st.loc_cap) ||
         dalloc(h, &h->summaries, R * VGSIM_NSUMMARY) || dalloc(h, &h->tau_order, 2 * R)) {
         vgsim_destroy(h);
