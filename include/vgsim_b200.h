@@ -185,7 +185,10 @@ int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step
  * <= 1, and splits a non-zero total multinomially over the group's channels (independent Poissons
  * conditioned on their sum are multinomial, so the joint distribution is unchanged).  Variant 1 draws every
  * channel separately, exactly like the reference's GenerateEvents_tau (src/_BirthDeath.pyx:2454-2532);
- * tests compare both with theory and with each other. */
+ * tests compare both with theory and with each other.
+ * Bits 2 and 3 pick the kernel mapping (scheduling only, same log bit for bit): by default a batch small enough to
+ * be resident as 256-thread teams runs on the team kernel, larger batches on the warp-per-replicate kernel; bit 2
+ * forces the former, bit 3 the latter. */
 int vgsim_set_tau_variant(vgsim_handle h, int variant);
 /* Measurement tap: with bit 1 of the variant set, thread 0 of every CTA of the tau kernel accumulates the clock
  * cycles between consecutive barriers of the leap loop (critical path per phase: 0 row wipe + lists + Q,

@@ -314,7 +314,7 @@ def _run_kernel(name, Sx0, I0, R, variant, leaps, dt, seed0, two_points=False):
                                                  ("table3_k10", 3, 60.0, 3.0, False), ("t3small", 5, 60.0, 6.0, True),
                                                  ("w", 4, 80.0, 0.5, False)])
 def test_warp_kernel_reproduces_team_kernel(name, seed, t0, dt, two, variant):
-    """The warp-per-replicate kernel (default) and the team kernel (variant bit 2) share the drift / propensity
+    """The warp-per-replicate kernel (default for large batches) and the team kernel (default for few replicates) share the drift / propensity
     expressions, the summation orders, the Philox addressing and the samplers, so from the same state and seeds
     they must leave the same log: identical leap counts, per-type counters, final compartments and dense rows.
     Covers the mask path (H <= 64, K <= 32), the generic path (w: K = 100), lockdown flips (s7, s9, table3) and
@@ -322,8 +322,8 @@ def test_warp_kernel_reproduces_team_kernel(name, seed, t0, dt, two, variant):
     Sx0, I0 = warm_state(name, seed, t0)
     assert I0.sum() > 0
     R = 24 if name == "w" else 150
-    a = _run_kernel(name, Sx0, I0, R, variant, 40, dt, 700 + variant, two)
-    b = _run_kernel(name, Sx0, I0, R, variant | 4, 40, dt, 700 + variant, two)
+    a = _run_kernel(name, Sx0, I0, R, variant | 8, 40, dt, 700 + variant, two)   # bit 3: warp kernel even for few replicates
+    b = _run_kernel(name, Sx0, I0, R, variant | 4, 40, dt, 700 + variant, two)   # bit 2: team kernel
     ca, cb = a[0], b[0]
     assert ca["leaps"].min() >= 1
     for k in ("leaps", "bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus", "swapLockdown"):

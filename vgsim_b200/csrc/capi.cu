@@ -744,8 +744,8 @@ int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset) {
 }
 
 int vgsim_set_tau_variant(vgsim_handle h, int variant) {
-    if (variant < 0 || variant > 7)
-        return fail("tau variant must be 0..7 (bit 0: per-channel draws, bit 1: phase timing, bit 2: team kernel)");
+    if (variant < 0 || variant > 15 || (variant & 12) == 12)
+        return fail("tau variant must be 0..15 (bit 0: per-channel draws, bit 1: phase timing, bit 2: force the team kernel, bit 3: force the warp kernel)");
     h->tau_variant = variant;
     return 0;
 }

@@ -319,16 +319,34 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                 } else if (ty == EV_MULTITYPE) {  // :869-993
                     const long long leap = unpack_multi(d);
                     const int *row = st.tau_counts + ((size_t)r * st.leap_cap + leap) * D.Pp;
-                    for (int base = 0; base < D.P && !bad; base += 32) {
-                        int c_l = base + lane;
-                        int num_l = c_l < D.P ? row[c_l] : 0;
-                        unsigned nzmask = __ballot_sync(0xffffffffu, num_l != 0);
+                    // the row is scanned in ascending channel order, 128 counts (one int4 per lane) per step; eight steps'
+                    // worth of loads (4 KB per warp) are in flight at a time -- one dependent 128-byte load per step made
+                    // the scan latency-bound (11 s for 32 world-shape replicates x 1,200 leaps of 493,400 channels)
+                    const int4 *row4 = reinterpret_cast<const int4 *>(row);
+                    const int n16 = D.Pp >> 2;
+                    int4 pre[8];
+                    for (int base4 = 0; base4 < n16 && !bad; base4 += 32) {
+                        if ((base4 & 255) == 0) {
+#pragma unroll
+                            for (int u = 0; u < 8; u++) {
+                                const int j4 = base4 + u * 32 + lane;
+                                pre[u] = j4 < n16 ? __ldcs(row4 + j4) : make_int4(0, 0, 0, 0);
+                            }
+                        }
+                        const int4 v_l = pre[0];
+#pragma unroll
+                        for (int u = 0; u < 7; u++) pre[u] = pre[u + 1];
+                        unsigned nzmask = __ballot_sync(0xffffffffu, (v_l.x | v_l.y | v_l.z | v_l.w) != 0);
                         while (nzmask) {
                             int b = __ffs(nzmask) - 1;
                             nzmask &= nzmask - 1;
-                            const long long num = __shfl_sync(0xffffffffu, num_l, b);
+                            const int q0 = __shfl_sync(0xffffffffu, v_l.x, b), q1 = __shfl_sync(0xffffffffu, v_l.y, b),
+                                      q2 = __shfl_sync(0xffffffffu, v_l.z, b), q3 = __shfl_sync(0xffffffffu, v_l.w, b);
+                            for (int e4 = 0; e4 < 4; e4++) {
+                            const long long num = e4 == 0 ? q0 : e4 == 1 ? q1 : e4 == 2 ? q2 : q3;
+                            if (num == 0) continue;
                             int mty, mh, mp, mnh, mnp;
-                            decode_record(base + b, D, pp, mty, mh, mp, mnh, mnp);
+                            decode_record((base4 + b) * 4 + e4, D, pp, mty, mh, mp, mnh, mnp);
                             const int cell = mp * H + mh;  // the cell that receives the parked (new) lineages
                             int nnl = 0;
                             if (mty == EV_BIRTH) {  // :879-915
@@ -423,6 +441,8 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                             // receiving cell can hold any — untouched cells have nothing parked and no delta)
                             for (int i = nnl - 1; i >= 0; i--) L.push(cell, nl[i]);
                             if (g.err | L.err | O.err) bad = 1;
+                            if (bad) break;
+                            }  // e4
                             if (bad) break;
                         }
                     }

@@ -1245,8 +1245,19 @@ static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStre
 cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp,
                        int *order_buf) {
     if ((long long)st.D.K * st.D.H + st.D.K >= (1 << 20)) return cudaErrorInvalidValue;  // owner id is packed in 20 bits
-    bool team = (variant & 4) != 0;
-    if (const char *e = getenv("VGSIM_TAU_KERNEL")) team = team || e[0] == 't';
+    const size_t stride = ((size_t)tau_layout(st.D, false, TAU_TEAM).bytes + 15) & ~(size_t)15;
+    int teams = (int)((227 * 1024 - TAU_CTA_TAIL) / stride), cap = 0;
+    if (teams > 4) teams = 4;
+    if (teams < 1) teams = 1;
+    bool team = (variant & 4) != 0, force_warp = (variant & 8) != 0;
+    if (const char *e = getenv("VGSIM_TAU_KERNEL")) {
+        team = team || e[0] == 't';
+        force_warp = force_warp || e[0] == 'w';
+    }
+    // Few replicates (all of them resident at once as 256-thread teams): the GPU is latency- not throughput-bound, and a
+    // team walks a leap sooner than a single warp does -- 8.1x at the world shape (K = 100: the K x K x H force-of-
+    // infection sums), 32 replicates x 1,200 leaps: 607 ms vs 4,948 ms (profiles/r1_k_*), same log bit for bit.
+    if (!team && !force_warp && st.R <= num_sms * teams) team = true;
     if (!team) {
         int max_warps = 16;
         if (const char *e = getenv("VGSIM_TAU_WARPS")) max_warps = atoi(e);
@@ -1278,10 +1289,6 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
         }
         // a single replicate's state does not fit one warp slice: fall through to the team kernel
     }
-    const size_t stride = ((size_t)tau_layout(st.D, false, TAU_TEAM).bytes + 15) & ~(size_t)15;
-    int teams = (int)((227 * 1024 - TAU_CTA_TAIL) / stride), cap = 0;
-    if (teams > 4) teams = 4;
-    if (teams < 1) teams = 1;
     if (const char *e = getenv("VGSIM_TAU_CFG")) sscanf(e, "%dx%d", &teams, &cap);
     if (teams >= 4) return launch_tau_cfg<4>(st, a, stream, num_sms, variant, cap);
     if (teams == 3) return launch_tau_cfg<3>(st, a, stream, num_sms, variant, cap);
