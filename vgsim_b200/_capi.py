@@ -190,10 +190,19 @@ class Handle:
         if sync:
             self.synchronize()
 
+    # bit 16 (ERR_CLAMPED): a MULTITYPE BIRTH record drew more coalescences than its cell has lineage pairs left.  The
+    # reference walks off the end of a vector there (src/_BirthDeath.pyx:885-915: `lbs -= 2` per coalescence with no
+    # bound); the device clamps, the tree stays valid -- reported as a warning, everything else raises.
+    NONFATAL_FLAGS = 16
+
     def synchronize(self, strict=True):
         rc = lib.vgsim_synchronize(self._h)
         if rc != 0 and strict:
-            raise VgsimError(lib.vgsim_last_error().decode())
+            msg = lib.vgsim_last_error().decode()
+            if rc & ~self.NONFATAL_FLAGS:
+                raise VgsimError(msg)
+            import warnings
+            warnings.warn(msg, RuntimeWarning, stacklevel=2)
         return rc
 
     def genealogy(self, seed=None, uniform_stream=None, raw_words=False, sync=True):
