@@ -748,7 +748,7 @@ __device__ __forceinline__ void primary_draw(double lam, uint32_t hi, int owner,
 // multinomial split of an aggregated total: n events of cell (p,h), each assigned to one channel of the
 // group with probability prop_channel / prop_total (exact: independent Poissons conditioned on their sum)
 template <class SH>
-static __device__ __noinline__ int split_total(int n, int p, int h, int code, int *row, const Dims &D, const SH &s,
+__device__ __forceinline__ int split_total_impl(int n, int p, int h, int code, int *row, const Dims &D, const SH &s,
                                                 const double *eff, const DrawGeom &g, PhiloxCtx ctx) {
     LeapTally tr;  // the events are all of one type: the caller tallies the returned count
     tr.B = tr.Dd = tr.Sm = tr.M = tr.I = tr.G = 0;
@@ -815,6 +815,16 @@ static __device__ __noinline__ int split_total(int n, int p, int h, int code, in
     return booked;
 }
 
+// Team kernel: one out-of-line copy (the 1024-thread CTA is capped at 64 registers).  Warp kernel: inlined -- out of
+// line, every `s.X[...]` inside re-read the view's (offset, stride) pair through a GENERIC pointer to the
+// __grid_constant__ parameter block (LD.E, ~145 per leap, each a long-scoreboard wait with two live lanes while the
+// other 13 warps of the CTA sat at the generation barrier; ncu profiles/r1_i_*).
+template <class SH>
+static __device__ __noinline__ int split_total(int n, int p, int h, int code, int *row, const Dims &D, const SH &s,
+                                                const double *eff, const DrawGeom &g, PhiloxCtx ctx) {
+    return split_total_impl(n, p, h, code, row, D, s, eff, g, ctx);
+}
+
 // one slow-path queue entry: recompute its lambda (same expression as the primary pass), finish the Poisson
 // draw, then write / split the count
 template <class SH>
@@ -844,7 +854,9 @@ __device__ __forceinline__ void process_entry(int e, double tau, int *row, const
         ctx.dom0 = 0u;
         const int n = (int)poisson_inversion(lam, hi, ctx, code);
         if (n != 0) {
-            const int nb = split_total(n, p, h, code, row, D, s, eff, g, ctx);
+            int nb;
+            if constexpr (SH::has_qin) nb = split_total_impl(n, p, h, code, row, D, s, eff, g, ctx);
+            else nb = split_total(n, p, h, code, row, D, s, eff, g, ctx);
             if (code == 2) tr.M += nb;
             else tr.G += nb;
         }
