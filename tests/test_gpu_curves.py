@@ -98,3 +98,74 @@ def test_curves_argument_errors():
         e.epidemic_curves(0)
     with pytest.raises(VgsimError):
         e.epidemic_curves(10, rep_first=1, rep_count=2)
+
+
+def _oracle_curves(chain, I0_total, grid):
+    """Total infectious at the grid times and sampling-time statistics from an oracle (== reference algorithm) log."""
+    t, ty = chain[0], chain[1].astype(int)
+    delta = np.where((ty == 0) | (ty == 5), 1, 0) - np.where((ty == 1) | (ty == 2), 1, 0)
+    cum = np.concatenate([[0], np.cumsum(delta)])
+    inf = I0_total + cum[np.searchsorted(t, grid, side="right")]
+    ts = t[ty == 2]
+    return inf, ts
+
+
+@pytest.mark.parametrize("name,t_end", [("s9", 5.0), ("s4", 8.0), ("s7", 7.0)])
+def test_curve_and_sample_time_distributions_match_oracle(name, t_end):
+    """BASELINE north_star: 'two-sample KS at alpha = 0.01 on ... epidemic curves, sample times'.  Device replicates
+    (Philox, curves from the curves kernel) vs oracle runs (PCG64, curves from the exported log), both stopped at the
+    same epidemic time; KS (Bonferroni) on the total infectious count at 8 fixed times, the number of sampled cases,
+    and the mean / first sampling time."""
+    from scipy import stats
+    from test_gpu_tau import _ks_all
+    R, RO, T = 1000, 150, 64
+    e = make_engine(name, 9100, replicates=R)
+    e.SimulatePopulation(10 ** 7, 10 ** 9, t_end, 200)
+    c = e.epidemic_curves(T, want=("infectious", "sampled"))
+    cnt = e.counters()
+    alive = cnt["events"] > 100                      # the reference restarts runs that die within 100 events
+    fixed = np.linspace(0.1, 0.95, 8) * t_end
+    tp = c["time_points"]                            # [R, T+1]; every replicate's grid ends at its own last event
+    tot = c["infectious"].sum(axis=(2, 3))
+    smp = c["sampled"].sum(axis=(2, 3))
+    dev = {}
+    idx = np.stack([np.searchsorted(tp[r], fixed, side="right") - 1 for r in range(R)])   # last grid point <= fixed time
+    for j in range(len(fixed)):
+        dev["inf_%d" % j] = tot[np.arange(R), idx[:, j]][alive]
+    dev["samples"] = cnt["sCounter"][alive]
+    keys = list(dev)
+    ora = {k: [] for k in keys}
+    ora_first, ora_mean, dev_first, dev_mean = [], [], [], []
+    for r in range(RO):
+        eo = make_engine(name, 40000 + r)
+        Sx0, I0 = first_infection(eo._susceptible, eo._infectious)
+        om = O.OracleModel.from_engine(eo)
+        om.simulate(10 ** 7, sample_size=10 ** 9, epidemic_time=t_end)
+        chain = om.events()
+        if chain.shape[1] <= 100:
+            continue
+        # same discretisation as the device side: the value at a fixed time is read at the last grid point before it
+        ct = om.counters()["time"]
+        grid = np.array([i * ct / T for i in range(T + 1)])
+        g_idx = np.searchsorted(grid, fixed, side="right") - 1
+        inf, ts = _oracle_curves(chain, int(I0.sum()), grid[g_idx])
+        for j in range(len(fixed)):
+            ora["inf_%d" % j].append(inf[j])
+        ora["samples"].append(len(ts))
+        if len(ts):
+            ora_first.append(ts[0]); ora_mean.append(ts.mean())
+    assert len(ora["samples"]) > 0.5 * RO
+    bad = _ks_all(dev, ora, keys)
+    assert not bad, bad
+    # sampling times on the device side, from the cumulative `sampled` curve: first grid time with a sample, and the
+    # mean sampling time up to the grid resolution (same reduction applied to the oracle's exact times)
+    for r in np.flatnonzero(alive):
+        if smp[r, -1] == 0:
+            continue
+        inc = np.diff(np.concatenate([[0], smp[r]]))
+        dev_first.append(tp[r][np.flatnonzero(inc)[0]])
+        dev_mean.append((inc * tp[r]).sum() / inc.sum())
+    step = t_end / T                                  # grid resolution: the device times are rounded UP to a grid point
+    p1 = stats.ks_2samp(np.asarray(dev_first) - step / 2, ora_first).pvalue
+    p2 = stats.ks_2samp(np.asarray(dev_mean) - step / 2, ora_mean).pvalue
+    assert p1 > 0.005 and p2 > 0.005, (p1, p2)
