@@ -296,6 +296,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     # ---- Phase A (untimed): device direct method to T_WARM for every replicate; snapshot the states
     h.simulate_direct(250000, -1, T_WARM, 200)
+    direct_ms = h.last_kernel_ms()
     cA = h.get_counters()
     Sx0, I0 = h.get_state()
     hSx = torch.from_numpy(Sx0).pin_memory()
@@ -456,7 +457,8 @@ def gpu_arm(args, rank, world, local_rank):
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "device_error_flags": err,
             "phase_a": {"mean_events": float(np.mean(cA["events"])), "mean_time": float(np.mean(cA["time"])),
-                        "mean_infectious": float(I0.sum() / R)},
+                        "mean_infectious": float(I0.sum() / R), "direct_kernel_ms": direct_ms,
+                        "direct_events_per_s": float(np.sum(cA["events"])) / (direct_ms * 1e-3)},
         }
         if curves is not None:
             line["epidemic_curves"] = curves
