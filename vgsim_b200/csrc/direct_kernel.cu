@@ -200,7 +200,9 @@ __device__ __forceinline__ int small_choose(WF wf, int n, double total, double &
     return pick;
 }
 
-__global__ void direct_kernel(DevState st, SimArgs a, int warps_per_cta) {
+// 16 warps per CTA at 128 registers: the event loop is one dependent chain per replicate, so what the SM needs is
+// more replicates in flight (the unbounded build used 168 registers = 8 warps per SM)
+__global__ void __launch_bounds__(512, 1) direct_kernel(DevState st, SimArgs a, int warps_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Dims D = st.D;
     const int K = D.K, H = D.H, S = D.S, U = D.U;
@@ -525,8 +527,8 @@ __global__ void rates_tap_kernel(DevState st, int r, double *ev, double *hp, dou
 
 cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms) {
     size_t wbytes = (dir_warp_bytes(st.D) + 15) & ~(size_t)15;
-    int wpc = 8;
-    while (wpc > 1 && wbytes * wpc > 100 * 1024) wpc >>= 1;
+    int wpc = 16;
+    while (wpc > 1 && wbytes * wpc > 220 * 1024) wpc >>= 1;
     size_t smem = wbytes * wpc;
     if (smem > 220 * 1024) return cudaErrorInvalidConfiguration;
     cudaError_t e = cudaFuncSetAttribute(direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
