@@ -50,8 +50,10 @@ __device__ __forceinline__ void curve_apply(int type, int hap, int pop, int nhap
     } else if (type == EV_DEATH || type == EV_SAMPLING) {  // recovered go to group nhap = suscType[hap]
         atomicAdd(&I[cell], m);
         atomicAdd(&Sx[pop * S + nhap], u);
-        atomicAdd(&rem[cell], u);
-        if (type == EV_SAMPLING) atomicAdd(&smp[cell], u);
+        if (rem) {  // the cumulative tallies exist only when one of them was asked for
+            atomicAdd(&rem[cell], u);
+            if (type == EV_SAMPLING) atomicAdd(&smp[cell], u);
+        }
     } else if (type == EV_MUTATION) {
         atomicAdd(&I[cell], m);
         atomicAdd(&I[pop * H + nhap], u);
@@ -69,8 +71,10 @@ __global__ void __launch_bounds__(512, 1) curves_kernel(const DevState st, const
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned long long *I = reinterpret_cast<unsigned long long *>(curves_smem + (size_t)wid * slice_bytes);
-    unsigned long long *Sx = I + KH, *rem = Sx + KS, *smp = rem + KH;
-    int2 *queue = reinterpret_cast<int2 *>(smp + KH);  // (channel, count) of the non-zero counts of the row being scanned
+    const bool tallies = a.removed != nullptr || a.sampled != nullptr;
+    unsigned long long *Sx = I + KH, *rem = tallies ? Sx + KS : nullptr, *smp = tallies ? rem + KH : nullptr;
+    // (channel, count) of the non-zero counts of the row being scanned
+    int2 *queue = reinterpret_cast<int2 *>(tallies ? smp + KH : Sx + KS);
     const int T = a.step_num;
     for (int q = blockIdx.x * nw + wid; q < a.rep_count; q += gridDim.x * nw) {
         const int r = a.rep_first + q;
@@ -79,8 +83,10 @@ __global__ void __launch_bounds__(512, 1) curves_kernel(const DevState st, const
         const long long *S0 = (st.first_simulation ? st.initSx : st.Sx) + (size_t)r * KS;
         for (int i = lane; i < KH; i += 32) {
             I[i] = (unsigned long long)I0[i];
-            rem[i] = 0ull;
-            smp[i] = 0ull;
+            if (tallies) {
+                rem[i] = 0ull;
+                smp[i] = 0ull;
+            }
         }
         for (int i = lane; i < KS; i += 32) Sx[i] = (unsigned long long)S0[i];
         __syncwarp();
@@ -159,12 +165,19 @@ __global__ void __launch_bounds__(512, 1) curves_kernel(const DevState st, const
                     qn = 0;
                 };
                 const unsigned lt = (1u << lane) - 1u;
+                int4 nxt[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int j = u * 32 + lane;
+                    nxt[u] = j < n16 ? __ldcs(row + j) : make_int4(0, 0, 0, 0);  // streamed once: evict first
+                }
                 for (int b4 = 0; b4 < n16; b4 += 256) {
                     int4 v[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) {
-                        const int j = b4 + u * 32 + lane;
-                        v[u] = j < n16 ? __ldcs(row + j) : make_int4(0, 0, 0, 0);  // streamed once: evict first
+                    for (int u = 0; u < 8; u++) {  // this block arrives while the previous one was compacted
+                        v[u] = nxt[u];
+                        const int j = b4 + 256 + u * 32 + lane;
+                        nxt[u] = j < n16 ? __ldcs(row + j) : make_int4(0, 0, 0, 0);
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
@@ -202,7 +215,8 @@ cudaError_t launch_curves(const DevState &st, int rep_first, int rep_count, int 
     a.rep_first = rep_first; a.rep_count = rep_count; a.step_num = step_num;
     a.inf = inf; a.sus = sus; a.removed = removed; a.sampled = sampled;
     a.time_points = time_points; a.last_point = last_point;
-    const int slice = ((3 * st.D.K * st.D.H + st.D.K * st.D.S) * 8 + CURVE_QCAP * 8 + 15) & ~15;
+    const int ncell = (removed || sampled) ? 3 : 1;  // I (+ removed, sampled) per infectious cell
+    const int slice = ((ncell * st.D.K * st.D.H + st.D.K * st.D.S) * 8 + CURVE_QCAP * 8 + 15) & ~15;
     int nw = (227 * 1024) / slice;
     if (nw < 1) return cudaErrorInvalidValue;  // the state of one replicate does not fit one SM's shared memory
     if (nw > 16) nw = 16;
