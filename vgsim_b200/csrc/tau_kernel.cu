@@ -1251,7 +1251,7 @@ static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStre
 }
 
 // Default: the warp-per-replicate kernel (tau_warp.cuh), one CTA per SM with as many warps as the shared memory
-// holds (<= 16).  The team kernel (256-thread teams, CTA-wide generations) stays available as a parity tap:
+// holds (<= 14).  The team kernel (256-thread teams, CTA-wide generations) stays available as a parity tap:
 // variant bit 2, or VGSIM_TAU_KERNEL=team; VGSIM_TAU_CFG = "<teams>x<ctas per SM>" then overrides its shape.
 // VGSIM_TAU_WARPS caps the warps per CTA of the warp kernel (A/B measurements).
 cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp,

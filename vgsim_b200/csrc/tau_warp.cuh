@@ -5,7 +5,7 @@
 // 1-lane multinomial split) while the other 31 warps of the SM idle, and the 64-register cap of a
 // 1024-thread CTA spills.  At T3 a leap touches ~70 infectious cells and ~200 real Poisson draws: that is
 // warp-sized work.  Here ONE WARP owns a replicate: no named barriers, no CTA-wide generations, every phase
-// is a lane-strided loop closed by __syncwarp(), and 14-16 independent replicates per SM keep the issue
+// is a lane-strided loop closed by __syncwarp(), and 14 independent replicates per SM keep the issue
 // slots busy while any one of them waits on a dependent chain.
 //
 // Per-replicate state lives in the warp's slice of dynamic shared memory: I as int32 (converted on use),
@@ -101,7 +101,9 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     L.o_warp0 = o;
     int nw = (max_bytes - o) / L.warp_bytes;
     if (nw > max_warps) nw = max_warps;
-    if (nw > 14) nw = 14;  // 448 threads: 144 registers per thread; 148 x 14 = 2072 replicates in flight
+    if (nw > 14) nw = 14;  // 148 x 14 = 2072 replicates in flight.  ptxas gives a 448-thread CTA 128 registers per thread
+                           // (4 warps of an SM sub-partition share 16 K registers; 144 does not launch), so 15-16 warps
+                           // would cost no registers -- at T3 the shared-memory slice (14.4 KB + Q table) is the limit
     L.nwarps = nw;
     if (nw >= 1) {  // what is left of the shared memory holds the per-leap table of Q[p, present h]
         int spare = ((max_bytes - o) / nw - L.warp_bytes) & ~15;
