@@ -706,7 +706,13 @@ __device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
     return g;
 }
 
-#define TAU_THETA 1.0        // a mutation / out-migration group is drawn as ONE Poisson total when lam_total <= theta
+#ifndef TAU_THETA
+// a mutation / out-migration group is drawn as ONE Poisson total when lam_total <= theta (exact for any theta < 10).
+// The total wins when it is almost surely 0 (one early-out instead of 9 / 27 channel draws); a non-zero total costs a
+// serial multinomial split in one lane while the warp waits.  Measured at T3: theta 8 / 3 / 1 / 0.3 / 0.15 / 0.1 / 0.03
+// -> 8.60 / 7.19 / 6.38 / 6.17 / 6.16 / 6.19 / 6.43 ms per 131,072 leaps.
+#define TAU_THETA 0.25
+#endif
 
 // total out-migration propensity of cell (p,h): sum over targets and groups of the channel propensities,
 // factorised through Q[tp,h] = sum_s Sx[tp,s] sigma[s,h]
