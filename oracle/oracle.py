@@ -372,3 +372,36 @@ def ref_data_susceptible(chain, multi, initial, current_time, pop, sus, step_num
                 elif mt == MIGRATION and multi["npop"][j] == pop and multi["hap"][j] == sus:
                     Data[point] -= n
     return Data, tp
+
+
+def ref_epidemiology_timelines(chain, sizes, K, S, H, current_time, step_num):
+    """Literal restatement of output_epidemiology_timelines (reference src/_BirthDeath.pyx:1765-1847, dict branch).
+    Upstream the method cannot run (it reads `self.susceptible_num`, an attribute that does not exist, :1767), so there
+    is no reference output to pin against: this loop IS the specification the vectorised product code is checked
+    with.  Returns (times, sus[pts][K][S], inf[pts][K][H])."""
+    tp = [i * current_time / step_num for i in range(step_num + 1)]
+    sus = np.zeros((K, S), np.int64)
+    inf = np.zeros((K, H), np.int64)
+    for i in range(K):
+        sus[i, 0] = sizes[i]
+    inf[0, 0] += 1
+    sus[0, 0] -= 1
+    t_, ty_, h_, p_, nh_, np_ = (chain[k] for k in range(6))
+    times, out_s, out_i = [], [], []
+    point = 0
+    for j in range(chain.shape[1]):
+        ty, h, p, nh, npp = int(ty_[j]), int(h_[j]), int(p_[j]), int(nh_[j]), int(np_[j])
+        if ty == BIRTH:
+            inf[p, h] += 1; sus[p, nh] -= 1
+        elif ty == DEATH or ty == SAMPLING:
+            inf[p, h] -= 1; sus[p, nh] += 1
+        elif ty == MUTATION:
+            inf[p, h] -= 1; inf[p, nh] += 1
+        elif ty == SUSCCHANGE:
+            sus[p, h] -= 1; sus[p, nh] += 1
+        elif ty == MIGRATION:
+            sus[npp, nh] -= 1; inf[npp, h] += 1
+        if point <= step_num and tp[point] <= t_[j]:   # (the reference would raise IndexError past the last point)
+            times.append(tp[point]); out_s.append(sus.copy()); out_i.append(inf.copy())
+            point += 1
+    return times, np.array(out_s).reshape(-1, K, S), np.array(out_i).reshape(-1, K, H)

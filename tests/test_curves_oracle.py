@@ -63,3 +63,40 @@ def test_restated_curves_equal_reference(kind, name):
     for k, (p, s) in enumerate(g["groups"]):
         Data, tp = O.ref_data_susceptible(chain, multi, Sx0[p, s], ct, int(p), int(s), steps)
         np.testing.assert_array_equal(Data, g["sus_%d" % k])
+
+
+@pytest.mark.parametrize("name,steps", [("s9", 23), ("s7", 1000), ("s4", 7)])
+def test_vectorised_timelines_equal_the_literal_loop(name, steps):
+    """output_epidemiology_timelines: the product's numpy implementation (vgsim_b200/io.py) against the literal
+    restatement of the reference loop, on a reference-exact direct chain (upstream the method itself raises
+    AttributeError, so its loop is the specification)."""
+    from scenarios import SCENARIOS
+    from vgsim_b200 import io as vio
+    (U, K, S), _ = SCENARIOS[name]
+    H = 4 ** U
+    om = make_oracle(name, 2020)
+    om.simulate(100000)
+    chain, ct = om.events(), om.counters()["time"]
+    sizes = [1000000] * K if name != "s7" else None
+    from test_oracle_golden import Eng
+    (_, _, _), setup = SCENARIOS[name]
+    e = Eng(U, K, S, 1, False, False, int(1e6), 0.0)
+    setup(e)
+    sizes = list(e.sizes)
+    want = O.ref_epidemiology_timelines(chain, sizes, K, S, H, ct, steps)
+    got = vio.epidemiology_timelines(chain, sizes, K, S, H, ct, steps)
+    assert len(got[0]) == len(want[0]) > 0 and got[0] == want[0]
+    np.testing.assert_array_equal(got[1], want[1])
+    np.testing.assert_array_equal(got[2], want[2])
+    log = vio.timelines_as_dict(*got)
+    assert log["time"] == want[0] and log["P0"]["H0"] == list(want[2][:, 0, 0]) and len(log["P%d" % (K - 1)]) == S + H
+
+
+def test_timeline_log_files(tmp_path):
+    from vgsim_b200 import io as vio
+    times = [0.0, 0.5]
+    sus = np.array([[[9, 1]], [[8, 2]]], np.int64)          # [pts][K=1][S=2]
+    inf = np.array([[[1, 0, 0, 0]], [[2, 0, 1, 0]]], np.int64)
+    vio.write_timelines(times, sus, inf, directory=str(tmp_path / "logs"))
+    lines = open(tmp_path / "logs" / "PID0.log").read().splitlines()
+    assert lines == ["time S0 S1 H0 H1 H2 H3", "0.0 9 1 1 0 0 0 ", "0.5 8 2 2 0 1 0 "]

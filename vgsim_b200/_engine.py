@@ -783,6 +783,17 @@ class BirthDeathModel:
         Data[last + 1:] = 0.0
         return Data, [float(x) for x in tp], self._lockdown_rows(pop, replicate)
 
+    def output_epidemiology_timelines(self, step_num, output_file, replicate=0):
+        """Reference src/_BirthDeath.pyx:1765-1847 (semantics and quirks in vgsim_b200/io.py: epidemiology_timelines)."""
+        from . import io as _io
+        c = self._handle.get_counters()
+        times, sus, inf = _io.epidemiology_timelines(self.get_chain_events(replicate), self.sizes, self.popNum, self.susNum,
+                                                     self.hapNum, float(c["time"][replicate]), int(step_num))
+        if output_file == True:  # noqa: E712  (the reference compares with == True)
+            _io.write_timelines(times, sus, inf)
+            return None
+        return _io.timelines_as_dict(times, sus, inf)
+
     def get_lockdowns(self, replicate=0):
         return self._handle.get_lockdowns(replicate)
 

@@ -277,6 +277,10 @@ class Simulator:
         """infections, sample, time_points, lockdowns (reference src/_interface.py:617-633)."""
         return self.simulation.get_data_infectious(population, haplotype, step_num, replicate)
 
+    def output_epidemiology_timelines(self, step=1000, output_file=False, replicate=0):
+        """Compartment counts of every deme over `step` grid intervals (reference src/_interface.py:553-566)."""
+        return self.simulation.output_epidemiology_timelines(step, output_file, replicate)
+
     def epidemic_curves(self, step_num, rep_first=0, rep_count=None):
         """Every compartment of a range of replicates on the reference's time grid, one device pass over the logs."""
         return self.simulation.epidemic_curves(step_num, rep_first, rep_count)

@@ -216,3 +216,77 @@ def read_matrix(fn):
     """*.mg / *.st -> list of rows of floats (one header line)."""
     _, body = _rows(fn, 1)
     return [[float(v) for v in row] for row in body]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# output_epidemiology_timelines (reference src/_BirthDeath.pyx:1765-1847): compartment counts of every deme at the
+# grid times i*currentTime/step_num, as a dict or as logs/PID<deme>.log files.  Reference behaviour kept as is:
+# the start state is "everybody in group 0 of its deme, one case of haplotype 0 in deme 0" (:1768-1778) whatever
+# the configured state was; MULTITYPE rows change nothing (`#TODO` at :1822); a grid point is written after the
+# first row whose time is >= that point, at most one point per row (:1823).  Vectorised: the reference walks the
+# log in a Python loop.
+
+def epidemiology_timelines(chain, sizes, K, S, H, current_time, step_num):
+    """(times[n_pts], sus[n_pts][K][S], inf[n_pts][K][H]) from a 6 x N chain in export_chain_events layout."""
+    t = np.asarray(chain[0], dtype=np.float64)
+    ty, hap, pop, nhap, npop = (np.asarray(chain[k]).astype(np.int64) for k in range(1, 6))
+    n = t.shape[0]
+    tp = [i * current_time / step_num for i in range(step_num + 1)]
+    # row after which each grid point is written
+    rows, j_prev = [], -1
+    for k in range(step_num + 1):
+        j = max(j_prev + 1, int(np.searchsorted(t, tp[k], side="left")))
+        if j >= n:
+            break
+        rows.append(j)
+        j_prev = j
+    sus0 = np.zeros((K, S), np.int64)
+    sus0[:, 0] = np.asarray(sizes, np.int64)
+    inf0 = np.zeros((K, H), np.int64)
+    inf0[0, 0] += 1
+    sus0[0, 0] -= 1
+    n_pts = len(rows)
+    if n_pts == 0:
+        return [], np.zeros((0, K, S), np.int64), np.zeros((0, K, H), np.int64)
+    seg = np.searchsorted(np.asarray(rows), np.arange(n), side="left")     # grid segment each row falls into
+    live = seg < n_pts                                                      # rows after the last written point
+    d_inf = np.zeros((n_pts, K, H), np.int64)
+    d_sus = np.zeros((n_pts, K, S), np.int64)
+
+    def add(arr, mask, p, c, v):
+        m = mask & live
+        np.add.at(arr, (seg[m], p[m], c[m]), v)
+
+    b, dth, mut, sch, mig = ty == 0, (ty == 1) | (ty == 2), ty == 3, ty == 4, ty == 5
+    add(d_inf, b, pop, hap, 1);      add(d_sus, b, pop, nhap, -1)
+    add(d_inf, dth, pop, hap, -1);   add(d_sus, dth, pop, nhap, 1)
+    add(d_inf, mut, pop, hap, -1);   add(d_inf, mut, pop, nhap, 1)
+    add(d_sus, sch, pop, hap, -1);   add(d_sus, sch, pop, nhap, 1)
+    add(d_sus, mig, npop, nhap, -1); add(d_inf, mig, npop, hap, 1)
+    return [tp[k] for k in range(n_pts)], sus0 + np.cumsum(d_sus, axis=0), inf0 + np.cumsum(d_inf, axis=0)
+
+
+def timelines_as_dict(times, sus, inf):
+    """The reference's return value: {"time": [...], "P<i>": {"S<j>": [...], "H<j>": [...]}}."""
+    K, S, H = sus.shape[1], sus.shape[2], inf.shape[2]
+    log = {"time": list(times)}
+    for i in range(K):
+        log["P" + str(i)] = {}
+        for j in range(S):
+            log["P" + str(i)]["S" + str(j)] = list(sus[:, i, j])
+        for j in range(H):
+            log["P" + str(i)]["H" + str(j)] = list(inf[:, i, j])
+    return log
+
+
+def write_timelines(times, sus, inf, directory="logs"):
+    """logs/PID<i>.log in the reference's layout (:1779-1790, 1824-1832)."""
+    import os
+    if not os.path.isdir(directory):
+        os.mkdir(directory)
+    K, S, H = sus.shape[1], sus.shape[2], inf.shape[2]
+    for i in range(K):
+        with open(os.path.join(directory, "PID" + str(i) + ".log"), "w") as f:
+            f.write("time" + "".join(" S" + str(j) for j in range(S)) + "".join(" H" + str(j) for j in range(H)) + "\n")
+            for k in range(len(times)):
+                f.write(str(times[k]) + " " + "".join(str(v) + " " for v in sus[k, i]) + "".join(str(v) + " " for v in inf[k, i]) + "\n")
