@@ -186,3 +186,27 @@ def test_tree_statistics_distribution_matches_oracle(name):
         ora["root_time"].append(times.min())
     bad = _ks_all(dev, ora, keys)
     assert not bad, bad
+
+
+def test_chain_export_import_roundtrip(tmp_path):
+    """export_chain_events -> set_chain_events on a fresh engine -> genealogy over the imported log with the same
+    uniform stream gives the same tree; output_epidemiology_timelines of the exported log equals
+    the literal restatement of the reference loop."""
+    from test_gpu_tau import make_engine
+    a = make_engine("s9", 2020)
+    a.SimulatePopulation(20000, 20000, -1, 200)
+    fn = str(tmp_path / "chain")
+    a.export_chain_events(fn)
+    chain = a.get_chain_events(0)
+    log = a.output_epidemiology_timelines(15, False)
+    want = O.ref_epidemiology_timelines(chain, list(a.sizes), a.popNum, a.susNum, a.hapNum, float(a.counters()["time"][0]), 15)
+    assert log["time"] == want[0] and log["P0"]["H0"] == list(want[2][:, 0, 0]) and log["P2"]["S1"] == list(want[1][:, 2, 1])
+    u = O.OracleRng(7, 0).doubles(4 * chain.shape[1] + 16)
+    a.GetGenealogy(None, uniform_stream=[u])
+    tree_a, times_a = a.get_tree(0)
+    b = make_engine("s9", 2020)
+    b.set_chain_events(fn)
+    assert np.array_equal(b.get_chain_events(0), chain)
+    b.GetGenealogy(None, uniform_stream=[u])
+    tree_b, times_b = b.get_tree(0)
+    assert len(tree_a) > 100 and np.array_equal(tree_a, tree_b) and np.array_equal(times_a, times_b)

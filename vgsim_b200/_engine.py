@@ -676,6 +676,33 @@ class BirthDeathModel:
     def get_multievents(self, replicate=0):
         return self._handle.get_multievents(replicate)
 
+    def set_chain_events(self, name_file, replicate=0):
+        """Working counterpart of the reference's set_chain_events (src/_BirthDeath.pyx:1705-1719; upstream it assigns
+        to attributes the cdef class does not have).  Loads ``<name_file>.npy`` in the export_chain_events layout
+        (direct-method rows; the zero rows the reference saves past its write pointer are dropped), installs it as the
+        event log of `replicate` and sets the infectious counts to the state at the end of that log, so that
+        genealogy() can replay it.  Epidemic curves need the initial snapshot of a simulate() call and are not defined
+        for an imported log."""
+        tokens = np.load(name_file + '.npy')
+        if tokens.ndim != 2 or tokens.shape[0] != 6:
+            raise ValueError('Incorrect chain of events: a 6 x N array is expected.')
+        n = int(np.count_nonzero(tokens[0]))            # every real row has time > 0
+        chain = np.ascontiguousarray(tokens[:, :n], dtype=np.float64)
+        ty, hap, pop, nhap, npop = (chain[k].astype(np.int64) for k in range(1, 6))
+        I = self._infectious.astype(np.int64).copy()
+        if I.sum() == 0:                                # FirstInfection (:234-242)
+            I[0, 0] += 1
+        for mask, p, h, v in ((ty == 0, pop, hap, 1), ((ty == 1) | (ty == 2), pop, hap, -1), (ty == 3, pop, hap, -1),
+                              (ty == 3, pop, nhap, 1), (ty == 5, npop, hap, 1)):
+            np.add.at(I, (p[mask], h[mask]), v)
+        if I.min() < 0:
+            raise ValueError('Incorrect chain of events: it does not replay from the configured initial state.')
+        h = self._sync_params()
+        h.set_event_log(replicate, chain, I)
+        self.first_simulation = True
+        self._genealogy_done = False
+        self._refresh_host_state()
+
     def _require_tree(self):
         if not self._genealogy_done:
             print('Genealogy was not simulated. Use VGsim.genealogy() method to simulate it.')

@@ -269,6 +269,10 @@ class Simulator:
     def get_chain_events(self, replicate=0):
         return self.simulation.get_chain_events(replicate)
 
+    def set_chain_events(self, file_name="chain_events", replicate=0):
+        """Imports an event chain saved by export_chain_events (reference src/_interface.py: set_chain_events)."""
+        self.simulation.set_chain_events(file_name, replicate)
+
     def get_data_susceptible(self, population, susceptibility_type, step_num, replicate=0):
         """susceptible, time_points, lockdowns (reference src/_interface.py:599-615)."""
         return self.simulation.get_data_susceptible(population, susceptibility_type, step_num, replicate)
