@@ -109,3 +109,29 @@ def test_cli_end_to_end(tmp_path):
     chain = np.load(out + ".npy")
     # a binary tree over every sampled individual: one '(' per internal node
     assert chain.shape[0] == 6 and (chain[1] == 2).sum() == nwk.count("(") + 1
+
+
+def test_export_settings_round_trip(tmp_path, capsys):
+    """export_settings -> the readers -> cli.configure gives back the same model (host side only)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from scenarios import SCENARIOS
+    from vgsim_b200 import cli
+    from vgsim_b200._engine import BirthDeathModel as Eng
+    for name in ("example", "s9", "s1"):
+        (U, K, S), setup = SCENARIOS[name]
+        e = Eng(U, K, S, 3, False, False, int(1e6), 0.0)
+        setup(e)
+        d = str(tmp_path / ("model_" + name))
+        e.export_settings(d)
+        base = os.path.join(d, "model_" + name)
+        assert "Command line command: " + base + ".rt -pm " in capsys.readouterr().out
+        args = cli.build_parser().parse_args(["-rt", base + ".rt", "-pm", base + ".pp", base + ".mg", "-su", base + ".su",
+                                              "-st", base + ".st", "-seed", "3"])
+        sim, _ = cli.configure(args)
+        a, b = e.param_arrays(), sim.simulation.param_arrays()
+        for k in a:
+            if k in ("cd", "cdBefore"):
+                continue
+            np.testing.assert_allclose(np.asarray(b[k], float), np.asarray(a[k], float), rtol=1e-15, atol=0, err_msg=name + ":" + k)
+        np.testing.assert_allclose(np.asarray(b["cd"], float), np.asarray(a["cd"], float), rtol=1e-15)

@@ -676,6 +676,18 @@ class BirthDeathModel:
     def get_multievents(self, replicate=0):
         return self._handle.get_multievents(replicate)
 
+    def export_settings(self, file_template):
+        """Writes the model as the command-line tool's parameter files <file_template>/<file_template>.{rt,pp,mg,su,st}
+        (reference src/_BirthDeath.pyx:1853-1907; same text, written without changing the working directory) and
+        prints the matching command line.  `vgsim_b200.io.read_*` / `python -m vgsim_b200.cli` read them back."""
+        import os
+        from . import io as _io
+        if not os.path.isdir(file_template):
+            os.mkdir(file_template)
+        base = os.path.join(file_template, os.path.basename(os.path.normpath(file_template)))
+        _io.write_settings(base, [self.calculate_string_from_haplotype(h) for h in range(self.hapNum)], self.param_arrays())
+        print('Command line command: ' + base + '.rt -pm ' + base + '.pp ' + base + '.mg -su ' + base + '.su -st ' + base + '.st ')
+
     def set_chain_events(self, name_file, replicate=0):
         """Working counterpart of the reference's set_chain_events (src/_BirthDeath.pyx:1705-1719; upstream it assigns
         to attributes the cdef class does not have).  Loads ``<name_file>.npy`` in the export_chain_events layout

@@ -269,6 +269,10 @@ class Simulator:
     def get_chain_events(self, replicate=0):
         return self.simulation.get_chain_events(replicate)
 
+    def export_settings(self, file_template="parameters"):
+        """Exports the model as text parameter files (reference src/_interface.py:578-585)."""
+        self.simulation.export_settings(file_template)
+
     def set_chain_events(self, file_name="chain_events", replicate=0):
         """Imports an event chain saved by export_chain_events (reference src/_interface.py: set_chain_events)."""
         self.simulation.set_chain_events(file_name, replicate)
@@ -315,4 +319,4 @@ class Simulator:
 
     add_plot_infectious = add_plot_susceptible = add_legend = add_title = plot = _out_of_scope
     print_basic_parameters = print_populations = print_immunity_model = print_all = _out_of_scope
-    export_ts = export_settings = export_state = set_settings = set_state = debug = _out_of_scope
+    export_ts = export_state = set_settings = set_state = debug = _out_of_scope

@@ -290,3 +290,35 @@ def write_timelines(times, sus, inf, directory="logs"):
             f.write("time" + "".join(" S" + str(j) for j in range(S)) + "".join(" H" + str(j) for j in range(H)) + "\n")
             for k in range(len(times)):
                 f.write(str(times[k]) + " " + "".join(str(v) + " " for v in sus[k, i]) + "".join(str(v) + " " for v in inf[k, i]) + "\n")
+
+
+def write_settings(base, hap_names, a):
+    """<base>.rt/.pp/.mg/.su/.st from the engine's parameter arrays (`BirthDeathModel.param_arrays()`), in the layout of
+    the reference's export_settings (src/_BirthDeath.pyx:1861-1905): numbers are written with str(), every mutation
+    field is `rate,w1,w2,w3` (the weights of the three OTHER alleles), matrix rows end with a space."""
+    H, U = a["mRate"].shape
+    K, S = a["sizes"].shape[0], a["sigma"].shape[1]
+    with open(base + ".rt", "w") as f:
+        f.write("#Rates_format_version 0.0.1\nH B D S" + "".join(" M" + str(u) for u in range(U)) + "\n")
+        for h in range(H):
+            f.write(hap_names[h] + " " + str(a["b"][h]) + " " + str(a["d"][h]) + " " + str(a["s"][h]) + " ")
+            for u in range(U):
+                f.write(str(a["mRate"][h, u]) + "," + ",".join(str(a["hapMutType"][h, u, k]) for k in range(3)) + " ")
+            f.write("\n")
+    with open(base + ".pp", "w") as f:
+        f.write("#Population_format_version 0.0.1\nid size contactDensity conDenAfterLD startLD endLD samplingMulriplier\n")
+        for p in range(K):
+            f.write(str(p) + " " + str(a["sizes"][p]) + " " + str(a["cd"][p]) + " " + str(a["cdAfter"][p]) + "," +
+                    str(a["startLD"][p]) + "," + str(a["endLD"][p]) + " " + str(a["sm"][p]) + "\n")
+    with open(base + ".mg", "w") as f:
+        f.write("#Migration_format_version 0.0.1\n")
+        for p in range(K):
+            f.write("".join(str(a["m"][p, q]) + " " for q in range(K)) + "\n")
+    with open(base + ".su", "w") as f:
+        f.write("#Susceptibility_format_version 0.0.1\nH T" + "".join(" S" + str(g) for g in range(S)) + "\n")
+        for h in range(H):
+            f.write(hap_names[h] + " " + str(a["suscType"][h]) + "".join(" " + str(a["sigma"][h, g]) for g in range(S)) + "\n")
+    with open(base + ".st", "w") as f:
+        f.write("#Susceptibility_format_version 0.0.1\n")
+        for g in range(S):
+            f.write("".join(str(a["T"][g, g2]) + " " for g2 in range(S)) + "\n")
