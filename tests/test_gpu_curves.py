@@ -118,7 +118,7 @@ def test_curve_and_sample_time_distributions_match_oracle(name, t_end):
     and the mean / first sampling time."""
     from scipy import stats
     from test_gpu_tau import _ks_all
-    R, RO, T = 1000, 400, 64
+    R, RO, T = 1000, 150, 64
     e = make_engine(name, 9100, replicates=R)
     e.SimulatePopulation(10 ** 7, 10 ** 9, t_end, 200)
     c = e.epidemic_curves(T, want=("infectious", "sampled"))
