@@ -1275,7 +1275,8 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
     // Few replicates (all of them resident at once as 256-thread teams): the GPU is latency- not throughput-bound, and a
     // team walks a leap sooner than a single warp does -- 8.1x at the world shape (K = 100: the K x K x H force-of-
     // infection sums), 32 replicates x 1,200 leaps: 607 ms vs 4,948 ms (profiles/r1_k_*), same log bit for bit.
-    if (!team && !force_warp && st.R <= num_sms * teams) team = true;
+    const bool team_fits = stride + TAU_CTA_TAIL <= (size_t)227 * 1024;  // else only the warp kernel's leaner slice may fit
+    if (!team && !force_warp && team_fits && st.R <= num_sms * teams) team = true;
     if (!team) {
         int max_warps = 16;
         if (const char *e = getenv("VGSIM_TAU_WARPS")) max_warps = atoi(e);
