@@ -739,6 +739,22 @@ class BirthDeathModel:
         self._require_tree()
         return self._handle.get_migrations(replicate)
 
+    def print_mutations(self, replicate=0):
+        """Reference src/_BirthDeath.pyx:1176-1179: one tuple (nodeId, DS, AS, site, time) per line."""
+        self._require_tree()
+        node, AS, DS, site, t = self._handle.get_mutations(replicate)
+        print('nodeId\tDS\tAS\tsite\ttime')
+        for i in range(len(node)):
+            print((int(node[i]), int(DS[i]), int(AS[i]), int(site[i]), float(t[i])))
+
+    def print_migrations(self, replicate=0):
+        """Reference src/_BirthDeath.pyx:1181-1184: one tuple (nodeId, time, oldPop, newPop) per line."""
+        self._require_tree()
+        node, t, oldp, newp = self._handle.get_migrations(replicate)
+        print('nodeId\ttime\tsource population\ttarget population')
+        for i in range(len(node)):
+            print((int(node[i]), float(t[i]), int(oldp[i]), int(newp[i])))
+
     def output_tree_mutations(self, replicate=0):
         self._require_tree()
         tree, pop, times = self._handle.get_tree(replicate)

@@ -302,6 +302,12 @@ class Simulator:
     def get_proportion(self):
         return self.simulation.get_proportion()
 
+    def print_mutations(self, replicate=0):
+        self.simulation.print_mutations(replicate)
+
+    def print_migrations(self, replicate=0):
+        self.simulation.print_migrations(replicate)
+
     def print_counters(self):
         self.simulation.PrintCounters()
 
@@ -320,3 +326,5 @@ class Simulator:
     add_plot_infectious = add_plot_susceptible = add_legend = add_title = plot = _out_of_scope
     print_basic_parameters = print_populations = print_immunity_model = print_all = _out_of_scope
     export_ts = export_state = set_settings = set_state = debug = _out_of_scope
+    # print_chain / print_tree / print_recomb delegate to engine methods that do not exist upstream either
+    plot_infectious = print_chain = print_tree = print_recomb = _out_of_scope
