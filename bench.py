@@ -14,10 +14,17 @@ so no L2 flush is needed between steps).
   value  : events/s with the batch's input state already resident in HBM (device->device restore).
   e2e    : the same step through the C ABI with HOST buffers: seeds + states are copied host->device
            from pinned memory and counters + final states are read back device->host every step.
+           Two handles alternate (double buffering): the copies of one overlap the kernel of the other.
            The event log stays in HBM, as it stays inside the engine object in the reference; it is
            what vgsim_genealogy consumes.
   roofline: dominant kernel = tau_warp_kernel; achieved = leaps * (4P+16) B / its CUDA-event duration
            (events recorded inside vgsim_simulate_tau on the launching stream).
+  windows: the same step measured from snapshots of the SAME trajectories further into the epidemic
+           (SURVEY 8(d) config 3 times tau from t=60 to t=150): the replicates are advanced by tau-leaping
+           in leap blocks (vgsim_recycle_log between blocks) to t=90 and t=120 and every window reports
+           leaps/s, events per leap, active cells and its own roofline fraction; `value` stays the t=60
+           window, `roofline_min_frac` is the smallest fraction over the windows.
+  direct : phase A's device direct method (16 B of log per event) with its own roofline and CPU baseline.
   cpu_baseline / --impl reference: the UNMODIFIED reference engine (oracle/_ref, Cython build of
            /root/reference made by oracle/build_ref.py) on the host cores, one process per core,
            each process running whole replicates of the same workload (direct warm-up to t = 60
@@ -43,8 +50,7 @@ T_WARM = 60.0
 SEED0 = 1000
 WORKLOAD = "T3 tau-leap: 3 sites (64 haplotypes) x 10 demes x 3 susceptibility groups, 1e6/deme"
 CPU_SAMPLE_TIMEOUT = 180.0   # wall seconds allowed for one bounded CPU sample (all workers)
-# the team kernel (parity tap) is selected with VGSIM_TAU_KERNEL=team; the default is the warp-per-replicate kernel
-KERNEL = "tau_kernel" if os.environ.get("VGSIM_TAU_KERNEL", "").startswith("t") else "tau_warp_kernel"
+KERNEL = "tau_warp_kernel"   # 4,096 replicates per GPU run on the warp-per-replicate kernel
 EVENT_KEYS = ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus")
 
 
@@ -57,6 +63,9 @@ def parse_args():
     ap.add_argument("--replicates", type=int, default=4096, help="replicates per GPU")
     ap.add_argument("--leaps", type=int, default=32, help="tau leaps per replicate per step")
     ap.add_argument("--scenario", default="t3")
+    ap.add_argument("--profile-window", type=float, default=None,
+                    help="cudaProfilerStart/Stop around the timed steps of this window (ncu --profile-from-start off)")
+    ap.add_argument("--windows", default="60,90,120", help="epidemic times of the measured windows (first = the metric's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-curves", action="store_true", help="skip the (untimed) epidemic-curves pass reported beside the metric")
     ap.add_argument("--phases", action="store_true", help="add the tau kernel's per-phase critical-path cycles (timing tap)")
@@ -91,6 +100,8 @@ def cpu_worker(seed, reps, leaps, scenario):
     t_tau = 0.0
     events = 0
     n_leaps = 0
+    t_direct = 0.0
+    n_direct_ev = 0
     for r in range(reps):
         if use_ref:
             def fresh():
@@ -108,7 +119,10 @@ def cpu_worker(seed, reps, leaps, scenario):
                     n_direct = int(np.count_nonzero(np.load(os.path.join(d, "c.npy"))[0]))
                 del m
                 m = fresh()
+                t0 = time.perf_counter()
                 m.SimulatePopulation(n_direct, 10 ** 9, T_WARM, 200)
+                t_direct += time.perf_counter() - t0
+                n_direct_ev += n_direct
                 c0 = _ref_counters(m)
                 t0 = time.perf_counter()
                 m.SimulatePopulation_tau(leaps, 10 ** 9, -1, 1)
@@ -120,18 +134,41 @@ def cpu_worker(seed, reps, leaps, scenario):
             e = Eng(U, K, S, seed + r, False, False, int(1e6), 0.0)
             setup(e)
             om = O.OracleModel.from_engine(e)
+            t0 = time.perf_counter()
             om.simulate(2000000, sample_size=10 ** 9, epidemic_time=T_WARM)
+            t_direct += time.perf_counter() - t0
             c0 = om.counters()
+            n_direct_ev += c0["events"]
             t0 = time.perf_counter()
             om.simulate(leaps, sample_size=10 ** 9, epidemic_time=-1, method="tau", attempts=1)
             t_tau += time.perf_counter() - t0
             c1 = om.counters()
             events += sum(c1[k] - c0[k] for k in EVENT_KEYS)
             n_leaps += c1["events"] - c0["events"]
+    # what the reference's per-call log allocation costs (multievents.CreateEvents(iterations * propNum) inside every
+    # SimulatePopulation_tau call, src/_BirthDeath.pyx:2305: 7 arrays of leaps*P 8-byte zeros, first-touch page faults):
+    # measured on equal arrays so that the rate can also be quoted without it.  The GPU arm reuses its log capacity.
+    t_alloc = 0.0
+    if use_ref:
+        t0 = time.perf_counter()
+        for _ in range(3):
+            z = [np.zeros(leaps * P, dtype=np.int64) for _ in range(7)]
+            for a_ in z:
+                a_[::512] = 1
+            del z
+        t_alloc = (time.perf_counter() - t0) / 3 * reps
     print(json.dumps({"events": int(events), "leaps": int(n_leaps), "seconds": t_tau, "P": P,
-                      "kind": "reference" if use_ref else "port"}))
+                      "kind": "reference" if use_ref else "port", "direct_events": int(n_direct_ev),
+                      "direct_seconds": t_direct, "alloc_seconds": t_alloc}))
     sys.stdout.flush()
-    os._exit(0)  # the reference's destructor can abort on exit (free(): invalid pointer); results are out
+    # the reference's destructor can abort at interpreter teardown (free(): invalid pointer): run the registered exit
+    # hooks (the driver's record of loaded .so files among them) explicitly, then leave without teardown
+    try:
+        import atexit
+        atexit._run_exitfuncs()
+    except Exception:
+        pass
+    os._exit(0)
 
 
 def run_cpu_sample(scenario, leaps, reps_per_worker, seed_base):
@@ -162,8 +199,11 @@ def run_cpu_sample(scenario, leaps, reps_per_worker, seed_base):
     # workers run concurrently; aggregate rate = sum of per-worker rates over their timed (tau) sections
     rate = sum(o["events"] / o["seconds"] for o in outs if o["seconds"] > 0)
     lrate = sum(o["leaps"] / o["seconds"] for o in outs if o["seconds"] > 0)
+    drate = sum(o["direct_events"] / o["direct_seconds"] for o in outs if o.get("direct_seconds", 0) > 0)
+    rate_xa = sum(o["events"] / max(o["seconds"] - o.get("alloc_seconds", 0.0), 1e-9) for o in outs if o["seconds"] > 0)
     return dict(events_per_s=rate, leaps_per_s=lrate, events=ev, leaps=lp, cores=len(outs), wall=wall,
-                kind=outs[0]["kind"], P=outs[0]["P"], timed_seconds=max(o["seconds"] for o in outs))
+                kind=outs[0]["kind"], P=outs[0]["P"], timed_seconds=max(o["seconds"] for o in outs),
+                direct_events_per_s=drate, events_per_s_excl_alloc=rate_xa)
 
 
 def calibrate_cpu_reps(scenario, leaps, target_seconds):
@@ -199,7 +239,11 @@ def reference_arm(args, rank):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "scenario": args.scenario, "leaps_per_step": args.leaps, "channels_P": res["P"]},
         "cpu_baseline": {"value": value, "unit": "events/s", "cores": res["cores"], "kind": res["kind"], "sample": sample,
-                         "leaps_per_s": res["leaps_per_s"]},
+                         "leaps_per_s": res["leaps_per_s"],
+                         "note": "the timed call includes the reference's own per-call log allocation (CreateEvents, "
+                                 "src/_BirthDeath.pyx:2305); excluding an equal allocation measured beside it the rate "
+                                 "would be %.4g events/s" % res["events_per_s_excl_alloc"],
+                         "direct_events_per_s": res["direct_events_per_s"]},
         "e2e": {"value": value, "unit": "events/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -285,34 +329,63 @@ def gpu_arm(args, rank, world, local_rank):
     (U, K, S), setup = SCENARIOS[args.scenario]
     lo, hi = _shard.replicate_range(rank, world, world * R)   # weak scaling: R replicates per GPU
     seed_base = SEED0 + lo
-    eng = Eng(U, K, S, seed_base, False, False, int(1e6), 0.0, replicates=R, device=local_rank)
-    setup(eng)
-    h = eng._sync_params()
+    windows_t = [float(x) for x in args.windows.split(",") if x]
+
+    def make_handle():
+        eng = Eng(U, K, S, seed_base, False, False, int(1e6), 0.0, replicates=R, device=local_rank)
+        setup(eng)
+        h = eng._sync_params()
+        st = torch.cuda.Stream(device=dev)
+        h.set_stream(st.cuda_stream)
+        return eng, h, st
+
+    eng, h, stream = make_handle()
     P, H = h.P, h.H
-    stream = torch.cuda.Stream(device=dev)
-    h.set_stream(stream.cuda_stream)
     if args.phases:
         h.set_tau_variant(2)
+    b_leap = 4 * P + 16
+    pSx, pI = h.state_dev_ptrs()
+    live_Sx = torch.as_tensor(_DevArray(pSx, (R, K, S), "<i8"), device=dev)
+    live_I = torch.as_tensor(_DevArray(pI, (R, K, H), "<i8"), device=dev)
 
-    # ---- Phase A (untimed): device direct method to T_WARM for every replicate; snapshot the states
-    h.simulate_direct(250000, -1, T_WARM, 200)
+    # ---- Phase A (untimed for the metric; reported as the `direct` block): device direct method to T_WARM
+    h.simulate_direct(250000, -1, windows_t[0], 200)
     direct_ms = h.last_kernel_ms()
     cA = h.get_counters()
-    Sx0, I0 = h.get_state()
+
+    def snapshot():
+        with torch.cuda.stream(stream):
+            sx, ii = live_Sx.clone(), live_I.clone()
+        stream.synchronize()
+        return sx, ii
+
+    # ---- the same trajectories further into the epidemic: tau-leaping in leap blocks up to each window's time
+    snaps = []
+    t_now = windows_t[0]
+    for wt in windows_t:
+        blocks = 0
+        if wt > t_now:
+            for blocks in range(1, 400):
+                h.recycle_log()
+                h.simulate_tau(L, -1, wt, 1, sync=False)
+                c = h.get_counters()
+                if bool(np.all((c["time"] >= np.float32(wt)) | (c["globalInfectious"] == 0))):
+                    break
+            t_now = wt
+        c = h.get_counters()
+        sx, ii = snapshot()
+        iin = ii.cpu().numpy()
+        snaps.append({"t": wt, "Sx": sx, "I": ii, "mean_time": float(np.mean(c["time"])),
+                      "mean_infectious": float(iin.sum() / R), "mean_active_cells": float((iin != 0).sum() / R),
+                      "extinct": int((iin.reshape(R, -1).sum(axis=1) == 0).sum()), "advance_blocks": blocks})
+    Sx0, I0 = snaps[0]["Sx"].cpu().numpy(), snaps[0]["I"].cpu().numpy()
     hSx = torch.from_numpy(Sx0).pin_memory()
     hI = torch.from_numpy(I0).pin_memory()
-    with torch.cuda.stream(stream):
-        dSx = hSx.to(dev, non_blocking=True)
-        dI = hI.to(dev, non_blocking=True)
-    stream.synchronize()
-    out_Sx = torch.empty_like(hSx).pin_memory()
-    out_I = torch.empty_like(hI).pin_memory()
-    out_cnt = torch.empty((R, _capi.NCOUNTERS), dtype=torch.int64).pin_memory()
-    out_time = torch.empty(R, dtype=torch.float64).pin_memory()
+
     cptr, _tptr = h.counters_dev_ptrs()
     dev_counters = torch.as_tensor(_DevArray(cptr, (R, _capi.NCOUNTERS), "<i8"), device=dev)
     n_total = args.warmup + args.steps
-    acc = torch.zeros((2 * n_total + 2, R, _capi.NCOUNTERS), dtype=torch.int64, device=dev)
+    acc = torch.zeros((n_total, R, _capi.NCOUNTERS), dtype=torch.int64, device=dev)
     seeds_pinned = torch.empty(R, dtype=torch.int64).pin_memory()
 
     def seeds_for(step):
@@ -321,99 +394,136 @@ def gpu_arm(args, rank, world, local_rank):
         seeds_pinned.numpy()[:] = s.view(np.int64)
         return seeds_pinned.numpy().view(np.uint64)
 
-    kernel_ms = []
-
-    def step_resident(i):
-        h.reset()
-        h.set_seeds(seeds_for(i))
-        h.set_state_dev(dSx.data_ptr(), dI.data_ptr())
-        h.simulate_tau(L, -1, -1.0, 1, sync=False)
-        with torch.cuda.stream(stream):
-            acc[i].copy_(dev_counters, non_blocking=True)
-
-    def step_e2e(i):
-        h.reset()
-        h.set_seeds(seeds_for(i))                                    # H2D  R*8
-        h.set_state(hSx.numpy(), hI.numpy())                          # H2D  R*K*(S+H)*8 from pinned memory
-        h.simulate_tau(L, -1, -1.0, 1, sync=False)
-        h.get_counters(out=(out_cnt.numpy(), out_time.numpy()))       # D2H  R*(12+1)*8
-        h.get_state(out=(out_Sx.numpy(), out_I.numpy()))              # D2H  R*K*(S+H)*8
-        return int(out_cnt[:, :6].sum())
-
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident timing
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    launches0 = h.launch_count()
-    if args.phases:
-        h.tau_phase_cycles(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.warmup, n_total):
-        step_resident(i)
-        kernel_ms.append(h.last_kernel_ms())
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = h.launch_count() - launches0
-    phase_cycles = h.tau_phase_cycles(reset=True) if args.phases else None
-    err = h.synchronize(strict=False)
-    cnt = acc[args.warmup:n_total].cpu().numpy()
-    events = int(cnt[:, :, :6].sum())
-    leaps = int(cnt[:, :, 10].sum())
+    def step_resident(i, snap, slot):
+        h.reset()
+        h.set_seeds(seeds_for(i))
+        h.set_state_dev(snap["Sx"].data_ptr(), snap["I"].data_ptr())
+        h.simulate_tau(L, -1, -1.0, 1, sync=False)
+        with torch.cuda.stream(stream):
+            acc[slot].copy_(dev_counters, non_blocking=True)
 
-    # ---- end-to-end timing (host buffers through the C ABI)
-    for i in range(args.warmup):
-        step_e2e(n_total + i)
-    barrier()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0 = time.perf_counter()
-    f0.record(stream)
-    ev_e2e = 0
-    for i in range(args.steps):
-        ev_e2e += step_e2e(2 * n_total + i)
-    f1.record(stream)
-    barrier()
-    # the host-blocking copies make the host clock the honest one here: take the larger of the two
-    ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - w0))
-    clk = clocks.stop() if rank == 0 else None
+    def measure_window(snap, seed_off, clocks=None):
+        """W warm-up + K timed device-resident steps from one snapshot; CUDA events on the launching stream."""
+        kernel_ms = []
+        for i in range(args.warmup):
+            step_resident(seed_off + i, snap, i)
+        barrier()
+        if clocks is not None:
+            clocks.start()
+        launches0 = h.launch_count()
+        if args.phases:
+            h.tau_phase_cycles(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.warmup, n_total):
+            step_resident(seed_off + i, snap, i)
+            kernel_ms.append(h.last_kernel_ms())
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        cnt = acc[args.warmup:n_total].cpu().numpy()
+        return {"ms": ms, "events": int(cnt[:, :, :6].sum()), "leaps": int(cnt[:, :, 10].sum()),
+                "launches": h.launch_count() - launches0, "kernel_ms_sum": sum(kernel_ms),
+                "phase_cycles": h.tau_phase_cycles(reset=True) if args.phases else None}
+
+    # ---- device-resident timing: the metric's window first (clocks sampled there), then the later windows
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    res_w = []
+    for wi, snap in enumerate(snaps):
+        prof_on = args.profile_window is not None and abs(args.profile_window - snap["t"]) < 1e-9
+        if prof_on:
+            torch.cuda.synchronize(dev)
+            torch.cuda.cudart().cudaProfilerStart()
+        res_w.append(measure_window(snap, wi * 10 * n_total, clocks if wi == 0 else None))
+        if prof_on:
+            torch.cuda.cudart().cudaProfilerStop()
+    m0 = res_w[0]
+    ms, events, leaps, launches, phase_cycles = m0["ms"], m0["events"], m0["leaps"], m0["launches"], m0["phase_cycles"]
+    err = h.synchronize(strict=False)
 
     # ---- (reported beside the metric, outside the timed regions) epidemic curves of every replicate over the log the
     #      last step left in HBM: one read of R*L dense rows (B_leap each) by curves_kernel
     curves = None
     if rank == 0 and not args.no_curves:
         try:
+            step_resident(5 * 10 * n_total, snaps[0], 0)
             t_c = []
             for _ in range(3):
                 cv = h.epidemic_curves(8, want=("infectious",))
                 t_c.append(h.last_kernel_ms())
             Sx_l, I_l = h.get_state()
             assert np.array_equal(cv["infectious"][:, -1], I_l), "curves: last grid point != final state"
-            log_bytes = float(R) * L * (4 * P + 16)
+            log_bytes = float(R) * L * b_leap
             curves = {"kernel": "curves_kernel", "kernel_ms": min(t_c), "log_bytes_read": log_bytes,
                       "achieved_GBps": log_bytes / (min(t_c) * 1e-3) / 1e9, "grid_points": 9,
                       "check": "last grid point equals the final state of all %d replicates" % R}
         except Exception as ex:
             curves = {"error": str(ex)}
 
+    # ---- end-to-end timing (host buffers through the C ABI).  Two handles alternate: while one runs its kernel the
+    #      other's results are read back and its next inputs uploaded (each handle blocks only on its own stream).
+    eng2, h2, stream2 = make_handle()
+    hs = [h, h2]
+    outs = []
+    for _ in hs:
+        outs.append({"Sx": torch.empty_like(hSx).pin_memory(), "I": torch.empty_like(hI).pin_memory(),
+                     "cnt": torch.empty((R, _capi.NCOUNTERS), dtype=torch.int64).pin_memory(),
+                     "time": torch.empty(R, dtype=torch.float64).pin_memory(), "pending": False})
+
+    def harvest(k):
+        o = outs[k]
+        if not o["pending"]:
+            return 0
+        hs[k].get_counters(out=(o["cnt"].numpy(), o["time"].numpy()))      # D2H  R*(12+1)*8
+        hs[k].get_state(out=(o["Sx"].numpy(), o["I"].numpy()))            # D2H  R*K*(S+H)*8
+        o["pending"] = False
+        return int(o["cnt"][:, :6].sum())
+
+    def step_e2e(i):
+        k = i & 1
+        got = harvest(k)                                                   # results of step i-2
+        hs[k].reset()
+        hs[k].set_seeds(seeds_for(i))                                      # H2D  R*8
+        hs[k].set_state(hSx.numpy(), hI.numpy())                           # H2D  R*K*(S+H)*8 from pinned memory
+        hs[k].simulate_tau(L, -1, -1.0, 1, sync=False)
+        outs[k]["pending"] = True
+        return got
+
+    for i in range(max(args.warmup, 2)):
+        step_e2e(7 * 10 * n_total + i)
+    harvest(0), harvest(1)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    f0.record(stream)
+    ev_e2e = 0
+    for i in range(args.steps):
+        ev_e2e += step_e2e(8 * 10 * n_total + i)
+    ev_e2e += harvest(0) + harvest(1)
+    f1.record(stream)
+    barrier()
+    # the host-blocking copies make the host clock the honest one here: take the larger of the two
+    ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - w0))
+    clk = clocks.stop() if rank == 0 else None
+    h2.close()
+    del eng2
+
     # ---- final all-gather of per-replicate summaries (the only collective of the path)
     sptr = h.summaries_dev_ptr()
     summ = torch.as_tensor(_DevArray(sptr, (R, _capi.NSUMMARY), "<f8"), device=dev)
     stream.synchronize()
+    wstats = [[w["ms"], float(w["events"]), float(w["leaps"]), w["kernel_ms_sum"]] for w in res_w]
     if world > 1:
         gathered = _shard.gather_summaries(summ.clone(), world)
         assert gathered.shape == (world * R, _capi.NSUMMARY)
-        t = torch.tensor([ms, ms_e2e, float(events), float(leaps), float(ev_e2e), float(launches), float(err),
-                          sum(kernel_ms)], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, ms_e2e, float(events), float(leaps), float(ev_e2e), float(launches), float(err)] +
+                         [x for w in wstats for x in w], dtype=torch.float64, device=dev)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
@@ -421,9 +531,9 @@ def gpu_arm(args, rank, world, local_rank):
         ms, ms_e2e = float(tmax[0]), float(tmax[1])
         events, leaps, ev_e2e, launches = int(tsum[2]), int(tsum[3]), int(tsum[4]), int(tsum[5])
         err = int(tmax[6])
-        kms_sum = float(tmax[7])
-    else:
-        kms_sum = sum(kernel_ms)
+        for wi in range(len(wstats)):   # times: max over ranks; events / leaps: sums
+            o = 7 + 4 * wi
+            wstats[wi] = [float(tmax[o]), float(tsum[o + 1]), float(tsum[o + 2]), float(tmax[o + 3])]
 
     if rank == 0:
         peaks = {}
@@ -433,33 +543,51 @@ def gpu_arm(args, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        b_leap = 4 * P + 16
-        leaps_per_launch_rank = leaps / max(world, 1) / args.steps
-        k_ms = kms_sum / args.steps
-        achieved = leaps_per_launch_rank * b_leap / (k_ms * 1e-3) / 1e9
+        wlines = []
+        for snap, (w_ms, w_ev, w_lp, w_kms) in zip(snaps, wstats):
+            k_ms = w_kms / args.steps
+            ach = (w_lp / max(world, 1) / args.steps) * b_leap / (k_ms * 1e-3) / 1e9
+            wlines.append({"t": snap["t"], "mean_time": snap["mean_time"], "mean_infectious": snap["mean_infectious"],
+                           "mean_active_cells": snap["mean_active_cells"], "extinct_replicates": snap["extinct"],
+                           "events_per_s": w_ev / (w_ms * 1e-3), "leaps_per_s": w_lp / (w_ms * 1e-3),
+                           "events_per_leap": w_ev / max(w_lp, 1.0), "ms_per_step": w_ms / args.steps, "kernel_ms": k_ms,
+                           "achieved_GBps": ach, "frac": ach / peak})
+        k_ms, achieved = wlines[0]["kernel_ms"], wlines[0]["achieved_GBps"]
         h2d = R * 8 + R * K * (S + H) * 8
         d2h = R * (_capi.NCOUNTERS + 1) * 8 + R * K * (S + H) * 8
+        n_direct = float(np.sum(cA["events"]))
         line = {
             "metric": "simulated events/sec (tau-leap, replicate-batched)",
             "value": events / (ms * 1e-3), "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "scenario": args.scenario, "replicates_per_gpu": R, "leaps_per_step": L,
-                       "channels_P": P, "phase_a": "device direct method to t=%g per replicate (untimed)" % T_WARM,
+                       "channels_P": P, "phase_a": "device direct method to t=%g per replicate (untimed)" % windows_t[0],
+                       "window": "t=%g (value); later windows of the same trajectories under `windows`" % windows_t[0],
                        "l2": "each step writes %.1f GB of event log per GPU (> 126 MB L2): no flush needed" % (R * L * b_leap / 1e9),
-                       "parallelism": "replicates sharded %dx%d, no data-path collective" % (world, R)},
+                       "parallelism": "replicates sharded %dx%d, no data-path collective" % (world, R),
+                       "e2e_pipeline": "two handles alternate: H2D/D2H of one overlap the kernel of the other"},
             "leaps_per_s": leaps / (ms * 1e-3), "channel_draws_per_s": leaps * P / (ms * 1e-3),
             "events_per_leap": events / max(leaps, 1),
             "roofline": {"bound": "hbm", "kernel": KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_leap": b_leap, "kernel_ms": k_ms},
+            "windows": wlines, "roofline_min_frac": min(w["frac"] for w in wlines),
             "e2e": {"value": ev_e2e / (ms_e2e * 1e-3), "unit": "events/s", "h2d_bytes_per_step": h2d * world,
                     "d2h_bytes_per_step": d2h * world, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clk, "device_error_flags": err,
-            "phase_a": {"mean_events": float(np.mean(cA["events"])), "mean_time": float(np.mean(cA["time"])),
-                        "mean_infectious": float(I0.sum() / R), "direct_kernel_ms": direct_ms,
-                        "direct_events_per_s": float(np.sum(cA["events"])) / (direct_ms * 1e-3)},
+            "direct": {"kernel": "direct_kernel", "what": "phase A: %d replicates from one infected host to t=%g" % (R, windows_t[0]),
+                       "mean_events": float(np.mean(cA["events"])), "max_events": float(np.max(cA["events"])),
+                       "mean_time": float(np.mean(cA["time"])), "mean_infectious": snaps[0]["mean_infectious"],
+                       "kernel_ms": direct_ms, "events_per_s": n_direct / (direct_ms * 1e-3),
+                       "roofline": {"bound": "hbm", "achieved": n_direct * 16 / (direct_ms * 1e-3) / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": n_direct * 16 / (direct_ms * 1e-3) / 1e9 / peak,
+                                    "bytes_per_event": 16,
+                                    "note": "latency-bound: one dependent chain per replicate, the batch ends with its longest replicate"}},
         }
+        line["phase_a"] = {"mean_events": line["direct"]["mean_events"], "mean_time": line["direct"]["mean_time"],
+                           "mean_infectious": line["direct"]["mean_infectious"], "direct_kernel_ms": direct_ms,
+                           "direct_events_per_s": line["direct"]["events_per_s"]}
         if curves is not None:
             line["epidemic_curves"] = curves
             if "achieved_GBps" in curves:
@@ -485,7 +613,12 @@ def gpu_arm(args, rank, world, local_rank):
                 line["cpu_baseline"] = {
                     "value": res["events_per_s"], "unit": "events/s", "cores": res["cores"], "kind": res["kind"],
                     "sample": "%d cores x %d replicates x %d tau leaps (direct warm-up to t=%g untimed)" % (
-                        res["cores"], reps, L, T_WARM), "leaps_per_s": res["leaps_per_s"]}
+                        res["cores"], reps, L, T_WARM), "leaps_per_s": res["leaps_per_s"],
+                    "note": "includes the reference's per-call log allocation (CreateEvents); %.4g events/s without an equal "
+                            "allocation measured beside it" % res["events_per_s_excl_alloc"]}
+                line["direct"]["cpu_baseline"] = {
+                    "value": res["direct_events_per_s"], "unit": "events/s", "cores": res["cores"], "kind": res["kind"],
+                    "sample": "the same workers' direct warm-up to t=%g (%d replicates per core)" % (T_WARM, reps)}
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "events/s", "cores": 0, "kind": "unavailable",
                                         "sample": "failed: %s" % ex}

@@ -86,6 +86,13 @@ int vgsim_state_dev(vgsim_handle h, void **dSx, void **dI);
  * setters does; batch drivers call it between independent batches, followed by vgsim_set_state). */
 int vgsim_reset(vgsim_handle h);
 
+/* Long runs in leap blocks: drop the event log / dense tau log of every replicate but keep compartments, clocks,
+ * event counters, lockdown state and the Philox epoch, so that the next simulate call continues the same
+ * trajectories into recycled log capacity (the reference can only grow its log, src/events.pxi:52-68; 4,096
+ * replicates x 1,200 leaps of the T3 shape would be 520 GB).  A consumer (vgsim_epidemic_curves, vgsim_genealogy)
+ * must have read the block first; events.ptr and the leap count restart at 0. */
+int vgsim_recycle_log(vgsim_handle h);
+
 /* SimulatePopulation (src/_BirthDeath.pyx:396-429): batched direct Gillespie, one warp per
  * replicate.  `epidemic_time` is a C float like the reference's (quirk Q1); -1 = no limit;
  * sample_size -1 = no limit.  Appends up to `iterations` rows to each replicate's event log. */
@@ -188,7 +195,8 @@ int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step
  * tests compare both with theory and with each other.
  * Bits 2 and 3 pick the kernel mapping (scheduling only, same log bit for bit): by default a batch small enough to
  * be resident as 256-thread teams runs on the team kernel, larger batches on the warp-per-replicate kernel; bit 2
- * forces the former, bit 3 the latter. */
+ * forces the former, bit 3 the latter.  Bits 4 and 5 switch off the warp kernel's lockstep generations and its
+ * size-sorted replicate schedule (scheduling only as well; tests check that the log does not change). */
 int vgsim_set_tau_variant(vgsim_handle h, int variant);
 /* Measurement tap: with bit 1 of the variant set, thread 0 of every CTA of the tau kernel accumulates the clock
  * cycles between consecutive barriers of the leap loop (critical path per phase: 0 row wipe + lists + Q,

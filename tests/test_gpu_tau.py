@@ -338,19 +338,16 @@ def test_warp_kernel_reproduces_team_kernel(name, seed, t0, dt, two, variant):
     assert exact, "tau/time streams agree to 1e-13 but not bit for bit"
 
 
-def test_schedule_does_not_change_results(monkeypatch):
+def test_schedule_does_not_change_results():
     """Lockstep generations and the size-sorted replicate schedule (more replicates than warps in flight) are
     scheduling only: the free-running, unsorted kernel must leave exactly the same counters, states and logs."""
     name, seed, t0 = "t3small", 5, 60.0
     Sx0, I0 = warm_state(name, seed, t0)
     R = 2300  # > 148 SMs x 14 warps, so the sorted boustrophedon walk has a second visit
     # unequal replicates: a third of them start from a thinned-out state
-    monkeypatch.setenv("VGSIM_TAU_SYNC", "0")
-    a = _run_kernel(name, Sx0, I0, R, 0, 12, 3.0, 4100)
-    monkeypatch.delenv("VGSIM_TAU_SYNC")
+    a = _run_kernel(name, Sx0, I0, R, 16, 12, 3.0, 4100)   # variant bit 4: free-running warps
     b = _run_kernel(name, Sx0, I0, R, 0, 12, 3.0, 4100)
-    monkeypatch.setenv("VGSIM_TAU_SORT", "0")
-    c = _run_kernel(name, Sx0, I0, R, 0, 12, 3.0, 4100)
+    c = _run_kernel(name, Sx0, I0, R, 32, 12, 3.0, 4100)   # variant bit 5: lockstep, unsorted schedule
     for other in (b, c):
         for k in ("leaps", "bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus", "time"):
             assert np.array_equal(a[0][k], other[0][k]), k

@@ -23,11 +23,16 @@ c_void_p, c_int, c_int64, c_uint64, c_float, c_char_p = (ctypes.c_void_p, ctypes
 
 
 def _load():
+    from . import build as _build
     if not os.path.exists(LIB_PATH):
         # in-tree build (nvcc cross-compiles sm_100a without a GPU); raises if nvcc is unavailable
-        from . import build as _build
         _build.build()
     lib = ctypes.CDLL(LIB_PATH)
+    if not hasattr(lib, "vgsim_recycle_log") and LIB_PATH == _build.LIB and _build.have_nvcc():
+        # a library built from older sources (it lacks the newest entry point): rebuild once and load the new file
+        del lib
+        _build.build(force=True)
+        lib = ctypes.CDLL(LIB_PATH)
     P = c_void_p
     sig = {
         "vgsim_last_error": (c_char_p, []),
@@ -43,6 +48,7 @@ def _load():
         "vgsim_set_state_dev": (c_int, [P, P, P]),
         "vgsim_state_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vgsim_reset": (c_int, [P]),
+        "vgsim_recycle_log": (c_int, [P]),
         "vgsim_simulate_direct": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
         "vgsim_simulate_tau": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
         "vgsim_synchronize": (c_int, [P]),
@@ -163,6 +169,9 @@ class Handle:
 
     def reset(self):
         _ck(lib.vgsim_reset(self._h))
+
+    def recycle_log(self):
+        _ck(lib.vgsim_recycle_log(self._h))
 
     def get_state(self, full=False, out=None):
         """out=(Sx, I): caller-owned (e.g. pinned) int64 buffers of the right shape to fill instead."""

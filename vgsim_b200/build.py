@@ -19,6 +19,12 @@ def _nvcc():
     return "nvcc"
 
 
+def have_nvcc():
+    import shutil
+    n = _nvcc()
+    return os.path.exists(n) if os.path.isabs(n) else shutil.which(n) is not None
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True

@@ -98,7 +98,7 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
         dalloc(h, &st.initSx, R * K * S) || dalloc(h, &st.cd, R * K) || dalloc(h, &st.lock, R * K) ||
         dalloc(h, &st.eff, R * K * K) || dalloc(h, &st.ceff, R * K) || dalloc(h, &st.maxEBM, R * K) ||
         dalloc(h, &st.time, R) || dalloc(h, &st.counters, R * NCOUNT) || dalloc(h, &st.epoch, R) ||
-        dalloc(h, &st.err, R) || dalloc(h, &st.loc_n, R)) {
+        dalloc(h, &st.err, R) || dalloc(h, &st.loc_n, R) || dalloc(h, &st.ev_base, R)) {
         vgsim_destroy(h);
         return 1;
     }
@@ -328,6 +328,7 @@ int vgsim_reset(vgsim_handle h) {
     CK(cudaMemsetAsync(st.epoch, 0, R * 4, h->stream));
     CK(cudaMemsetAsync(st.err, 0, R * 4, h->stream));
     CK(cudaMemsetAsync(st.loc_n, 0, R * 4, h->stream));
+    CK(cudaMemsetAsync(st.ev_base, 0, R * 8, h->stream));
     CK(cudaMemsetAsync(st.lock, 0, R * st.D.K * 4, h->stream));
     // live contact density back to the uploaded value of each replicate's parameter point
     {
@@ -343,6 +344,25 @@ int vgsim_reset(vgsim_handle h) {
     h->ev_bound = 0;
     h->leap_bound = 0;
     st.first_simulation = 0;
+    h->gen.valid = false;
+    return 0;
+}
+
+__global__ void recycle_log_kernel(DevState st) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= st.R) return;
+    st.ev_base[r] += st.counters[(size_t)r * NCOUNT + C_EVPTR];
+    st.counters[(size_t)r * NCOUNT + C_EVPTR] = 0;
+    st.counters[(size_t)r * NCOUNT + C_LEAPS] = 0;
+}
+
+int vgsim_recycle_log(vgsim_handle h) {
+    CK(cudaSetDevice(h->device));
+    recycle_log_kernel<<<(h->R + 255) / 256, 256, 0, h->stream>>>(h->st);
+    h->launches++;
+    CK(cudaGetLastError());
+    h->ev_bound = 0;
+    h->leap_bound = 0;
     h->gen.valid = false;
     return 0;
 }
@@ -744,8 +764,8 @@ int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset) {
 }
 
 int vgsim_set_tau_variant(vgsim_handle h, int variant) {
-    if (variant < 0 || variant > 15 || (variant & 12) == 12)
-        return fail("tau variant must be 0..15 (bit 0: per-channel draws, bit 1: phase timing, bit 2: force the team kernel, bit 3: force the warp kernel)");
+    if (variant < 0 || variant > 63 || (variant & 12) == 12)
+        return fail("tau variant must be 0..63 (bit 0: per-channel draws, bit 1: phase timing, bit 2: force the team kernel, bit 3: force the warp kernel, bit 4: free-running warps, bit 5: unsorted schedule)");
     h->tau_variant = variant;
     return 0;
 }

@@ -152,6 +152,7 @@ struct DevState {
     int *loc_n;                // [R]
     int *loc_sp;               // [R][loc_cap]  state | pop<<1
     double *loc_t;             // [R][loc_cap]
+    long long *ev_base;        // [R] log rows dropped by vgsim_recycle_log (the <= 100-row Restart test counts them)
     int first_simulation;      // 0 until the first simulate call snapshotted the initial state
 };
 

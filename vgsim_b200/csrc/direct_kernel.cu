@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(DevState st, SimArgs a, 
             }
             if (errbits) break;
             // ---- extinction retry (:414-418) and Restart (:714-738)
-            if (evptr <= 100 && a.iterations > 100) {
+            if (evptr + st.ev_base[r] <= 100 && a.iterations > 100) {
                 evptr = 0;
                 leaps = 0;
                 cB = cD = cS = cM = cI = cGp = cGn = 0;

@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(TAU_TEAM * TEAMS, 1) tau_kernel(const __grid_c
                 }
             }
             // ---- extinction-retry (:2331-2335): <= 100 log rows with iterations > 100 => Restart (:714-738)
-            if (evptr <= 100 && a.iterations > 100) {
+            if (evptr + st.ev_base[r] <= 100 && a.iterations > 100) {
                 evptr = 0;
                 leaps = 0;
                 sC = 0;
@@ -1258,8 +1258,7 @@ static cudaError_t launch_tau_cfg(const DevState &st, const SimArgs &a, cudaStre
 
 // Default: the warp-per-replicate kernel (tau_warp.cuh), one CTA per SM with as many warps as the shared memory
 // holds (<= 14).  The team kernel (256-thread teams, CTA-wide generations) stays available as a parity tap:
-// variant bit 2, or VGSIM_TAU_KERNEL=team; VGSIM_TAU_CFG = "<teams>x<ctas per SM>" then overrides its shape.
-// VGSIM_TAU_WARPS caps the warps per CTA of the warp kernel (A/B measurements).
+// variant bit 2 (vgsim_set_tau_variant).
 cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp,
                        int *order_buf) {
     if ((long long)st.D.K * st.D.H + st.D.K >= (1 << 20)) return cudaErrorInvalidValue;  // owner id is packed in 20 bits
@@ -1268,7 +1267,14 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
     if (teams > 4) teams = 4;
     if (teams < 1) teams = 1;
     bool team = (variant & 4) != 0, force_warp = (variant & 8) != 0;
-    if (const char *e = getenv("VGSIM_TAU_KERNEL")) {
+    // A/B knobs of the kernel mapping exist only in debug builds (-DVGSIM_DEBUG_KNOBS): the environment must not be able
+    // to change the mapping of a production run.  Measured dead ends they were used for are listed in DESIGN.md 4.1.
+#ifdef VGSIM_DEBUG_KNOBS
+#define VG_KNOB(name) getenv(name)
+#else
+#define VG_KNOB(name) ((const char *)nullptr)
+#endif
+    if (const char *e = VG_KNOB("VGSIM_TAU_KERNEL")) {
         team = team || e[0] == 't';
         force_warp = force_warp || e[0] == 'w';
     }
@@ -1279,13 +1285,13 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
     if (!team && !force_warp && team_fits && st.R <= num_sms * teams) team = true;
     if (!team) {
         int max_warps = 16;
-        if (const char *e = getenv("VGSIM_TAU_WARPS")) max_warps = atoi(e);
+        if (const char *e = VG_KNOB("VGSIM_TAU_WARPS")) max_warps = atoi(e);
         if (max_warps < 1) max_warps = 1;
         WarpLayout L = warp_layout(st.D, uniform_pp >= 0, uniform_pp >= 0 ? uniform_pp : 0, 227 * 1024, max_warps);
-        L.gsync = 3;  // lockstep generations on by default: leap start + before the draws (A/B: VGSIM_TAU_SYNC=0..7)
-        if (const char *e = getenv("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
-        if (const char *e = getenv("VGSIM_TAU_SYNC_EVERY")) L.gevery = atoi(e) < 1 ? 1 : atoi(e);
-        if (const char *e = getenv("VGSIM_TAU_GROUP")) L.ggroup = atoi(e) < 0 ? 0 : atoi(e);
+        L.gsync = (variant & 16) ? 0 : 3;  // lockstep generations: the warps of a CTA meet at leap start and before the draws
+        if (const char *e = VG_KNOB("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
+        if (const char *e = VG_KNOB("VGSIM_TAU_SYNC_EVERY")) L.gevery = atoi(e) < 1 ? 1 : atoi(e);
+        if (const char *e = VG_KNOB("VGSIM_TAU_GROUP")) L.ggroup = atoi(e) < 0 ? 0 : atoi(e);
         if (L.nwarps >= 1 && st.D.K * st.D.H < 65536) {  // cell ids are held as uint16
             const WS ws = make_ws(L, st.D);
             auto kern = L.has_eff ? ((variant & 2) ? tau_warp_kernel<true, true> : tau_warp_kernel<false, true>)
@@ -1295,11 +1301,11 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
             int grid = (st.R + L.nwarps - 1) / L.nwarps;
             if (grid > num_sms) grid = num_sms;
             // size-sorted schedule (only useful with lockstep generations and more than one visit per CTA)
-            int sorted = L.gsync != 0 && order_buf != nullptr && st.R > grid * L.nwarps;
-            if (const char *e2 = getenv("VGSIM_TAU_SORT")) sorted = sorted && atoi(e2) != 0;
+            int sorted = L.gsync != 0 && order_buf != nullptr && st.R > grid * L.nwarps && !(variant & 32);
+            if (const char *e2 = VG_KNOB("VGSIM_TAU_SORT")) sorted = sorted && atoi(e2) != 0;
             if (sorted) {
-                int wmode = 0;  // A/B: VGSIM_TAU_WEIGHT=1 sorts by loop items (cells and present haplotypes) instead of cells
-                if (const char *e3 = getenv("VGSIM_TAU_WEIGHT")) wmode = atoi(e3);
+                int wmode = 0;  // debug A/B: 1 sorts by loop items (cells and present haplotypes) instead of cells
+                if (const char *e3 = VG_KNOB("VGSIM_TAU_WEIGHT")) wmode = atoi(e3);
                 tau_weight_kernel<<<(st.R * 32 + 255) / 256, 256, 0, stream>>>(st, order_buf, wmode);
                 tau_order_kernel<<<1, 1024, 0, stream>>>(st.R, (wmode == 1 ? 3 : 1) * st.D.K * st.D.H, order_buf, order_buf + st.R);
             }
@@ -1308,7 +1314,8 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
         }
         // a single replicate's state does not fit one warp slice: fall through to the team kernel
     }
-    if (const char *e = getenv("VGSIM_TAU_CFG")) sscanf(e, "%dx%d", &teams, &cap);
+    if (const char *e = VG_KNOB("VGSIM_TAU_CFG")) sscanf(e, "%dx%d", &teams, &cap);
+#undef VG_KNOB
     if (teams >= 4) return launch_tau_cfg<4>(st, a, stream, num_sms, variant, cap);
     if (teams == 3) return launch_tau_cfg<3>(st, a, stream, num_sms, variant, cap);
     if (teams == 2) return launch_tau_cfg<2>(st, a, stream, num_sms, variant, cap);

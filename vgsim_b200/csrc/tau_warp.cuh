@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(448, 1)
                 }
             }
             // ---- extinction-retry (:2331-2335): <= 100 log rows with iterations > 100 => Restart (:714-738)
-            if (evptr <= 100 && a.iterations > 100) {
+            if (evptr + st.ev_base[r] <= 100 && a.iterations > 100) {
                 evptr = 0;
                 leaps = 0;
                 sC = 0;
