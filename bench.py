@@ -466,33 +466,39 @@ def gpu_arm(args, rank, world, local_rank):
         except Exception as ex:
             curves = {"error": str(ex)}
 
-    # ---- end-to-end timing (host buffers through the C ABI).  Two handles alternate: while one runs its kernel the
-    #      other's results are read back and its next inputs uploaded (each handle blocks only on its own stream).
+    # ---- end-to-end timing (host buffers through the C ABI).  Two handles alternate in async mode (vgsim_set_async):
+    #      every call below only enqueues on its handle's stream, so the upload of one batch and the read-back of the
+    #      other overlap the running kernel; a batch's results are consumed after vgsim_wait, two steps later.
     eng2, h2, stream2 = make_handle()
     hs = [h, h2]
     outs = []
-    for _ in hs:
+    for hh in hs:
+        hh.set_async(True)
         outs.append({"Sx": torch.empty_like(hSx).pin_memory(), "I": torch.empty_like(hI).pin_memory(),
                      "cnt": torch.empty((R, _capi.NCOUNTERS), dtype=torch.int64).pin_memory(),
-                     "time": torch.empty(R, dtype=torch.float64).pin_memory(), "pending": False})
+                     "time": torch.empty(R, dtype=torch.float64).pin_memory(),
+                     "seeds": torch.empty(R, dtype=torch.int64).pin_memory(), "pending": False})
 
     def harvest(k):
         o = outs[k]
         if not o["pending"]:
             return 0
-        hs[k].get_counters(out=(o["cnt"].numpy(), o["time"].numpy()))      # D2H  R*(12+1)*8
-        hs[k].get_state(out=(o["Sx"].numpy(), o["I"].numpy()))            # D2H  R*K*(S+H)*8
+        hs[k].wait()                                                       # the batch and its D2H copies are complete
         o["pending"] = False
         return int(o["cnt"][:, :6].sum())
 
     def step_e2e(i):
         k = i & 1
+        o = outs[k]
         got = harvest(k)                                                   # results of step i-2
+        o["seeds"].numpy()[:] = _shard.replicate_seeds(SEED0, lo, hi, batch=i + 1).view(np.int64)
         hs[k].reset()
-        hs[k].set_seeds(seeds_for(i))                                      # H2D  R*8
+        hs[k].set_seeds(o["seeds"].numpy().view(np.uint64))                # H2D  R*8
         hs[k].set_state(hSx.numpy(), hI.numpy())                           # H2D  R*K*(S+H)*8 from pinned memory
         hs[k].simulate_tau(L, -1, -1.0, 1, sync=False)
-        outs[k]["pending"] = True
+        hs[k].get_counters(out=(o["cnt"].numpy(), o["time"].numpy()))      # D2H  R*(12+1)*8
+        hs[k].get_state(out=(o["Sx"].numpy(), o["I"].numpy()))             # D2H  R*K*(S+H)*8
+        o["pending"] = True
         return got
 
     for i in range(max(args.warmup, 2)):
@@ -511,6 +517,7 @@ def gpu_arm(args, rank, world, local_rank):
     # the host-blocking copies make the host clock the honest one here: take the larger of the two
     ms_e2e = max(f0.elapsed_time(f1), 1e3 * (time.perf_counter() - w0))
     clk = clocks.stop() if rank == 0 else None
+    h.set_async(False)
     h2.close()
     del eng2
 
@@ -566,7 +573,7 @@ def gpu_arm(args, rank, world, local_rank):
                        "window": "t=%g (value); later windows of the same trajectories under `windows`" % windows_t[0],
                        "l2": "each step writes %.1f GB of event log per GPU (> 126 MB L2): no flush needed" % (R * L * b_leap / 1e9),
                        "parallelism": "replicates sharded %dx%d, no data-path collective" % (world, R),
-                       "e2e_pipeline": "two handles alternate: H2D/D2H of one overlap the kernel of the other"},
+                       "e2e_pipeline": "two handles in async mode alternate: H2D/D2H of one batch overlap the kernel of the other"},
             "leaps_per_s": leaps / (ms * 1e-3), "channel_draws_per_s": leaps * P / (ms * 1e-3),
             "events_per_leap": events / max(leaps, 1),
             "roofline": {"bound": "hbm", "kernel": KERNEL, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -47,6 +47,16 @@ int vgsim_destroy(vgsim_handle h);
  * legacy default stream).  Lets the caller time the kernels with events on its own stream. */
 int vgsim_set_stream(vgsim_handle h, void *cuda_stream);
 
+/* Pipelined batch drivers: with async on, the entry points that copy between HOST buffers and the device
+ * (vgsim_set_seeds, vgsim_set_state, vgsim_get_state without the lockdown output, vgsim_get_counters) and vgsim_reset
+ * only ENQUEUE their work on the handle's stream and return; the caller's buffers must be page-locked and stay
+ * untouched until vgsim_wait (or vgsim_synchronize) returns.  Two handles on two streams then overlap the uploads and
+ * read-backs of one batch with the kernels of the other (what bench.py's e2e number does).  Default: off (every call
+ * blocks until its copy is complete, like the reference's synchronous methods). */
+int vgsim_set_async(vgsim_handle h, int on);
+/* Block until everything queued on the handle's stream has finished (no error-flag read-back). */
+int vgsim_wait(vgsim_handle h);
+
 /* Per-replicate seeds: replaces RndmWrapper(seed=(user_seed, attempt)) (src/_BirthDeath.pyx:74,403,2310).
  * Replicate r draws from the counter-based Philox4x32-10 stream keyed by seeds[r]; the attempt
  * index, step index and channel index form the counter, so results do not depend on how

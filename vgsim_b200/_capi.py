@@ -48,6 +48,8 @@ def _load():
         "vgsim_set_state_dev": (c_int, [P, P, P]),
         "vgsim_state_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vgsim_reset": (c_int, [P]),
+        "vgsim_set_async": (c_int, [P, c_int]),
+        "vgsim_wait": (c_int, [P]),
         "vgsim_recycle_log": (c_int, [P]),
         "vgsim_simulate_direct": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
         "vgsim_simulate_tau": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
@@ -169,6 +171,13 @@ class Handle:
 
     def reset(self):
         _ck(lib.vgsim_reset(self._h))
+
+    def set_async(self, on=True):
+        """Host-buffer copies only enqueue (buffers must be pinned and stay valid until wait())."""
+        _ck(lib.vgsim_set_async(self._h, 1 if on else 0))
+
+    def wait(self):
+        _ck(lib.vgsim_wait(self._h))
 
     def recycle_log(self):
         _ck(lib.vgsim_recycle_log(self._h))

@@ -17,6 +17,10 @@ static int fail(const std::string &m) {
     g_err = m;
     return 1;
 }
+#define HOST_SYNC(h)                                                    \
+    do {                                                                \
+        if (!(h)->async_host) CK(cudaStreamSynchronize((h)->stream));   \
+    } while (0)
 #define CK(call)                                                                                   \
     do {                                                                                           \
         cudaError_t e_ = (call);                                                                   \
@@ -145,7 +149,7 @@ int vgsim_set_stream(vgsim_handle h, void *cuda_stream) {
 int vgsim_set_seeds(vgsim_handle h, const uint64_t *seeds) {
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync((void *)h->st.seeds, seeds, (size_t)h->R * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    HOST_SYNC(h);
     return 0;
 }
 
@@ -265,6 +269,7 @@ int vgsim_upload_params(vgsim_handle h, int pp, const double *b, const double *d
         for (int q = 0; q < K; q++) blob[D.o_m + p * K + q] = mm[(size_t)p * K + q];
         blob[D.o_A + p] = A[p];
         blob[D.o_sm + p] = P.sm[p];
+        blob[D.o_cd0 + p] = P.cd[p];
         blob[D.o_cdB + p] = P.cdBefore[p];
         blob[D.o_cdA + p] = P.cdAfter[p];
         blob[D.o_startN + p] = P.startLD[p] * (double)P.sizes[p];
@@ -301,7 +306,7 @@ int vgsim_set_state(vgsim_handle h, const int64_t *Sx, const int64_t *I) {
     const Dims &D = h->D;
     if (Sx) CK(cudaMemcpyAsync(h->st.Sx, Sx, (size_t)h->R * D.K * D.S * 8, cudaMemcpyHostToDevice, h->stream));
     if (I) CK(cudaMemcpyAsync(h->st.I, I, (size_t)h->R * D.K * D.H * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    HOST_SYNC(h);
     return 0;
 }
 
@@ -319,6 +324,24 @@ int vgsim_state_dev(vgsim_handle h, void **dSx, void **dI) {
     return 0;
 }
 
+__global__ void reset_cd_kernel(DevState st) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.R * st.D.K) return;
+    int r = i / st.D.K, p = i - r * st.D.K;
+    st.cd[i] = st.params[(size_t)st.rep_pp[r] * st.D.blob + st.D.o_cd0 + p];
+}
+
+int vgsim_set_async(vgsim_handle h, int on) {
+    h->async_host = on != 0;
+    return 0;
+}
+
+int vgsim_wait(vgsim_handle h) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int vgsim_reset(vgsim_handle h) {
     CK(cudaSetDevice(h->device));
     DevState &st = h->st;
@@ -330,17 +353,10 @@ int vgsim_reset(vgsim_handle h) {
     CK(cudaMemsetAsync(st.loc_n, 0, R * 4, h->stream));
     CK(cudaMemsetAsync(st.ev_base, 0, R * 8, h->stream));
     CK(cudaMemsetAsync(st.lock, 0, R * st.D.K * 4, h->stream));
-    // live contact density back to the uploaded value of each replicate's parameter point
-    {
-        const int K = st.D.K;
-        std::vector<double> cdv(R * K, 1.0);
-        for (size_t r = 0; r < R; r++) {
-            const HostParams &P = h->hp[h->rep_pp_host[r]];
-            if (P.uploaded) std::copy(P.cd.begin(), P.cd.end(), cdv.begin() + r * K);
-        }
-        CK(cudaMemcpyAsync(st.cd, cdv.data(), cdv.size() * 8, cudaMemcpyHostToDevice, h->stream));
-        CK(cudaStreamSynchronize(h->stream));  // cdv is pageable and goes out of scope
-    }
+    // live contact density back to the uploaded value of each replicate's parameter point (device side: no host sync)
+    reset_cd_kernel<<<((int)R * st.D.K + 255) / 256, 256, 0, h->stream>>>(st);
+    h->launches++;
+    CK(cudaGetLastError());
     h->ev_bound = 0;
     h->leap_bound = 0;
     st.first_simulation = 0;
@@ -377,8 +393,9 @@ int vgsim_get_state(vgsim_handle h, int64_t *Sx, int64_t *I, double *cd, int64_t
     if (lock) {
         lk.resize((size_t)h->R * D.K);
         CK(cudaMemcpyAsync(lk.data(), h->st.lock, lk.size() * 4, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));  // converted on the host below
     }
-    CK(cudaStreamSynchronize(h->stream));
+    HOST_SYNC(h);
     if (lock)
         for (size_t i = 0; i < lk.size(); i++) lock[i] = lk[i];
     return 0;
@@ -578,7 +595,7 @@ int vgsim_get_counters(vgsim_handle h, int64_t *counters, double *current_time) 
     if (counters)
         CK(cudaMemcpyAsync(counters, h->st.counters, (size_t)h->R * NCOUNT * 8, cudaMemcpyDeviceToHost, h->stream));
     if (current_time) CK(cudaMemcpyAsync(current_time, h->st.time, (size_t)h->R * 8, cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    HOST_SYNC(h);
     return 0;
 }
 

@@ -35,7 +35,7 @@ struct Dims {
     int hshift;   // log2(H)
     // parameter blob offsets (in doubles)
     int o_b, o_d, o_sr, o_q, o_tmq, o_sigT, o_T, o_Tc, o_m, o_A, o_sm, o_cdB, o_cdA, o_startN, o_endN,
-        o_size, o_g, o_mu, o_w, o_maxB, blob;
+        o_size, o_g, o_mu, o_w, o_maxB, o_cd0, blob;
 };
 
 __host__ __device__ inline Dims make_dims(int U, int K, int S) {
@@ -72,6 +72,7 @@ __host__ __device__ inline Dims make_dims(int U, int K, int S) {
     D.o_mu = o; o += H * (U > 0 ? U : 1);      // mRate (direct method: site choice)
     D.o_w = o; o += H * (U > 0 ? U : 1) * 3;   // hapMutType weights (direct method: allele choice)
     D.o_maxB = o; o += 1;           // max_h,s b*sigma
+    D.o_cd0 = o; o += K;            // contact density as uploaded (what vgsim_reset restores)
     D.blob = (o + 1) & ~1;
     return D;
 }

@@ -49,6 +49,7 @@ struct Handle {
     long long launches = 0;
     int tau_variant = 0;  // 0 = aggregated small groups (product), 1 = one Poisson draw per channel (parity tap)
     bool state_set = false;
+    bool async_host = false;  // vgsim_set_async: host-buffer copies are enqueued without blocking the calling thread
     GenealogyBuffers gen;
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
     int *tau_order = nullptr;      // [2R] scratch of the tau kernel's size-sorted schedule (weights, order)

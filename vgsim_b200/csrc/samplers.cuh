@@ -50,7 +50,7 @@ VGSIM_TABLE_SPACE const double RCP32[32] = {
     1.0 / 12, 1.0 / 13, 1.0 / 14, 1.0 / 15, 1.0 / 16, 1.0 / 17, 1.0 / 18, 1.0 / 19, 1.0 / 20, 1.0 / 21, 1.0 / 22,
     1.0 / 23, 1.0 / 24, 1.0 / 25, 1.0 / 26, 1.0 / 27, 1.0 / 28, 1.0 / 29, 1.0 / 30, 1.0 / 31};
 
-static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCtx ctx, int lane) {
+__device__ __forceinline__ long long poisson_ptrs_impl(double lam, const PhiloxCtx &ctx, int lane) {
     const double slam = sqrt(lam);
     const double b = 0.931 + 2.53 * slam;
     const double a = -0.059 + 0.02483 * b;
@@ -76,11 +76,16 @@ static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCt
     }
     return (long long)floor(lam + 0.5);  // unreachable in practice (acceptance ~0.9 per trial)
 }
+// out-of-line copy for call sites that sit inside divergent code (team kernel, per-channel parity paths); the warp
+// kernel's drain calls the inline body once, with its lanes converged
+static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCtx ctx, int lane) {
+    return poisson_ptrs_impl(lam, ctx, lane);
+}
 
 // Inversion by sequential search.  U = (hi + f) / 2^32 with f in [0,1) supplied by the low word of a second Philox
 // block: the walk is first done with f = 0, and if (hi + 1) / 2^32 lands in the same pmf cell the low word cannot
 // change the answer and is never drawn (it decides in ~n * 2^-32 of the calls); the result is the same either way.
-static __device__ __noinline__ long long poisson_inversion(double lam, uint32_t hi, const PhiloxCtx ctx, int lane) {
+__device__ __forceinline__ long long poisson_inversion_impl(double lam, uint32_t hi, const PhiloxCtx &ctx, int lane) {
     const double Ulo = (double)hi * (1.0 / 4294967296.0), Uhi = ((double)hi + 1.0) * (1.0 / 4294967296.0);
     double p = exp(-lam), cdf = p;
     long long n = 0;
@@ -98,6 +103,9 @@ static __device__ __noinline__ long long poisson_inversion(double lam, uint32_t 
         cdf += p;
     }
     return n;
+}
+static __device__ __noinline__ long long poisson_inversion(double lam, uint32_t hi, const PhiloxCtx ctx, int lane) {
+    return poisson_inversion_impl(lam, hi, ctx, lane);
 }
 
 // `hi`: this channel's word of the chunk's domain-0 Philox block.

@@ -713,6 +713,14 @@ __device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
 // -> 8.60 / 7.19 / 6.38 / 6.17 / 6.16 / 6.19 / 6.43 ms per 131,072 leaps.
 #define TAU_THETA 0.25
 #endif
+// separate thresholds for the two kinds of groups (3U mutation channels / (K-1)S out-migration channels); both < 10
+#ifndef TAU_THETA_MUT
+#define TAU_THETA_MUT TAU_THETA
+#endif
+#ifndef TAU_THETA_MIG
+#define TAU_THETA_MIG TAU_THETA
+#endif
+static_assert(TAU_THETA_MUT < 10.0 && TAU_THETA_MIG < 10.0, "aggregated totals are drawn by inversion (lambda < 10)");
 
 // total out-migration propensity of cell (p,h): sum over targets and groups of the channel propensities,
 // factorised through Q[tp,h] = sum_s Sx[tp,s] sigma[s,h]
@@ -970,11 +978,11 @@ __global__ void __launch_bounds__(TAU_TEAM * TEAMS, 1) tau_kernel(const __grid_c
                                     lam[1] = s.sr[h] * Ii * s.sm[p] * tau;
                                     lam[2] = s.tmq[h] * Ii * tau;
                                     lam[3] = K > 1 ? mig_total(p, h, Ii, D, s, eff) * tau : 0.0;
-                                    if (lam[2] > 0.0 && ((variant & 1) || lam[2] > TAU_THETA)) {
+                                    if (lam[2] > 0.0 && ((variant & 1) || lam[2] > TAU_THETA_MUT)) {
                                         s.xq[atomicAdd(&qn[2], 1)] = cell;
                                         lam[2] = 0.0;
                                     }
-                                    if (lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA)) {
+                                    if (lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA_MIG)) {
                                         s.xq[nt + atomicAdd(&qn[3], 1)] = cell;
                                         lam[3] = 0.0;
                                     }
@@ -1292,10 +1300,13 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
         if (const char *e = VG_KNOB("VGSIM_TAU_SYNC")) L.gsync = atoi(e) & 7;
         if (const char *e = VG_KNOB("VGSIM_TAU_SYNC_EVERY")) L.gevery = atoi(e) < 1 ? 1 : atoi(e);
         if (const char *e = VG_KNOB("VGSIM_TAU_GROUP")) L.ggroup = atoi(e) < 0 ? 0 : atoi(e);
-        if (L.nwarps >= 1 && st.D.K * st.D.H < 65536) {  // cell ids are held as uint16
+        const int LC = st.D.E + (st.D.K - 1) * st.D.S;     // local channels of a cell: 12-bit field of a queue entry
+        if (L.nwarps >= 1 && st.D.K * st.D.H < 65536 && LC < 4000) {  // cell ids are held as uint16
             const WS ws = make_ws(L, st.D);
-            auto kern = L.has_eff ? ((variant & 2) ? tau_warp_kernel<true, true> : tau_warp_kernel<false, true>)
-                                  : ((variant & 2) ? tau_warp_kernel<true, false> : tau_warp_kernel<false, false>);
+            const bool prof = (variant & 2) != 0, masks = L.use_masks != 0;
+            const void *kern = L.has_eff ? (masks ? (prof ? (const void *)tau_warp_kernel<true, true, true> : (const void *)tau_warp_kernel<false, true, true>)
+                                                  : (prof ? (const void *)tau_warp_kernel<true, true, false> : (const void *)tau_warp_kernel<false, true, false>))
+                                         : (prof ? (const void *)tau_warp_kernel<true, false, false> : (const void *)tau_warp_kernel<false, false, false>);
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
             if (e != cudaSuccess) return e;
             int grid = (st.R + L.nwarps - 1) / L.nwarps;
@@ -1309,8 +1320,9 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
                 tau_weight_kernel<<<(st.R * 32 + 255) / 256, 256, 0, stream>>>(st, order_buf, wmode);
                 tau_order_kernel<<<1, 1024, 0, stream>>>(st.R, (wmode == 1 ? 3 : 1) * st.D.K * st.D.H, order_buf, order_buf + st.R);
             }
-            kern<<<grid, L.nwarps * 32, L.total_bytes, stream>>>(st, a, L, ws, variant, sorted ? order_buf + st.R : nullptr);
-            return cudaGetLastError();
+            const int *order = sorted ? order_buf + st.R : nullptr;
+            void *args[] = {(void *)&st, (void *)&a, (void *)&L, (void *)&ws, (void *)&variant, (void *)&order};
+            return cudaLaunchKernel(kern, dim3(grid), dim3(L.nwarps * 32), args, L.total_bytes, stream);
         }
         // a single replicate's state does not fit one warp slice: fall through to the team kernel
     }

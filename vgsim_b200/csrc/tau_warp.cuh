@@ -31,14 +31,18 @@ struct WarpLayout {
     int p_b, p_d, p_sr, p_tmq, p_q, p_sigT, p_sb, p_T, p_sm, p_mdiag, p_sizeD, p_startN, p_endN, p_g, p_qmax, par_bytes;
     // inside a warp slice (bytes)
     int w_par, w_cd, w_c, w_maxEBM, w_eff, w_Sx, w_Bp, w_Rp, w_I, w_chk, w_upd, w_act, w_dSx, w_lock, w_tot, w_dstart,
-        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qhi, w_qoc, w_xq, w_cnt, w_tally, w_hidx, w_qtab;
+        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qlam, w_qhi, w_qoc, w_xq, w_cnt, w_tally, w_hidx, w_qtab;
     int qtab_cap;      // doubles in the per-leap Q table (0: always recompute)
     int qcap, xcap;
     int has_eff, use_masks;
     int o_done, gsync, gevery;  // gevery: the warps meet only every gevery-th leap of each warp
     int ggroup;                  // warps per lockstep group (0: the whole CTA); every group has its own named barrier
     int total_bytes;
+    // n / d = __umulhi(n, m) for the small divisors of the item decode (n < 2^20, d <= 4096: exact)
+    unsigned mS, mS1, mNBT, mG2, mnbm, mnbg, mK;
 };
+inline unsigned div_magic(int d) { return d > 1 ? (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u; }
+__device__ __forceinline__ int fdiv(int n, unsigned magic, int d) { return d > 1 ? (int)__umulhi((unsigned)n, magic) : n; }
 
 inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_bytes, int max_warps) {
     WarpLayout L;
@@ -50,8 +54,16 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     L.pp0 = pp0;
     L.use_masks = (H <= 64 && K <= 32) ? 1 : 0;
     L.has_eff = tau_eff_in_smem(D) ? 1 : 0;
-    L.qcap = 256;
+#ifndef VGSIM_TW_QCAP
+#define VGSIM_TW_QCAP 128   // >= 128: one round can push 4 entries per lane
+#endif
+    L.qcap = VGSIM_TW_QCAP;
     L.xcap = 64;
+    {
+        const int NBT = (S + 3) >> 2, G2 = (S * (S - 1) + 3) >> 2, nbm = (3 * U + 3) >> 2, nbg = ((K - 1) * S + 3) >> 2;
+        L.mS = div_magic(S); L.mS1 = div_magic(S - 1); L.mNBT = div_magic(NBT); L.mG2 = div_magic(G2);
+        L.mnbm = div_magic(nbm); L.mnbg = div_magic(nbg); L.mK = div_magic(K);
+    }
     int o = 0;
     auto take = [&](int &f, int bytes, int align) {
         o = (o + align - 1) & ~(align - 1);
@@ -69,6 +81,7 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     L.w_par = 0;
     if (!par_shared) o = L.par_bytes;
     take(L.w_cd, K * 8, 8); take(L.w_c, K * 8, 8); take(L.w_maxEBM, K * 8, 8);
+    take(L.w_qlam, L.qcap * 8, 8);
     take(L.w_eff, L.has_eff ? K * K * 8 : 0, 8);
     take(L.w_Sx, KS * 8, 8); take(L.w_Bp, KS * 8, 8); take(L.w_Rp, KS * 8, 8);
     take(L.w_rowmask, L.use_masks ? K * 8 : 0, 8);
@@ -101,7 +114,10 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     L.o_warp0 = o;
     int nw = (max_bytes - o) / L.warp_bytes;
     if (nw > max_warps) nw = max_warps;
-    if (nw > 14) nw = 14;  // 148 x 14 = 2072 replicates in flight.  ptxas gives a 448-thread CTA 128 registers per thread
+#ifndef VGSIM_TW_MAXWARPS
+#define VGSIM_TW_MAXWARPS 14
+#endif
+    if (nw > VGSIM_TW_MAXWARPS) nw = VGSIM_TW_MAXWARPS;  // 148 x 14 = 2072 replicates in flight.  ptxas gives a 448-thread CTA 128 registers per thread
                            // (4 warps of an SM sub-partition share 16 K registers; 144 does not launch), so 15-16 warps
                            // would cost no registers -- at T3 the shared-memory slice (14.4 KB + Q table) is the limit
     L.nwarps = nw;
@@ -167,12 +183,17 @@ struct WS {
     WQval Qm;
     WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, xq, cnt;
     WArr<unsigned short> act, hidx;
-    WArr<double> qtab;
+    WArr<double> qtab, qlam;
     int qtab_cap;
     WArr<long long> tally64;
     WArr<unsigned long long> rowmask, nbrmask;
     int qcap;
-    bool use_masks, has_effS;
+    bool has_effS;
+};
+// the mask path (H <= 64, K <= 32) is a compile-time property of the kernel instance: helpers see s.use_masks as a constant
+template <bool MASKS>
+struct WSX : WS {
+    static constexpr bool use_masks = MASKS;
 };
 
 inline WS make_ws(const WarpLayout &L, const Dims &D) {
@@ -196,13 +217,13 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     s.q.slot = s.tally64; s.q.o_q = D.o_q;
     s.hidx.off = wb + L.w_hidx; s.hidx.scale = ws;
     s.qtab = Wd(L.w_qtab);
+    s.qlam = Wd(L.w_qlam);
     s.qtab_cap = L.qtab_cap;
     s.Qm.Sx = s.Sx; s.Qm.sg = s.sigT; s.Qm.H = D.H; s.Qm.S = D.S; s.Qm.hshift = D.hshift;
     s.Qm.tab = s.qtab; s.Qm.hidx = s.hidx; s.Qm.cnt = s.cnt;
     s.rowmask.off = wb + L.w_rowmask; s.rowmask.scale = ws;
     s.nbrmask.off = L.o_nbr; s.nbrmask.scale = 0;
     s.qcap = L.qcap;
-    s.use_masks = L.use_masks != 0;
     s.has_effS = L.has_eff != 0;
     return s;
 }
@@ -263,7 +284,8 @@ struct LaneGroup {  // rates.cuh group interface for one warp
 // CheckLockdown for every deme (:2328-2329 / :449-450 / :736-737): the lanes vote whether any deme crosses a
 // threshold; only then lane 0 runs the sequential reference pass and the warp refreshes the contact-density
 // dependent rates.  Returns the number of flips.
-static __device__ __noinline__ int w_lockdown_slow(const DevState &st, int r, const Dims &D, const WS &s, const double *pp,
+template <class WSQ>
+static __device__ __noinline__ int w_lockdown_slow(const DevState &st, int r, const Dims &D, const WSQ &s, const double *pp,
                                                    double *eff_g, double now) {
     const int lane = threadIdx.x & 31, K = D.K;
     int flips = 0;
@@ -283,7 +305,8 @@ static __device__ __noinline__ int w_lockdown_slow(const DevState &st, int r, co
     }
     return flips;
 }
-__device__ __forceinline__ int w_lockdown(const DevState &st, int r, const Dims &D, const WS &s, const double *pp,
+template <class WSQ>
+__device__ __forceinline__ int w_lockdown(const DevState &st, int r, const Dims &D, const WSQ &s, const double *pp,
                                           double *eff_g, double now) {
     int pred = 0;
 #pragma unroll 1
@@ -296,7 +319,8 @@ __device__ __forceinline__ int w_lockdown(const DevState &st, int r, const Dims 
 }
 
 // stage one parameter point (blob layout of common.cuh) into a shared-memory parameter block
-__device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const double *pp, int t, int n) {
+template <class WSQ>
+__device__ __forceinline__ void w_load_params(const Dims &D, const WSQ &s, const double *pp, int t, int n) {
     const int K = D.K, H = D.H, S = D.S, U = D.U;
 #pragma unroll 1
     for (int i = t; i < H; i += n) {
@@ -349,8 +373,8 @@ __device__ __forceinline__ void w_load_params(const Dims &D, const WS &s, const 
 // Ordered compaction of the infectious cells of the CURRENT counts (+ upd when APPLY): act[] ascending, dstart[],
 // presence masks / counts, per-deme totals, the ascending list of haplotypes present anywhere.  Returns the
 // number of infectious cells; nhap gets the number of present haplotypes.  One warp, ends with __syncwarp().
-template <bool APPLY>
-__device__ __forceinline__ int w_lists(const Dims &D, const WS &s, int &nhap, RowWiper &wp, int wk, int n32) {
+template <class WSQ, bool APPLY>
+__device__ __forceinline__ int w_lists(const Dims &D, const WSQ &s, int &nhap, RowWiper &wp, int wk, int n32) {
     const int lane = threadIdx.x & 31, K = D.K, H = D.H, KH = K * H;
 #pragma unroll 1
     for (int i = lane; i < H; i += 32) s.colcnt[i] = 0;  // (= colmask on the mask path)
@@ -464,7 +488,8 @@ __device__ __forceinline__ double warp_min_d(double v) {
 }
 
 // Drifts and tau (ChooseTau :2432-2450) of the warp's state; same sums as the team kernel's drifts_and_tau.
-__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WS &s, const double *eff, int nhap, RowWiper &wp,
+template <class WSQ>
+__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WSQ &s, const double *eff, int nhap, RowWiper &wp,
                                                    int wk, int n32, bool &dense_pass) {
     const int K = D.K, H = D.H, S = D.S, KS = K * S;
     const int lane = threadIdx.x & 31;
@@ -542,52 +567,391 @@ __device__ __forceinline__ int warp_sum32(int v) {
     return v;
 }
 
-// drain the slow-path queue and the expansion queues of the warp (team kernel step 3b), then reset them
-__device__ __forceinline__ void w_drain(double tau, int *row, const Dims &D, const WS &s, const double *eff,
-                                        const DrawGeom &g, PhiloxCtx &ctx, LeapTally &tr) {
-    const int lane = threadIdx.x & 31, K = D.K, H = D.H, S = D.S;
-    int *qn = s.cnt;
-    const int ninv = qn[0], nptr = qn[1], nxm = qn[2], nxg = qn[3];
-    __syncwarp();
-    if (lane < 4) qn[lane] = 0;
-    // inversion entries sit at the bottom of the queue, PTRS entries at the top: one loop, at most one mixed round
-#pragma unroll 1
-    for (int k = lane; k < ninv + nptr; k += 32)
-        process_entry(k < ninv ? k : s.qcap - 1 - (k - ninv), tau, row, D, s, eff, g, ctx, tr);
-    const int nchM = 3 * D.U, nchG = (K - 1) * S;
-    const int itM = nxm * nchM, itX = itM + nxg * nchG;
-#pragma unroll 1
-    for (int it = lane; it < itX; it += 32) {
-        int owner, lc, lbase, domb;
-        if (it < itM) {
-            const int xi = it / nchM;
-            lc = it - xi * nchM;
-            owner = s.xq[xi];
-            lbase = 2;
-            domb = g.NBP;
+// ---- draws of the warp kernel ------------------------------------------------------------------------------
+// Same draws as the team kernel (same lambda expressions, same Philox addresses, same samplers: a leap stays a pure
+// function of state and seed and both kernels leave the same log), organised so that the lanes of a warp stay converged:
+//   * every unit of work is a BLOCK of four channels that share one Philox call: block 0 of a cell (RECOVERY, SAMPLING,
+//     total of the mutation group, total of the out-migration group), its TRANSMISSION blocks, a deme's SUSCCHANGE
+//     blocks, and -- for a group whose total is too large to aggregate -- the blocks of its individual channels;
+//   * a draw that the top 32 bits of its uniform do not settle goes to the queue WITH its lambda: (lambda, word,
+//     owner | local channel << 20), inversion entries from the bottom, PTRS entries from the top.  Pushes are
+//     warp-aggregated (ballot + popcount; the counters are warp-uniform registers, no shared-memory atomics);
+//   * the drain runs ONE inlined copy of each sampler over the queue with all lanes busy, then books the counts from
+//     the (owner, local channel) pair alone (integer decode, no propensity is recomputed); an aggregated total that
+//     came out non-zero is split lane-parallel, one event per lane and iteration.
+// ncu of the previous structure (one queue entry per lane through a switch over draw kinds, three call sites per
+// sampler, expanded groups drawn channel by channel inside the drain): 34 % of a leap's instructions at t = 60 and
+// 67 % at t = 120 ran with 4-7 of 32 lanes active (profiles/r1_n_*, profiles/r2_a_*).
+#define TW_L_TOT_MUT 0xFFE
+#define TW_L_TOT_MIG 0xFFF
+#define TW_XCAP 64
+
+struct DrawState {  // warp-uniform registers of one attempt at a leap
+    int ninv, nptr, nxm, nxg;
+};
+
+// Philox domain and word index of the draw (owner, l)
+__device__ __forceinline__ void tw_addr(int owner, int l, const Dims &D, const DrawGeom &g, int &dom, int &q) {
+    const int KH = D.K * D.H;
+    if (owner >= KH) {  // SUSCCHANGE channel l of a deme
+        dom = l >> 2;
+        q = l & 3;
+    } else if (l >= TW_L_TOT_MUT) {
+        dom = 0;
+        q = l == TW_L_TOT_MUT ? 2 : 3;
+    } else if (l < 2) {
+        dom = 0;
+        q = l;
+    } else if (l < 2 + 3 * D.U) {
+        dom = g.NBP + ((l - 2) >> 2);
+        q = (l - 2) & 3;
+    } else if (l < D.E) {
+        const int sn = l - 2 - 3 * D.U;
+        dom = 1 + (sn >> 2);
+        q = sn & 3;
+    } else {
+        const int lc = l - D.E;
+        dom = g.NBP + g.nbm + (lc >> 2);
+        q = lc & 3;
+    }
+}
+
+// where the n events of channel (owner, l) go (cell_channel / susc_channel without the propensity) + the row index
+template <class WSQ>
+__device__ __forceinline__ int tw_channel_ids(int owner, int l, const Dims &D, const WSQ &s, const WarpLayout &L, Channel &ch) {
+    const int K = D.K, H = D.H, S = D.S, KH = K * H;
+    ch.i_dec = ch.i_inc = ch.i_chk = ch.s_dec = ch.s_inc = -1;
+    ch.prop = 0.0;
+    if (owner >= KH) {
+        const int p = owner - KH;
+        const int ss = fdiv(l, L.mS1, S - 1), tsp = l - ss * (S - 1);
+        const int ts = tsp + (tsp >= ss ? 1 : 0);
+        ch.type = EV_SUSCCHANGE;
+        ch.s_dec = p * S + ss;
+        ch.s_inc = p * S + ts;
+        return D.NA + p * D.PD + l;
+    }
+    const int p = owner >> D.hshift, h = owner & (H - 1);
+    if (l < D.E) {
+        if (l < 2) {
+            ch.type = l == 0 ? EV_DEATH : EV_SAMPLING;
+            ch.i_dec = owner;
+            ch.s_inc = p * S + s.g[h];
+        } else if (l < 2 + 3 * D.U) {
+            const int uk = l - 2, u = uk / 3, k = uk - u * 3;
+            ch.type = EV_MUTATION;
+            ch.i_dec = owner;
+            ch.i_inc = ch.i_chk = p * H + mutate_hap(h, u, k, D.U);
         } else {
-            const int it2 = it - itM, xi = it2 / nchG;
-            lc = it2 - xi * nchG;
-            owner = s.xq[64 + xi];
-            lbase = D.E;
-            domb = g.NBP + g.nbm;
+            ch.type = EV_BIRTH;
+            ch.i_inc = ch.i_chk = owner;
+            ch.s_dec = p * S + (l - 2 - 3 * D.U);
         }
-        const int p = owner >> D.hshift, h = owner & (H - 1);
-        Channel ch;
-        const int c = cell_channel(p, h, lbase + lc, D, s, eff, ch);
-        const double lam = ch.prop * tau;
-        if (lam > 0.0) {
+        return D.NA + p * D.PD + D.SS1 + h * D.E + l;
+    }
+    const int mm = l - D.E;
+    const int tpp = fdiv(mm, L.mS, S), sn = mm - tpp * S;
+    const int tp = tpp + (tpp >= p ? 1 : 0);
+    ch.type = EV_MIGRATION;
+    ch.i_inc = tp * H + h;
+    ch.i_chk = owner;
+    ch.s_dec = tp * S + sn;
+    return ((p * (K - 1) + tpp) * S + sn) * H + h;
+}
+
+// One event of the multinomial split of an aggregated total (split_total_impl of the team kernel, one event):
+// event e of the total of cell `owner` (kind 2: mutation group, 3: out-migration group) picks its channel with the
+// e-th 53-bit uniform of the group's split domain.  Returns the local channel or -1.
+template <class WSQ>
+__device__ __forceinline__ int tw_split_event(int owner, int kind, int e, const Dims &D, const WSQ &s, const double *eff,
+                                              const DrawGeom &g, PhiloxCtx &ctx) {
+    const int K = D.K, H = D.H, S = D.S, U = D.U;
+    const int p = owner >> D.hshift, h = owner & (H - 1);
+    const double Ii = s.I[owner];
+    ctx.c0 = (uint32_t)owner;
+    ctx.dom0 = (uint32_t)(g.NBP + g.nbm + g.nbg + (kind == 2 ? 0 : 1));
+    const uint4 w = ctx.draw((uint32_t)(e >> 1));
+    const double u = (e & 1) ? u53(w.z, w.w) : u53(w.x, w.y);
+    int l = -1;
+    if (kind == 2) {
+        const double x = u * (s.tmq[h] * Ii);
+        double acc = 0.0;
+#pragma unroll 1
+        for (int uk = 0; uk < 3 * U; uk++) {
+            const double pr = s.q[h * U * 3 + uk] * Ii;
+            if (pr > 0.0) {
+                l = 2 + uk;
+                acc += pr;
+                if (x < acc) break;
+            }
+        }
+    } else {
+        const double common = Ii * s.b[h] * s.mdiag[p];
+        double tot = 0.0;
+#pragma unroll 1
+        for (int tp = 0; tp < K; tp++)
+            if (tp != p) tot += eff[tp * K + p] * s.Qm[tp * H + h];
+        const double x = u * tot;
+        double acc = 0.0, before = 0.0;
+        int tsel = -1;
+#pragma unroll 1
+        for (int tp = 0; tp < K; tp++) {
+            if (tp == p) continue;
+            const double wt = eff[tp * K + p] * s.Qm[tp * H + h];
+            if (wt > 0.0) {
+                tsel = tp;
+                before = acc;
+                acc += wt;
+                if (x < acc) break;
+            }
+        }
+        if (tsel >= 0) {
+            const double x2 = (x - before) * common;
+            double acc2 = 0.0;
+            int ssel = -1;
+#pragma unroll 1
+            for (int sn = 0; sn < S; sn++) {
+                const double pr = eff[tsel * K + p] * s.Sx[tsel * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
+                if (pr > 0.0) {
+                    ssel = sn;
+                    acc2 += pr;
+                    if (x2 < acc2) break;
+                }
+            }
+            if (ssel >= 0) l = D.E + (tsel - (tsel > p ? 1 : 0)) * S + ssel;
+        }
+    }
+    return l;
+}
+
+// Finish every queued draw and book the counts; all lanes walk the same code.
+template <class WSQ>
+__device__ __forceinline__ void w_drain(int *row, const Dims &D, const WSQ &s, const double *eff, const DrawGeom &g,
+                                        const WarpLayout &L, PhiloxCtx &ctx, LeapTally &tr, DrawState &q) {
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    // ---- inversion entries: channels with lambda < 10 and aggregated totals
+#pragma unroll 1
+    for (int k0 = 0; k0 < q.ninv; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < q.ninv;
+        const double lam = valid ? s.qlam[k] : 0.0;
+        const uint32_t hi = valid ? (uint32_t)s.qhi[k] : 0u;
+        const unsigned oc = valid ? (unsigned)s.qoc[k] : 0u;
+        const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
+        int dom, qq;
+        tw_addr(owner, l, D, g, dom, qq);
+        int n = 0;
+        if (valid) {
             ctx.c0 = (uint32_t)owner;
-            ctx.dom0 = (uint32_t)(domb + (lc >> 2));
-            const uint4 w = ctx.draw(0u);
-            const int n = (int)poisson_draw(lam, pick_word(w, lc & 3), ctx, lc & 3);
+            ctx.dom0 = (uint32_t)dom;
+            n = (int)poisson_inversion_impl(lam, hi, ctx, qq);
+        }
+        const bool tot = l >= TW_L_TOT_MUT;
+        if (n != 0 && !tot) {
+            Channel ch;
+            const int c = tw_channel_ids(owner, l, D, s, L, ch);
+            row[c] = n;
+            book(ch, n, s, tr);
+        }
+        const int ns = tot ? n : 0;
+#pragma unroll 1
+        for (int e = 0; __any_sync(0xffffffffu, e < ns); e++) {
+            if (e < ns) {
+                const int ls = tw_split_event(owner, l == TW_L_TOT_MUT ? 2 : 3, e, D, s, eff, g, ctx);
+                if (ls >= 0) {
+                    Channel ch;
+                    const int c = tw_channel_ids(owner, ls, D, s, L, ch);
+                    atomicAdd(&row[c], 1);
+                    book(ch, 1, s, tr);
+                }
+            }
+        }
+    }
+    // ---- PTRS entries (lambda >= 10) sit at the top of the queue
+#pragma unroll 1
+    for (int k0 = 0; k0 < q.nptr; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < q.nptr;
+        const int e = s.qcap - 1 - k;
+        const double lam = valid ? s.qlam[e] : 100.0;
+        const unsigned oc = valid ? (unsigned)s.qoc[e] : 0u;
+        const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
+        int dom, qq;
+        tw_addr(owner, l, D, g, dom, qq);
+        if (valid) {
+            ctx.c0 = (uint32_t)owner;
+            ctx.dom0 = (uint32_t)dom;
+            const int n = (int)poisson_ptrs_impl(lam, ctx, qq);
             if (n != 0) {
+                Channel ch;
+                const int c = tw_channel_ids(owner, l, D, s, L, ch);
                 row[c] = n;
                 book(ch, n, s, tr);
             }
         }
     }
+    q.ninv = q.nptr = 0;
     __syncwarp();
+}
+
+struct RoundOut {  // what a lane's block leaves for the queue
+    double lam[4];
+    uint4 w4;
+    unsigned mi[4], mp[4];  // per word: lanes that push an inversion / a PTRS entry
+    int owner, lb;          // local channel of word w = lb + w; lb < 0: block 0 of a cell (0, 1, the two totals)
+};
+
+// One round of 32 block items: lambdas, the Philox block, early-outs; returns the number of queue entries the round
+// needs (w_push stores them).  mode 0: the primary item space [cells: block 0 | cells x transmission blocks | demes x
+// SUSCCHANGE blocks]; mode 1: the blocks of the groups listed in the expansion queues [mutation | out-migration].
+template <class WSQ>
+__device__ __forceinline__ int w_round(int item, int mode, int nAct, double tau, int variant, const Dims &D, const WSQ &s,
+                                       const double *eff, const DrawGeom &g, const WarpLayout &L, PhiloxCtx &ctx,
+                                       DrawState &q, RoundOut &ro) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    const int K = D.K, H = D.H, S = D.S, U = D.U, KH = K * H;
+    const int NBT = g.NB1 - 1;
+    double lam[4] = {0.0, 0.0, 0.0, 0.0};
+    int owner = 0, dom = 0, lb = 0;  // local channel of word w = lb + w (block 0 of a cell: 0, 1, the two totals)
+    int kind = -1;
+    if (mode == 0) {
+        const int nB = nAct * NBT;
+        if (item < nAct) {
+            kind = 0;
+            owner = s.act[item];
+            const int p = owner >> D.hshift, h = owner & (H - 1);
+            const double Ii = s.I[owner];
+            lam[0] = s.d[h] * Ii * tau;
+            lam[1] = s.sr[h] * Ii * s.sm[p] * tau;
+            lam[2] = s.tmq[h] * Ii * tau;
+            lam[3] = K > 1 ? mig_total(p, h, Ii, D, s, eff) * tau : 0.0;
+        } else if (item < nAct + nB) {
+            kind = 1;
+            const int it2 = item - nAct;
+            const int ai = fdiv(it2, L.mNBT, NBT), j = it2 - ai * NBT;
+            owner = s.act[ai];
+            const int p = owner >> D.hshift, h = owner & (H - 1);
+            const double Ii = s.I[owner];
+            dom = 1 + j;
+            lb = 2 + 3 * U + j * 4;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int sn = j * 4 + w;
+                if (sn < S) lam[w] = s.b[h] * s.sigT[sn * H + h] * s.c[p] * s.Sx[p * S + sn] * Ii * tau;
+            }
+        } else if (item < nAct + nB + K * g.G2) {
+            kind = 2;
+            const int it = item - nAct - nB;
+            const int p = fdiv(it, L.mG2, g.G2), j = it - p * g.G2;
+            owner = KH + p;
+            dom = j;
+            lb = j * 4;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int l = j * 4 + w;
+                if (l < D.SS1) {
+                    const int ss = fdiv(l, L.mS1, S - 1), tsp = l - ss * (S - 1);
+                    const int ts = tsp + (tsp >= ss ? 1 : 0);
+                    lam[w] = s.T[ss * S + ts] * s.Sx[p * S + ss] * tau;
+                }
+            }
+        }
+    } else {
+        const int itM = q.nxm * g.nbm;
+        if (item < itM) {
+            kind = 3;
+            const int xi = fdiv(item, L.mnbm, g.nbm), j = item - xi * g.nbm;
+            owner = s.xq[xi];
+            const int h = owner & (H - 1);
+            const double Ii = s.I[owner];
+            dom = g.NBP + j;
+            lb = 2 + j * 4;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int uk = j * 4 + w;
+                if (uk < 3 * U) lam[w] = s.q[h * U * 3 + uk] * Ii * tau;
+            }
+        } else if (item < itM + q.nxg * g.nbg) {
+            kind = 4;
+            const int it2 = item - itM;
+            const int xi = fdiv(it2, L.mnbg, g.nbg), j = it2 - xi * g.nbg;
+            owner = s.xq[TW_XCAP + xi];
+            const int p = owner >> D.hshift, h = owner & (H - 1);
+            const double Ii = s.I[owner];
+            dom = g.NBP + g.nbm + j;
+            lb = D.E + j * 4;
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                const int lc = j * 4 + w;
+                if (lc < (K - 1) * S && Ii != 0.0) {
+                    const int tpp = fdiv(lc, L.mS, S), sn = lc - tpp * S;
+                    const int tp = tpp + (tpp >= p ? 1 : 0);
+                    lam[w] = eff[tp * K + p] * s.Sx[tp * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p] * tau;
+                }
+            }
+        }
+    }
+    // groups too large to aggregate: list the cell, its channels are drawn block by block in mode 1
+    {
+        const bool xm = kind == 0 && lam[2] > 0.0 && ((variant & 1) || lam[2] > TAU_THETA_MUT);
+        const bool xg = kind == 0 && lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA_MIG);
+        const unsigned bm = __ballot_sync(0xffffffffu, xm), bg = __ballot_sync(0xffffffffu, xg);
+        if (xm) {
+            s.xq[q.nxm + __popc(bm & lt)] = owner;
+            lam[2] = 0.0;
+        }
+        if (xg) {
+            s.xq[TW_XCAP + q.nxg + __popc(bg & lt)] = owner;
+            lam[3] = 0.0;
+        }
+        q.nxm += __popc(bm);
+        q.nxg += __popc(bg);
+    }
+    ro.w4 = make_uint4(0, 0, 0, 0);
+    if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
+        ctx.c0 = (uint32_t)owner;
+        ctx.dom0 = (uint32_t)dom;
+        ro.w4 = ctx.draw(0u);
+    }
+    ro.owner = owner;
+    ro.lb = kind == 0 ? -1 : lb;
+    int pushes = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t hi = w == 0 ? ro.w4.x : w == 1 ? ro.w4.y : w == 2 ? ro.w4.z : ro.w4.w;
+        const double lm = lam[w];
+        ro.lam[w] = lm;
+        // U = (hi + f)/2^32 with f in [0,1).  (hi+1)/2^32 <= 1 - lam  =>  U < 1-lam <= exp(-lam)  =>  0
+        const bool inv = lm > 0.0 && lm < 10.0 && !((double)hi + 1.0 <= (1.0 - lm) * 4294967296.0);
+        const bool ptr = lm >= 10.0;
+        ro.mi[w] = __ballot_sync(0xffffffffu, inv);
+        ro.mp[w] = __ballot_sync(0xffffffffu, ptr);
+        pushes += __popc(ro.mi[w]) + __popc(ro.mp[w]);
+    }
+    return pushes;
+}
+
+// store the round's unsettled draws (the caller has made room): inversion entries from the bottom, PTRS from the top
+template <class WSQ>
+__device__ __forceinline__ void w_push(const RoundOut &ro, const WSQ &s, DrawState &q) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const bool inv = (ro.mi[w] & me) != 0, ptr = (ro.mp[w] & me) != 0;
+        if (inv || ptr) {
+            const uint32_t hi = w == 0 ? ro.w4.x : w == 1 ? ro.w4.y : w == 2 ? ro.w4.z : ro.w4.w;
+            const int e = inv ? q.ninv + __popc(ro.mi[w] & lt) : s.qcap - 1 - (q.nptr + __popc(ro.mp[w] & lt));
+            const int l = (ro.lb < 0) ? (w < 2 ? w : w == 2 ? TW_L_TOT_MUT : TW_L_TOT_MIG) : ro.lb + w;
+            s.qlam[e] = ro.lam[w];
+            s.qhi[e] = (int)hi;
+            s.qoc[e] = (int)((unsigned)ro.owner | ((unsigned)l << 20));
+        }
+        q.ninv += __popc(ro.mi[w]);
+        q.nptr += __popc(ro.mp[w]);
+    }
 }
 
 // ---- size-sorted schedule -----------------------------------------------------------------------------
@@ -633,14 +997,14 @@ __global__ void __launch_bounds__(1024) tau_order_kernel(int R, int KH, const in
     }
 }
 
-template <bool PROF, bool EFFS>
+template <bool PROF, bool EFFS, bool MASKS>
 #ifdef VGSIM_TW_MAXNREG
 __global__ void __maxnreg__(VGSIM_TW_MAXNREG)
 #else
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
 #endif
     tau_warp_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
-                    const __grid_constant__ WarpLayout L, const __grid_constant__ WS s, const int variant,
+                    const __grid_constant__ WarpLayout L, const __grid_constant__ WSX<MASKS> s, const int variant,
                     const int *__restrict__ order) {
     const Dims &D = st.D;
     const int K = D.K, H = D.H, S = D.S, KH = K * H, KS = K * S;
@@ -747,7 +1111,7 @@ __global__ void __launch_bounds__(448, 1)
         RowWiper wp;
         wp.idle();
         int pre_row = -1;  // leap whose row the wiper is working on / has finished
-        int nAct = w_lists<false>(D, s, nhap, wp, 0, n32);
+        int nAct = w_lists<WSX<MASKS>, false>(D, s, nhap, wp, 0, n32);
 
         bool restarted = false;
         if (lane < 6) s.tally64[lane] = 0;
@@ -814,85 +1178,41 @@ __global__ void __launch_bounds__(448, 1)
                         ctx.c1 = (uint32_t)leaps;
                         ctx.c2 = (retry & 0xffu) | (epoch << 8);
                         ctx.dstride = (uint32_t)g.GS;
-                        const int n1 = nAct * g.NB1, nItems = n1 + K * g.G2;
-                        int *qn = s.cnt;  // [0] inversion [1] PTRS [2] expand-mut [3] expand-mig
+                        // One loop, one call site per helper (the leap loop has to stay small: the SM's instruction cache is
+                        // shared by 14 warps): primary rounds; whenever an expansion queue could overflow -- and once more
+                        // after the last primary round -- the rounds over the listed groups' channel blocks; a drain
+                        // whenever the next round could overflow the slow-path queue and after the last round.
+                        const int nItems = nAct * g.NB1 + K * g.G2;
+                        DrawState dq;
+                        dq.ninv = dq.nptr = dq.nxm = dq.nxg = 0;
+                        int pbase = 0, xbase = 0, xlimit = 0;
+                        bool flush = false;  // the iteration after the last round only drains
 #pragma unroll 1
-                        for (int base = 0; base < nItems; base += 32) {
-                            const int item = base + lane;
-                            // ---- 3a. primary draws (identical to the team kernel's)
-                            if (item < n1) {
-                                // block 0 of every cell first (the lanes of a round then do the same kind of work)
-                                int ai = item, blk = 0;
-                                if (item >= nAct) {
-                                    const int it2 = item - nAct;
-                                    ai = it2 / (g.NB1 - 1);
-                                    blk = 1 + it2 - ai * (g.NB1 - 1);
+                        for (;;) {
+                            const bool inx = xbase < xlimit;
+                            RoundOut ro;
+                            int pushes = 0;
+                            if (!flush)
+                                pushes = w_round((inx ? xbase : pbase) + lane, inx ? 1 : 0, nAct, tau, variant, D, s, eff, g, L, ctx, dq, ro);
+                            if (flush || dq.ninv + dq.nptr + pushes > s.qcap) w_drain(row, D, s, eff, g, L, ctx, tr, dq);
+                            if (flush) break;
+                            w_push(ro, s, dq);
+                            if (inx) {
+                                xbase += 32;
+                                if (xbase >= xlimit) {
+                                    dq.nxm = dq.nxg = 0;
+                                    xbase = xlimit = 0;
+                                    __syncwarp();  // every lane has read the lists before the next round refills them
                                 }
-                                const int cell = s.act[ai];
-                                const int p = cell >> D.hshift, h = cell & (H - 1);
-                                const double Ii = s.I[cell];
-                                double lam[4];
-                                if (blk == 0) {
-                                    lam[0] = s.d[h] * Ii * tau;
-                                    lam[1] = s.sr[h] * Ii * s.sm[p] * tau;
-                                    lam[2] = s.tmq[h] * Ii * tau;
-                                    lam[3] = K > 1 ? mig_total(p, h, Ii, D, s, eff) * tau : 0.0;
-                                    if (lam[2] > 0.0 && ((variant & 1) || lam[2] > TAU_THETA)) {
-                                        s.xq[atomicAdd(&qn[2], 1)] = cell;
-                                        lam[2] = 0.0;
-                                    }
-                                    if (lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA)) {
-                                        s.xq[64 + atomicAdd(&qn[3], 1)] = cell;
-                                        lam[3] = 0.0;
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int q = 0; q < 4; q++) {
-                                        const int sn = (blk - 1) * 4 + q;
-                                        lam[q] = sn < S ? s.b[h] * s.sigT[sn * H + h] * s.c[p] * s.Sx[p * S + sn] * Ii * tau
-                                                        : 0.0;
-                                    }
-                                }
-                                if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
-                                    ctx.c0 = (uint32_t)cell;
-                                    ctx.dom0 = (uint32_t)blk;
-                                    const uint4 w = ctx.draw(0u);
-                                    const int code0 = blk == 0 ? 0 : 4 + (blk - 1) * 4;
-                                    if (lam[0] > 0.0) primary_draw(lam[0], w.x, cell, code0, s, qn);
-                                    if (lam[1] > 0.0) primary_draw(lam[1], w.y, cell, code0 + 1, s, qn);
-                                    if (lam[2] > 0.0) primary_draw(lam[2], w.z, cell, code0 + 2, s, qn);
-                                    if (lam[3] > 0.0) primary_draw(lam[3], w.w, cell, code0 + 3, s, qn);
-                                }
-                            } else if (item < nItems) {
-                                const int it = item - n1;
-                                const int p = it / g.G2, j = it - p * g.G2;
-                                double lam[4];
-                                Channel ch;
-#pragma unroll
-                                for (int q = 0; q < 4; q++) {
-                                    const int l = j * 4 + q;
-                                    lam[q] = 0.0;
-                                    if (l < D.SS1) {
-                                        susc_channel(p, l, D, s, ch);
-                                        lam[q] = ch.prop * tau;
-                                    }
-                                }
-                                if (lam[0] > 0.0 || lam[1] > 0.0 || lam[2] > 0.0 || lam[3] > 0.0) {
-                                    ctx.c0 = (uint32_t)(K * H + p);
-                                    ctx.dom0 = (uint32_t)j;
-                                    const uint4 w = ctx.draw(0u);
-                                    if (lam[0] > 0.0) primary_draw(lam[0], w.x, K * H + p, j * 4, s, qn);
-                                    if (lam[1] > 0.0) primary_draw(lam[1], w.y, K * H + p, j * 4 + 1, s, qn);
-                                    if (lam[2] > 0.0) primary_draw(lam[2], w.z, K * H + p, j * 4 + 2, s, qn);
-                                    if (lam[3] > 0.0) primary_draw(lam[3], w.w, K * H + p, j * 4 + 3, s, qn);
-                                }
+                            } else {
+                                pbase += 32;
                             }
-                            __syncwarp();
-                            // ---- 3b. drain when the next round could overflow a queue, and after the last round
-                            const bool last = base + 32 >= nItems;
-                            if (last || qn[0] + qn[1] + 128 > s.qcap || qn[2] + 32 > 64 || qn[3] + 32 > 64) {
-                                w_drain(tau, row, D, s, eff, g, ctx, tr);
+                            const bool primary_done = pbase >= nItems;
+                            if (xlimit == 0 && (dq.nxm + 32 > TW_XCAP || dq.nxg + 32 > TW_XCAP || (primary_done && (dq.nxm | dq.nxg)))) {
+                                xlimit = dq.nxm * g.nbm + dq.nxg * g.nbg;
+                                __syncwarp();      // the lists are complete before the rounds that read them
                             }
+                            flush = primary_done && xlimit == 0;
                         }
                         TW_MARK(2)
                         // ---- 4. feasibility (:2522-2528, quirk Q8) -- see the team kernel for the extra state test
@@ -947,7 +1267,7 @@ __global__ void __launch_bounds__(448, 1)
                     // ---- 5. apply (UpdateCompartmentCounts_tau, :2536-2593) fused with the list rebuild
 #pragma unroll 1
                     for (int i = lane; i < KS; i += 32) s.Sx[i] += (double)s.dSx[i];
-                    nAct = w_lists<true>(D, s, nhap, wp, wkl, n32);
+                    nAct = w_lists<WSX<MASKS>, true>(D, s, nhap, wp, wkl, n32);
                     if (lane == 0) {
                         double *tau_tt = st.tau_tt + ((size_t)r * st.leap_cap + leaps) * 2;
                         tau_tt[0] = t;
@@ -978,7 +1298,7 @@ __global__ void __launch_bounds__(448, 1)
 #pragma unroll 1
                 for (int i = lane; i < KS; i += 32) s.Sx[i] = (double)st.initSx[(size_t)r * KS + i];
                 __syncwarp();
-                nAct = w_lists<false>(D, s, nhap, wp, 0, n32);
+                nAct = w_lists<WSX<MASKS>, false>(D, s, nhap, wp, 0, n32);
                 flips_total += w_lockdown(st, r, D, s, pp, eff_g, t);
                 good_attempt = 0;
                 if (lane == 0) ctr[C_MIGN] = 0;
