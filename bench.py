@@ -386,13 +386,15 @@ def gpu_arm(args, rank, world, local_rank):
     dev_counters = torch.as_tensor(_DevArray(cptr, (R, _capi.NCOUNTERS), "<i8"), device=dev)
     n_total = args.warmup + args.steps
     acc = torch.zeros((n_total, R, _capi.NCOUNTERS), dtype=torch.int64, device=dev)
-    seeds_pinned = torch.empty(R, dtype=torch.int64).pin_memory()
+    # one pinned seed buffer per step of a window: in async mode the H2D copy of a step's seeds is only enqueued, so its
+    # source must stay untouched until the window has been synchronised
+    seeds_pinned = torch.empty((n_total, R), dtype=torch.int64).pin_memory()
 
-    def seeds_for(step):
+    def seeds_for(step, slot):
         # fresh Philox keys per step and per replicate, disjoint across ranks
         s = _shard.replicate_seeds(SEED0, lo, hi, batch=step + 1)
-        seeds_pinned.numpy()[:] = s.view(np.int64)
-        return seeds_pinned.numpy().view(np.uint64)
+        seeds_pinned[slot].numpy()[:] = s.view(np.int64)
+        return seeds_pinned[slot].numpy().view(np.uint64)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -402,7 +404,7 @@ def gpu_arm(args, rank, world, local_rank):
 
     def step_resident(i, snap, slot):
         h.reset()
-        h.set_seeds(seeds_for(i))
+        h.set_seeds(seeds_for(i, slot))
         h.set_state_dev(snap["Sx"].data_ptr(), snap["I"].data_ptr())
         h.simulate_tau(L, -1, -1.0, 1, sync=False)
         with torch.cuda.stream(stream):
@@ -411,6 +413,7 @@ def gpu_arm(args, rank, world, local_rank):
     def measure_window(snap, seed_off, clocks=None):
         """W warm-up + K timed device-resident steps from one snapshot; CUDA events on the launching stream."""
         kernel_ms = []
+        h.set_async(True)    # nothing in a resident step needs the host to wait: the steps queue back to back
         for i in range(args.warmup):
             step_resident(seed_off + i, snap, i)
         barrier()
@@ -423,11 +426,13 @@ def gpu_arm(args, rank, world, local_rank):
         e0.record(stream)
         for i in range(args.warmup, n_total):
             step_resident(seed_off + i, snap, i)
-            kernel_ms.append(h.last_kernel_ms())
+            kernel_ms.append(h.kernel_ms_async())      # per-step event pair, read back after the window
         e1.record(stream)
         barrier()
+        h.set_async(False)
         ms = e0.elapsed_time(e1)
         cnt = acc[args.warmup:n_total].cpu().numpy()
+        kernel_ms = [k() for k in kernel_ms]
         return {"ms": ms, "events": int(cnt[:, :, :6].sum()), "leaps": int(cnt[:, :, 10].sum()),
                 "launches": h.launch_count() - launches0, "kernel_ms_sum": sum(kernel_ms),
                 "phase_cycles": h.tau_phase_cycles(reset=True) if args.phases else None}
@@ -453,6 +458,7 @@ def gpu_arm(args, rank, world, local_rank):
     if rank == 0 and not args.no_curves:
         try:
             step_resident(5 * 10 * n_total, snaps[0], 0)
+            h.wait()
             t_c = []
             for _ in range(3):
                 cv = h.epidemic_curves(8, want=("infectious",))
@@ -492,9 +498,11 @@ def gpu_arm(args, rank, world, local_rank):
         o = outs[k]
         got = harvest(k)                                                   # results of step i-2
         o["seeds"].numpy()[:] = _shard.replicate_seeds(SEED0, lo, hi, batch=i + 1).view(np.int64)
-        hs[k].reset()
+        # uploads first: they overlap the other handle's kernel, which leaves no room on the SMs for anything else
+        # (its CTAs hold all of an SM's shared memory), so the reset kernel behind them waits for it anyway
         hs[k].set_seeds(o["seeds"].numpy().view(np.uint64))                # H2D  R*8
         hs[k].set_state(hSx.numpy(), hI.numpy())                           # H2D  R*K*(S+H)*8 from pinned memory
+        hs[k].reset()
         hs[k].simulate_tau(L, -1, -1.0, 1, sync=False)
         hs[k].get_counters(out=(o["cnt"].numpy(), o["time"].numpy()))      # D2H  R*(12+1)*8
         hs[k].get_state(out=(o["Sx"].numpy(), o["I"].numpy()))             # D2H  R*K*(S+H)*8

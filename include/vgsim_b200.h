@@ -220,6 +220,10 @@ int64_t vgsim_launch_count(vgsim_handle h);
  * stream inside vgsim_simulate_* (replaces the reference's time.time() pair, src/_interface.py:821-827).
  * Blocks until that kernel has finished. */
 int vgsim_last_kernel_ms(vgsim_handle h, float *ms);
+/* The same for a pipelined driver: every hot-kernel launch gets an id (vgsim_last_kernel_id, right after the simulate call);
+ * vgsim_kernel_ms reads the duration of launch `id` later (blocks until it has finished).  The last 64 launches are held. */
+int64_t vgsim_last_kernel_id(vgsim_handle h);
+int vgsim_kernel_ms(vgsim_handle h, int64_t id, float *ms);
 /* Device pointers of counters[R][VGSIM_NCOUNTERS] (int64) and current_time[R] (fp64). */
 int vgsim_counters_dev(vgsim_handle h, void **counters, void **current_time);
 
@@ -228,6 +232,13 @@ int vgsim_counters_dev(vgsim_handle h, void **counters, void **current_time);
 int vgsim_test_poisson(const double *lam, int64_t n, uint64_t seed, int64_t *out);
 int vgsim_test_hypergeometric(const int64_t *good, const int64_t *bad, const int64_t *sample, int64_t n,
                               const uint64_t *raw_words, int64_t n_words, int64_t *out, int64_t *words_used);
+
+/* Test tap for the cumulative search that replaces fastChoose / fastChoose_skip (src/fast_choose.pxi:18-52): m queries
+ * x[q] in [0, sum w) over the same n weights; skip >= 0 leaves that index out (fastChoose_skip); small != 0 runs the
+ * sequential every-lane variant used for the handful-of-weights levels.  Outputs per query: picked index (-1 when every
+ * weight is zero), cumulative weight before it, its weight, and the reference's residual (x - before) / w. */
+int vgsim_test_choose(const double *w, int n, const double *x, int m, int skip, int small, int64_t *idx,
+                      double *before, double *wsel, double *resid);
 
 #ifdef __cplusplus
 }

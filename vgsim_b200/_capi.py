@@ -78,9 +78,12 @@ def _load():
         "vgsim_set_tau_variant": (c_int, [P, c_int]),
         "vgsim_debug_tau_phases": (c_int, [P, P, c_int]),
         "vgsim_last_kernel_ms": (c_int, [P, ctypes.POINTER(c_float)]),
+        "vgsim_last_kernel_id": (c_int64, [P]),
+        "vgsim_kernel_ms": (c_int, [P, c_int64, ctypes.POINTER(c_float)]),
         "vgsim_counters_dev": (c_int, [P, ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p)]),
         "vgsim_test_poisson": (c_int, [P, c_int64, c_uint64, P]),
         "vgsim_test_hypergeometric": (c_int, [P, P, P, c_int64, P, c_int64, P, P]),
+        "vgsim_test_choose": (c_int, [P, c_int, P, c_int, c_int, c_int, P, P, P, P]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError here = the library does not export the declared ABI
@@ -360,6 +363,16 @@ class Handle:
         _ck(lib.vgsim_last_kernel_ms(self._h, ctypes.byref(ms)))
         return float(ms.value)
 
+    def kernel_ms_async(self):
+        """Returns a callable that reads the device time of the launch just enqueued (blocking only when called)."""
+        kid = int(lib.vgsim_last_kernel_id(self._h))
+
+        def read():
+            ms = c_float()
+            _ck(lib.vgsim_kernel_ms(self._h, kid, ctypes.byref(ms)))
+            return float(ms.value)
+        return read
+
     def counters_dev_ptrs(self):
         a, b = c_void_p(), c_void_p()
         _ck(lib.vgsim_counters_dev(self._h, ctypes.byref(a), ctypes.byref(b)))
@@ -396,3 +409,15 @@ def test_hypergeometric(good, bad, sample, raw_words):
     if lib.vgsim_test_hypergeometric(_p(good), _p(bad), _p(sample), good.size, _p(raw), raw.size, _p(out), _p(used)) != 0:
         raise VgsimError("vgsim_test_hypergeometric failed")
     return out, int(used[0])
+
+
+def test_choose(w, x, skip=-1, small=False):
+    """Device cumulative search (choose.cuh) over weights w for every target in x: (index, before, weight, residual)."""
+    w = np.ascontiguousarray(w, np.float64)
+    x = np.ascontiguousarray(x, np.float64)
+    idx = np.zeros(x.shape, np.int64)
+    before, wsel, resid = (np.zeros(x.shape, np.float64) for _ in range(3))
+    if lib.vgsim_test_choose(_p(w), w.size, _p(x), x.size, int(skip), 1 if small else 0, _p(idx), _p(before), _p(wsel),
+                             _p(resid)) != 0:
+        raise VgsimError("vgsim_test_choose failed")
+    return idx, before, wsel, resid

@@ -18,6 +18,19 @@ import sys
 import numpy as np
 
 from . import _capi
+from . import _params as P
+
+_GENOME_TEXT = ('Incorrect value of number of sites or genome length. Genome length should be more or equal number of sites.')
+
+
+def _refuse_recombination(probability):
+    """The reference's Birth() takes its recombination branch whenever rn < recombination_probability
+    (src/_BirthDeath.pyx:575-596); that experimental branch (logs one haplotype, infects another, ignored by
+    the genealogy) is not part of the device path, so a non-zero probability is refused instead of silently ignored."""
+    if probability > 0:
+        raise NotImplementedError('recombination / coinfection (recombination_probability > 0) is out of scope of the '
+                                  'device path: the forward kernels do not generate recombinant births')
+
 
 BIRTH, DEATH, SAMPLING, MUTATION, SUSCCHANGE, MIGRATION, MULTITYPE = range(7)  # src/events.pxi:2-8
 
@@ -27,34 +40,32 @@ class BirthDeathModel:
     def __init__(self, number_of_sites, populations_number, number_of_susceptible_groups, seed,
                  sampling_probability, memory_optimization, genome_length, recombination_probability,
                  replicates=1, device=None):
-        self.check_amount(seed, 'seed', zero=False)
+        P.count(seed, 'seed', positive=False)
         self.user_seed = seed
         self.first_simulation = False
-        if sampling_probability != True and sampling_probability != False:
-            raise ValueError('Incorrect value of sampling probability. Value of sampling probability should be True or False.')
+        for flag, what in ((sampling_probability, 'sampling probability'), (memory_optimization, 'memory optimization')):
+            if flag != True and flag != False:  # noqa: E712  (0 / 1 are accepted like the reference does)
+                raise ValueError('Incorrect value of %s. Value of %s should be True or False.' % (what, what))
         self._sampling_probability = sampling_probability
-        if memory_optimization != True and memory_optimization != False:
-            raise ValueError('Incorrect value of memory optimization. Value of memory optimization should be True or False.')
         self._memory_optimization = memory_optimization
 
-        self.check_amount(number_of_sites, 'number of sites', zero=False)
-        self.sites = number_of_sites
+        self.sites = P.count(number_of_sites, 'number of sites', positive=False)
         self.hapNum = int(4 ** self.sites)
-        self.check_amount(number_of_susceptible_groups, 'number of susceptible groups')
-        self.susNum = number_of_susceptible_groups
-        self.check_amount(populations_number, 'populations number')
-        self.popNum = populations_number
+        self.susNum = P.count(number_of_susceptible_groups, 'number of susceptible groups')
+        self.popNum = P.count(populations_number, 'populations number')
+        self._haps = P.Axis(self.hapNum, 'haplotype', sites=self.sites)
+        self._demes = P.Axis(self.popNum, 'population')
+        self._groups = P.Axis(self.susNum, 'susceptibility type')
+        self._sites_axis = P.Axis(self.sites, 'mutation site')
 
-        self.check_value(recombination_probability, 'recombination probability', edge=1)
-        self.recombination = recombination_probability
-        self.check_amount(genome_length, 'genome length')
-        self._genome_length = genome_length
+        self.recombination = P.quantity(recombination_probability, 'recombination probability', upper=1)
+        _refuse_recombination(recombination_probability)
+        self._genome_length = P.count(genome_length, 'genome length')
         self.sitesPosition = np.zeros(self.sites, dtype=np.int64)
         if self.sites > self._genome_length:
-            raise ValueError('Incorrect value of number of sites or genome length. Genome length should be more or equal number of sites.')
+            raise ValueError(_GENOME_TEXT)
         if self.sites > 1:
-            for s in range(self.sites):
-                self.sitesPosition[s] = int(s * self._genome_length / (self.sites - 1))
+            self._place_sites()
 
         # memory optimisation (lazy haplotype slots) is a direct-method-only CPU memory
         # trick; the device path keeps the dense K x H state.  The knobs are kept for API compatibility.
@@ -92,463 +103,262 @@ class BirthDeathModel:
         self.suscepTransition = np.zeros((S, S), dtype=float)
         self.migrationRates = np.zeros((K, K), dtype=float)
 
-        self.check_amount(replicates, 'replicates')
-        self.replicates = replicates
+        self.replicates = P.count(replicates, 'replicates')
+        self._cd_touched = np.ones(K, dtype=bool)   # demes whose live contact density the next upload overwrites
         self._device = device
         self._handle = None
         self._dirty = True  # parameters changed since last upload
         self._genealogy_done = False
         self.last_elapsed = None
 
-    # ------------------------------------------------------------------ haplotype index helpers (:1187-1267)
-    def calculate_indexes(self, indexes_list, edge):
-        if isinstance(indexes_list, list):
-            indexes = set()
-            for i in indexes_list:
-                indexes.update(self.calculate_index(i, edge))
-        else:
-            indexes = set(self.calculate_index(indexes_list, edge))
-        return indexes
-
-    def calculate_index(self, index, edge):
-        if isinstance(index, str):
-            out = ['']
-            for ch in index:
-                if ch == '*':
-                    out = [o + letter for o in out for letter in 'ATCG']
-                else:
-                    out = [o + ch for o in out]
-            return [self.calculate_haplotype_from_string(o) for o in out]
-        elif isinstance(index, int):
-            return [index]
-        else:
-            return range(edge)
-
-    def calculate_string_from_haplotype(self, hapNum):
-        letters = "ATCG"
-        string = ""
-        for _ in range(self.sites):
-            string = letters[hapNum % 4] + string
-            hapNum = hapNum // 4
-        return string
+    # ------------------------------------------------------------------ axes and haplotype words
+    # (validation and index selection live in _params.py; the behaviour is the reference's setter layer,
+    #  src/_BirthDeath.pyx:1187-1702, as pinned by its 278 interface tests)
+    def calculate_string_from_haplotype(self, haplotype):
+        return self._haps.decode(haplotype)
 
     calculate_string = calculate_string_from_haplotype  # the name the reference's printing code expects (Q12)
 
     def calculate_haplotype_from_string(self, string):
-        code = {'A': 0, 'T': 1, 'C': 2, 'G': 3}
-        haplotype = 0
-        for ch in string[:self.sites]:
-            haplotype = haplotype * 4 + code.get(ch, 0)
-        return haplotype
-
-    def calculate_allele(self, haplotype, site):
-        return (haplotype // 4 ** (self.sites - site - 1)) % 4
+        return self._haps.encode(string)
 
     def create_list_for_cycles(self, index, edge):
-        return sorted(self.calculate_indexes(index, edge))
+        axis = self._haps if edge == self.hapNum else P.Axis(edge, 'index')
+        return [int(i) for i in axis.indices(index)]
 
     # ------------------------------------------------------------------ read-only scalars (:1269-1295)
-    @property
-    def seed(self):
-        return self.user_seed
-
-    @property
-    def sampling_probability(self):
-        return self._sampling_probability
-
-    @property
-    def memory_optimization(self):
-        return self._memory_optimization
-
-    @property
-    def number_of_sites(self):
-        return self.sites
-
-    @property
-    def haplotypes_number(self):
-        return self.hapNum
-
+    seed = property(lambda self: self.user_seed)
+    sampling_probability = property(lambda self: self._sampling_probability)
+    memory_optimization = property(lambda self: self._memory_optimization)
+    number_of_sites = property(lambda self: self.sites)
+    haplotypes_number = property(lambda self: self.hapNum)
     haplotype_number = haplotypes_number
+    populations_number = property(lambda self: self.popNum)
+    number_of_susceptible_groups = property(lambda self: self.susNum)
 
-    @property
-    def populations_number(self):
-        return self.popNum
+    # ------------------------------------------------------------------ parameter views (live numpy arrays, like the reference's properties)
+    initial_haplotype = property(lambda self: self.maxHapNum)
+    step_haplotype = property(lambda self: self.addMemoryNum)
+    genome_length = property(lambda self: self._genome_length)
+    coinfection_parameters = property(lambda self: self.recombination)
+    transmission_rate = property(lambda self: self.bRate)
+    recovery_rate = property(lambda self: self.dRate)
+    sampling_rate = property(lambda self: self.sRate)
+    mutation_rate = property(lambda self: self.mRate)
+    mutation_probabilities = property(lambda self: self.hapMutType)
+    mutation_position = property(lambda self: self.sitesPosition)
+    susceptibility_type = property(lambda self: self.suscType)
+    susceptibility = property(lambda self: self._susceptibility)
+    immunity_transition = property(lambda self: self.suscepTransition)
+    population_size = property(lambda self: self.sizes)
+    susceptible = property(lambda self: self._susceptible)
+    infectious = property(lambda self: self._infectious)
+    contact_density = property(lambda self: self.contactDensity)
+    npi = property(lambda self: [self.contactDensityAfterLockdown, self.startLD, self.endLD])
+    sampling_multiplier = property(lambda self: self.samplingMultiplier)
+    migration_probability = property(lambda self: self.migrationRates)
 
-    @property
-    def number_of_susceptible_groups(self):
-        return self.susNum
+    def _changed(self):
+        self._dirty = True
 
-    # ------------------------------------------------------------------ validation (:1298-1377), messages pinned by the reference tests
-    def check_amount(self, amount, smth, zero=True):
-        if isinstance(amount, int) == False:
-            raise TypeError('Incorrect type of ' + smth + '. Type should be int.')
-        elif amount <= 0 and zero:
-            raise ValueError('Incorrect value of ' + smth + '. Value should be more 0.')
-        elif amount < 0 and zero == False:
-            raise ValueError('Incorrect value of ' + smth + '. Value should be more or equal 0.')
+    def _sites_axis_named(self, what):
+        return P.Axis(self.sites, what)
 
-    def check_value(self, value, smth, edge=None, none=False):
-        if none:
-            if isinstance(value, (int, float)) == False and value is not None:
-                raise TypeError('Incorrect type of ' + smth + '. Type should be int or float or None.')
-        else:
-            if isinstance(value, (int, float)) == False:
-                raise TypeError('Incorrect type of ' + smth + '. Type should be int or float.')
-        if isinstance(value, (int, float)):
-            if edge is None:
-                if value < 0:
-                    raise ValueError('Incorrect value of ' + smth + '. Value should be more or equal 0.')
-            elif value < 0 or value > edge:
-                raise ValueError('Incorrect value of ' + smth + '. Value should be more or equal 0 and equal or less ' + str(edge) + '.')
-
-    def check_indexes(self, index, edge, smth, hap=False, none=True):
-        if isinstance(index, list):
-            for i in index:
-                self.check_index(i, edge, smth, hap=hap, none=none)
-        else:
-            self.check_index(index, edge, smth, hap=hap, none=none)
-
-    def check_index(self, index, edge, smth, hap=False, none=True):
-        if none == False and index is None:
-            raise TypeError('Incorrect type of ' + smth + '. Type should be int.')
-        elif isinstance(index, int):
-            if index < 0 or index >= edge:
-                raise IndexError('There are no such ' + smth + '!')
-        elif isinstance(index, str) and hap:
-            if sum(index.count(c) for c in "ATCG*") != self.sites:
-                raise ValueError('Incorrect haplotype. Haplotype should contain only \"A\", \"T\", \"C\", \"G\", \"*\" and length of haplotype should be equal number of mutations sites.')
-        elif index is not None:
-            if hap:
-                raise TypeError('Incorrect type of haplotype. Type should be int or str or None.')
-            else:
-                raise TypeError('Incorrect type of ' + smth + '. Type should be int or None.')
-
-    def check_list(self, data, smth, length):
-        if isinstance(data, list):
-            if len(data) != length:
-                raise ValueError('Incorrect length of ' + smth + '. Length should be equal ' + str(length) + '.')
-        else:
-            raise TypeError('Incorrect type of ' + smth + '. Type should be list.')
-
-    def check_amount_sus(self, amount, source_type, target_type, population):
-        if self._susceptible[population, source_type] - amount < 0:
-            raise ValueError('Number of susceptible minus amount should be more or equal 0.')
-        if self._susceptible[population, target_type] + amount > self.sizes[population]:
-            raise ValueError('Number of susceptible plus amount should be equal or less population size.')
-
-    def check_amount_inf(self, amount, source_type, target_haplotype, population):
-        if self._susceptible[population, source_type] - amount < 0:
-            raise ValueError('Number of susceptible minus amount should be more or equal 0.')
-        if self._infectious[population, target_haplotype] + amount > self.sizes[population]:
-            raise ValueError('Number of infectious plus amount should be equal or less population size.')
-
-    def check_mig_rate(self):
-        for pn1 in range(self.popNum):
-            summa = 0
-            self.migrationRates[pn1, pn1] = 1.0
-            for pn2 in range(self.popNum):
-                if pn1 != pn2:
-                    summa += self.migrationRates[pn1, pn2]
-                    self.migrationRates[pn1, pn1] -= self.migrationRates[pn1, pn2]
-            if summa > 1:
-                raise ValueError('Incorrect the sum of migration probabilities. The sum of migration probabilities from each population should be equal or less 1.')
-        for pn in range(self.popNum):
-            if self.migrationRates[pn, pn] <= 1e-15:
-                raise ValueError('Incorrect value of migration probability. Value of migration probability from source population to target population should be more 0.')
-
-    # ------------------------------------------------------------------ setters / properties (:1380-1702)
-    @property
-    def initial_haplotype(self):
-        return self.maxHapNum
+    # ------------------------------------------------------------------ setters
+    def _need_memory_optimization(self):
+        if not self._memory_optimization:
+            raise ValueError("Incorrect value of memory optimization. Value should be equal 'True' for work this function.")
 
     def set_initial_haplotype(self, amount):
-        if self._memory_optimization == False:
-            raise ValueError('Incorrect value of memory optimization. Value should be equal \'True\' for work this function.')
-        self.check_amount(amount, 'amount of initial haplotype')
-        self.maxHapNum = self.hapNum if amount >= self.hapNum else amount
-
-    @property
-    def step_haplotype(self):
-        return self.addMemoryNum
+        self._need_memory_optimization()
+        P.count(amount, 'amount of initial haplotype')
+        self.maxHapNum = min(amount, self.hapNum)
 
     def set_step_haplotype(self, amount):
-        if self._memory_optimization == False:
-            raise ValueError('Incorrect value of memory optimization. Value should be equal \'True\' for work this function.')
-        self.check_amount(amount, 'amount of step haplotype')
-        self.addMemoryNum = amount
+        self._need_memory_optimization()
+        self.addMemoryNum = P.count(amount, 'amount of step haplotype')
 
-    @property
-    def genome_length(self):
-        return self._genome_length
+    def _place_sites(self):
+        for site in range(self.sites):
+            self.sitesPosition[site] = int(site * self._genome_length / (self.sites - 1))
 
     def set_genome_length(self, genome_length):
-        self.check_amount(genome_length, 'genome length')
+        P.count(genome_length, 'genome length')
         if self.sites > genome_length:
-            raise ValueError('Incorrect value of number of sites or genome length. Genome length should be more or equal number of sites.')
+            raise ValueError(_GENOME_TEXT)
         self._genome_length = genome_length
-        for s in range(self.sites):
-            self.sitesPosition[s] = int(s * self._genome_length / (self.sites - 1))
-
-    @property
-    def coinfection_parameters(self):
-        return self.recombination
+        self._place_sites()
 
     def set_coinfection_parameters(self, recombination):
-        self.check_value(recombination, 'recombination probability', edge=1)
-        self.recombination = recombination
-
-    @property
-    def transmission_rate(self):
-        return self.bRate
+        self.recombination = P.quantity(recombination, 'recombination probability', upper=1)
+        _refuse_recombination(recombination)
 
     def set_transmission_rate(self, rate, haplotype):
-        self.check_value(rate, 'transmission rate')
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        for hn in self.calculate_indexes(haplotype, self.hapNum):
-            self.bRate[hn] = rate
-        self._dirty = True
-
-    @property
-    def recovery_rate(self):
-        return self.dRate
+        P.quantity(rate, 'transmission rate')
+        self.bRate[self._haps.select(haplotype)] = rate
+        self._changed()
 
     def set_recovery_rate(self, rate, haplotype):
-        self.check_value(rate, 'recovery rate')
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        for hn in self.calculate_indexes(haplotype, self.hapNum):
-            self.dRate[hn] = rate
-        self._dirty = True
-
-    @property
-    def sampling_rate(self):
-        return self.sRate
+        P.quantity(rate, 'recovery rate')
+        self.dRate[self._haps.select(haplotype)] = rate
+        self._changed()
 
     def set_sampling_rate(self, rate, haplotype):
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
-        if self._sampling_probability == True:
-            self.check_value(rate, 'sampling probability', edge=1)
-            for hn in haplotypes:
-                deathRate = self.dRate[hn] + self.sRate[hn]
-                self.dRate[hn] = (1 - rate) * deathRate
-                self.sRate[hn] = rate * deathRate
-        elif self._sampling_probability == False:
-            self.check_value(rate, 'sampling rate')
-            for hn in haplotypes:
-                self.sRate[hn] = rate
-        self._dirty = True
-
-    @property
-    def mutation_rate(self):
-        return self.mRate
+        hs = self._haps.select(haplotype)
+        if self._sampling_probability:
+            # `rate` is the probability that a removal is a sampling: split the total removal rate accordingly
+            P.quantity(rate, 'sampling probability', upper=1)
+            removal = self.dRate[hs] + self.sRate[hs]
+            self.dRate[hs] = (1 - rate) * removal
+            self.sRate[hs] = rate * removal
+        else:
+            P.quantity(rate, 'sampling rate')
+            self.sRate[hs] = rate
+        self._changed()
 
     def set_mutation_rate(self, rate, haplotype, mutation):
-        self.check_value(rate, 'mutation rate')
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        self.check_indexes(mutation, self.sites, 'mutation site')
-        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
-        sites = self.calculate_indexes(mutation, self.sites)
-        for hn in haplotypes:
-            for s in sites:
-                self.mRate[hn, s] = rate
-        self._dirty = True
-
-    @property
-    def mutation_probabilities(self):
-        return self.hapMutType
+        P.quantity(rate, 'mutation rate')
+        self._haps.check(haplotype)
+        self._sites_axis.check(mutation)
+        self.mRate[np.ix_(self._haps.indices(haplotype), self._sites_axis.indices(mutation))] = rate
+        self._changed()
 
     def set_mutation_probabilities(self, probabilities, haplotype, mutation):
-        self.check_list(probabilities, 'probabilities list', 4)
-        for i in range(4):
-            self.check_value(probabilities[i], 'mutation probabilities')
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        self.check_indexes(mutation, self.sites, 'mutation site')
-        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
-        sites = self.calculate_indexes(mutation, self.sites)
-        for hn in haplotypes:
-            for s in sites:
-                others = list(probabilities)
-                del others[self.calculate_allele(hn, s)]
+        for weight in P.fixed_list(probabilities, 'probabilities list', 4):
+            P.quantity(weight, 'mutation probabilities')
+        self._haps.check(haplotype)
+        self._sites_axis.check(mutation)
+        for h in self._haps.indices(haplotype):
+            for site in self._sites_axis.indices(mutation):
+                # the three OTHER alleles in A, T, C, G order: the haplotype's own allele is left out
+                own = self._haps.allele(int(h), int(site))
+                others = [w for allele, w in enumerate(probabilities) if allele != own]
                 if sum(others) == 0:
                     raise ValueError('Incorrect probabilities list. The sum of three elements without mutation allele should be more 0.')
-                self.hapMutType[hn, s, :] = others
-        self._dirty = True
-
-    @property
-    def mutation_position(self):
-        return self.sitesPosition
+                self.hapMutType[h, site, :] = others
+        self._changed()
 
     def set_mutation_position(self, mutation, position):
-        self.check_index(mutation, self.sites, 'number of site', none=False)
-        self.check_index(position, self._genome_length, 'mutation position', none=False)
-        for s in range(self.sites):
-            if self.sitesPosition[s] == position and s != mutation:
-                raise IndexError('Incorrect value of position. Two mutations can\'t have the same position.')
+        self._sites_axis_named('number of site').check(mutation, required=True, lists=False)
+        P.Axis(self._genome_length, 'mutation position').check(position, required=True, lists=False)
+        taken = self.sitesPosition == position
+        taken[mutation] = False
+        if taken.any():
+            raise IndexError("Incorrect value of position. Two mutations can't have the same position.")
         self.sitesPosition[mutation] = position
 
-    @property
-    def susceptibility_type(self):
-        return self.suscType
-
     def set_susceptibility_type(self, susceptibility_type, haplotype):
-        if isinstance(susceptibility_type, int) == False:
-            raise TypeError('Incorrect type of susceptibility type. Type should be int.')
-        elif susceptibility_type < 0 or susceptibility_type >= self.susNum:
-            raise IndexError('There are no such susceptibility type!')
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        for hn in self.calculate_indexes(haplotype, self.hapNum):
-            self.suscType[hn] = susceptibility_type
-        self._dirty = True
-
-    @property
-    def susceptibility(self):
-        return self._susceptibility
+        self._groups.check(susceptibility_type, required=True, lists=False)
+        self.suscType[self._haps.select(haplotype)] = susceptibility_type
+        self._changed()
 
     def set_susceptibility(self, rate, haplotype, susceptibility_type):
-        self.check_value(rate, 'susceptibility rate')
-        self.check_indexes(haplotype, self.hapNum, 'haplotype', True)
-        self.check_indexes(susceptibility_type, self.susNum, 'susceptibility type')
-        haplotypes = self.calculate_indexes(haplotype, self.hapNum)
-        sus_types = self.calculate_indexes(susceptibility_type, self.susNum)
-        for hn in haplotypes:
-            for sn in sus_types:
-                self._susceptibility[hn, sn] = rate
-        self._dirty = True
-
-    @property
-    def immunity_transition(self):
-        return self.suscepTransition
+        P.quantity(rate, 'susceptibility rate')
+        self._haps.check(haplotype)
+        self._groups.check(susceptibility_type)
+        self._susceptibility[np.ix_(self._haps.indices(haplotype), self._groups.indices(susceptibility_type))] = rate
+        self._changed()
 
     def set_immunity_transition(self, rate, source, target):
-        self.check_value(rate, 'immunity transition rate')
-        self.check_indexes(source, self.susNum, 'susceptibility type')
-        self.check_indexes(target, self.susNum, 'susceptibility type')
-        for sn1 in self.calculate_indexes(source, self.susNum):
-            for sn2 in self.calculate_indexes(target, self.susNum):
-                if sn1 != sn2:
-                    self.suscepTransition[sn1, sn2] = rate
-        self._dirty = True
-
-    @property
-    def population_size(self):
-        return self.sizes
+        P.quantity(rate, 'immunity transition rate')
+        self._groups.check(source)
+        self._groups.check(target)
+        block = np.ix_(self._groups.indices(source), self._groups.indices(target))
+        keep = np.diagonal(self.suscepTransition).copy()      # a group never "transitions" to itself
+        self.suscepTransition[block] = rate
+        np.fill_diagonal(self.suscepTransition, keep)
+        self._changed()
 
     def set_population_size(self, amount, population):
-        if self.first_simulation == True:
+        if self.first_simulation:
             raise ValueError('Changing population size is available only before first simulation!')
-        self.check_amount(amount, 'population size')
-        self.check_index(population, self.popNum, 'population')
-        for pn in self.calculate_index(population, self.popNum):
-            self.sizes[pn] = amount
-            self._susceptible[pn, 0] = amount
-            self._susceptible[pn, 1:] = 0
-        self._dirty = True
+        P.count(amount, 'population size')
+        demes = self._demes.select(population, lists=False)
+        self.sizes[demes] = amount
+        self._susceptible[demes, :] = 0
+        self._susceptible[demes, 0] = amount
+        self._changed()
 
-    @property
-    def susceptible(self):
-        return self._susceptible
-
-    def set_susceptible(self, amount, source_type, target_type, population):
-        # The reference raises TypeError here unconditionally (it calls check_amount(amount) without
-        # the `smth` argument, src/_BirthDeath.pyx:1596, quirk Q11).  The replacement implements the
-        # documented behaviour instead (move `amount` hosts between susceptibility groups).
+    def _only_before_first_run(self):
         if self.first_simulation:
             raise ValueError('This function is available only before first simulation!')
-        self.check_amount(amount, 'amount')
-        self.check_index(source_type, self.susNum, 'susceptibility type')
-        self.check_index(target_type, self.susNum, 'susceptibility type')
-        if source_type == target_type:
-            raise ValueError('Source and target susceptibility type shouldn\'t be equal!')
-        self.check_indexes(population, self.popNum, 'population')
-        for pn in self.calculate_indexes(population, self.popNum):
-            self.check_amount_sus(amount, source_type, target_type, pn)
-            self._susceptible[pn, source_type] -= amount
-            self._susceptible[pn, target_type] += amount
-        self._dirty = True
 
-    @property
-    def infectious(self):
-        return self._infectious
+    def set_susceptible(self, amount, source_type, target_type, population):
+        # The reference raises TypeError here unconditionally (it calls check_amount(amount) without the `smth`
+        # argument, src/_BirthDeath.pyx:1596, quirk Q11); implemented as documented: move `amount` hosts of every
+        # selected deme from one susceptibility group to another.
+        self._only_before_first_run()
+        P.count(amount, 'amount')
+        self._groups.check(source_type, lists=False)
+        self._groups.check(target_type, lists=False)
+        if source_type == target_type:
+            raise ValueError("Source and target susceptibility type shouldn't be equal!")
+        for deme in self._demes.select(population):
+            if self._susceptible[deme, source_type] < amount:
+                raise ValueError('Number of susceptible minus amount should be more or equal 0.')
+            if self._susceptible[deme, target_type] + amount > self.sizes[deme]:
+                raise ValueError('Number of susceptible plus amount should be equal or less population size.')
+            self._susceptible[deme, source_type] -= amount
+            self._susceptible[deme, target_type] += amount
+        self._changed()
 
     def set_infectious(self, amount, source_type, target_haplotype, population):
         # see set_susceptible: broken upstream (Q11); implemented as documented.
-        if self.first_simulation:
-            raise ValueError('This function is available only before first simulation!')
-        self.check_amount(amount, 'amount')
-        self.check_index(source_type, self.susNum, 'susceptibility type')
-        self.check_index(target_haplotype, self.hapNum, 'haplotype', hap=True)
-        self.check_indexes(population, self.popNum, 'population')
-        haplotypes = self.calculate_index(target_haplotype, self.hapNum)
-        for pn in self.calculate_indexes(population, self.popNum):
-            for hn in haplotypes:
-                self.check_amount_inf(amount, source_type, hn, pn)
-                self._susceptible[pn, source_type] -= amount
-                self._infectious[pn, hn] += amount
-        self._dirty = True
-
-    @property
-    def contact_density(self):
-        return self.contactDensity
+        self._only_before_first_run()
+        P.count(amount, 'amount')
+        self._groups.check(source_type, lists=False)
+        haps = self._haps.select(target_haplotype, lists=False)
+        for deme in self._demes.select(population):
+            for h in haps:
+                if self._susceptible[deme, source_type] < amount:
+                    raise ValueError('Number of susceptible minus amount should be more or equal 0.')
+                if self._infectious[deme, h] + amount > self.sizes[deme]:
+                    raise ValueError('Number of infectious plus amount should be equal or less population size.')
+                self._susceptible[deme, source_type] -= amount
+                self._infectious[deme, h] += amount
+        self._changed()
 
     def set_contact_density(self, value, population):
-        self.check_value(value, 'contact density')
-        self.check_indexes(population, self.popNum, 'population')
-        for pn in self.calculate_indexes(population, self.popNum):
-            self.contactDensity[pn] = value
-            self.contactDensityBeforeLockdown[pn] = value
-        self._dirty = True
-        self._cd_changed = True
-
-    @property
-    def npi(self):
-        return [self.contactDensityAfterLockdown, self.startLD, self.endLD]
+        P.quantity(value, 'contact density')
+        demes = self._demes.select(population)
+        self.contactDensity[demes] = value
+        self.contactDensityBeforeLockdown[demes] = value
+        self._cd_touched[demes] = True      # only these demes' LIVE density is overwritten at the next upload
+        self._changed()
 
     def set_npi(self, parameters, population):
-        self.check_list(parameters, 'npi parameters', 3)
-        self.check_value(parameters[0], 'first npi parameter')
-        self.check_value(parameters[1], 'second npi parameter', edge=1)
-        self.check_value(parameters[2], 'third npi parameter', edge=1)
-        self.check_indexes(population, self.popNum, 'population')
-        for pn in self.calculate_indexes(population, self.popNum):
-            self.contactDensityAfterLockdown[pn] = parameters[0]
-            self.startLD[pn] = parameters[1]
-            self.endLD[pn] = parameters[2]
-        self._dirty = True
-
-    @property
-    def sampling_multiplier(self):
-        return self.samplingMultiplier
+        after, start, end = P.fixed_list(parameters, 'npi parameters', 3)
+        P.quantity(after, 'first npi parameter')
+        P.quantity(start, 'second npi parameter', upper=1)
+        P.quantity(end, 'third npi parameter', upper=1)
+        demes = self._demes.select(population)
+        self.contactDensityAfterLockdown[demes] = after
+        self.startLD[demes] = start
+        self.endLD[demes] = end
+        self._changed()
 
     def set_sampling_multiplier(self, multiplier, population):
-        self.check_value(multiplier, 'sampling multiplier')
-        self.check_indexes(population, self.popNum, 'population')
-        for pn in self.calculate_indexes(population, self.popNum):
-            self.samplingMultiplier[pn] = multiplier
-        self._dirty = True
-
-    @property
-    def migration_probability(self):
-        return self.migrationRates
+        P.quantity(multiplier, 'sampling multiplier')
+        self.samplingMultiplier[self._demes.select(population)] = multiplier
+        self._changed()
 
     def set_migration_probability(self, probability, source, target):
-        self.check_value(probability, 'migration probability', edge=1)
-        self.check_indexes(source, self.popNum, 'population')
-        self.check_indexes(target, self.popNum, 'population')
-        for pn1 in self.calculate_indexes(source, self.popNum):
-            for pn2 in self.calculate_indexes(target, self.popNum):
-                if pn1 != pn2:
-                    self.migrationRates[pn1, pn2] = probability
-        self.check_mig_rate()
-        self._dirty = True
+        P.quantity(probability, 'migration probability', upper=1)
+        self._demes.check(source)
+        self._demes.check(target)
+        block = np.ix_(self._demes.indices(source), self._demes.indices(target))
+        keep = np.diagonal(self.migrationRates).copy()
+        self.migrationRates[block] = probability
+        np.fill_diagonal(self.migrationRates, keep)
+        P.close_migration_matrix(self.migrationRates)
+        self._changed()
 
     def set_total_migration_probability(self, total_probability):
-        self.check_value(total_probability, 'total migration probability', edge=1)
-        source_rate = 1.0 - total_probability
-        target_rate = total_probability / (self.popNum - 1)
-        self.migrationRates[:, :] = target_rate
-        np.fill_diagonal(self.migrationRates, source_rate)
-        self.check_mig_rate()
-        self._dirty = True
+        P.quantity(total_probability, 'total migration probability', upper=1)
+        self.migrationRates[...] = total_probability / (self.popNum - 1)
+        np.fill_diagonal(self.migrationRates, 1.0 - total_probability)
+        P.close_migration_matrix(self.migrationRates)
+        self._changed()
 
     # ------------------------------------------------------------------ device plumbing
     def param_arrays(self):
@@ -570,8 +380,11 @@ class BirthDeathModel:
     def _sync_params(self):
         h = self._ensure_handle()
         if self._dirty:
-            h.upload_params(0, self.param_arrays(), reset_contact_density=getattr(self, '_cd_changed', True))
-            self._cd_changed = False
+            # only demes addressed by set_contact_density since the last upload have their LIVE density overwritten
+            # (the reference's setter touches just those, :1633-1640); a deme in lockdown keeps its lockdown density
+            h.upload_params(0, self.param_arrays(), reset_contact_density=bool(self._cd_touched.any()),
+                            cd_mask=self._cd_touched.astype(np.int32))
+            self._cd_touched[:] = False
             self._dirty = False
         if not self.first_simulation:
             R = self.replicates

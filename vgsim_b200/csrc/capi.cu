@@ -86,8 +86,10 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
     h->n_pp = n_param_points;
     h->hp.resize(n_param_points);
     h->rep_pp_host.assign(n_replicates, 0);
-    CK(cudaEventCreate(&h->ev_k0));
-    CK(cudaEventCreate(&h->ev_k1));
+    for (int i = 0; i < Handle::NTIMER; i++) {
+        CK(cudaEventCreate(&h->ev_ring0[i]));
+        CK(cudaEventCreate(&h->ev_ring1[i]));
+    }
     DevState &st = h->st;
     memset(&st, 0, sizeof(st));
     st.D = D;
@@ -111,7 +113,7 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
     st.seeds = seeds;
     st.loc_cap = 64 + 16 * K;  // a deme flips its lockdown on and off a few times per wave; overflow sets a sticky error bit
     if (dalloc(h, &st.loc_sp, R * st.loc_cap) || dalloc(h, &st.loc_t, R * st.loc_cap) ||
-        dalloc(h, &h->summaries, R * VGSIM_NSUMMARY) || dalloc(h, &h->tau_order, 2 * R)) {
+        dalloc(h, &h->summaries, R * VGSIM_NSUMMARY) || dalloc(h, &h->tau_order, 2 * R) || dalloc(h, &h->work, 4)) {
         vgsim_destroy(h);
         return 1;
     }
@@ -133,8 +135,10 @@ int vgsim_destroy(vgsim_handle h) {
     cudaDeviceSynchronize();
     for (void *p : h->allocs) cudaFree(p);
     h->allocs.clear();
-    if (h->ev_k0) cudaEventDestroy(h->ev_k0);
-    if (h->ev_k1) cudaEventDestroy(h->ev_k1);
+    for (int i = 0; i < Handle::NTIMER; i++) {
+        if (h->ev_ring0[i]) cudaEventDestroy(h->ev_ring0[i]);
+        if (h->ev_ring1[i]) cudaEventDestroy(h->ev_ring1[i]);
+    }
     delete h;
     return 0;
 }
@@ -324,11 +328,22 @@ int vgsim_state_dev(vgsim_handle h, void **dSx, void **dI) {
     return 0;
 }
 
-__global__ void reset_cd_kernel(DevState st) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= st.R * st.D.K) return;
-    int r = i / st.D.K, p = i - r * st.D.K;
-    st.cd[i] = st.params[(size_t)st.rep_pp[r] * st.D.blob + st.D.o_cd0 + p];
+__global__ void reset_kernel(DevState st) {  // one warp per replicate
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= st.R) return;
+    const int K = st.D.K;
+    for (int i = lane; i < NCOUNT; i += 32) st.counters[(size_t)r * NCOUNT + i] = 0;
+    for (int p = lane; p < K; p += 32) {
+        st.lock[(size_t)r * K + p] = 0;
+        st.cd[(size_t)r * K + p] = st.params[(size_t)st.rep_pp[r] * st.D.blob + st.D.o_cd0 + p];
+    }
+    if (lane == 0) {
+        st.time[r] = 0.0;
+        st.epoch[r] = 0;
+        st.err[r] = 0;
+        st.loc_n[r] = 0;
+        st.ev_base[r] = 0;
+    }
 }
 
 int vgsim_set_async(vgsim_handle h, int on) {
@@ -346,15 +361,9 @@ int vgsim_reset(vgsim_handle h) {
     CK(cudaSetDevice(h->device));
     DevState &st = h->st;
     const size_t R = h->R;
-    CK(cudaMemsetAsync(st.counters, 0, R * NCOUNT * 8, h->stream));
-    CK(cudaMemsetAsync(st.time, 0, R * 8, h->stream));
-    CK(cudaMemsetAsync(st.epoch, 0, R * 4, h->stream));
-    CK(cudaMemsetAsync(st.err, 0, R * 4, h->stream));
-    CK(cudaMemsetAsync(st.loc_n, 0, R * 4, h->stream));
-    CK(cudaMemsetAsync(st.ev_base, 0, R * 8, h->stream));
-    CK(cudaMemsetAsync(st.lock, 0, R * st.D.K * 4, h->stream));
-    // live contact density back to the uploaded value of each replicate's parameter point (device side: no host sync)
-    reset_cd_kernel<<<((int)R * st.D.K + 255) / 256, 256, 0, h->stream>>>(st);
+    // one kernel: counters, clocks, epochs, error bits, lockdown records / flags, recycled-row counts to zero; live contact
+    // density back to the uploaded value of each replicate's parameter point (device side: no host sync)
+    reset_kernel<<<((int)R * 32 + 255) / 256, 256, 0, h->stream>>>(st);
     h->launches++;
     CK(cudaGetLastError());
     h->ev_bound = 0;
@@ -453,6 +462,12 @@ static int prepare(Handle *h, int tau_mode) {
     return 0;
 }
 
+static void next_timer(Handle *h) {
+    h->timer_id++;
+    h->ev_k0 = h->ev_ring0[h->timer_id % Handle::NTIMER];
+    h->ev_k1 = h->ev_ring1[h->timer_id % Handle::NTIMER];
+}
+
 static SimArgs make_args(int64_t iterations, int64_t sample_size, float t, int64_t attempts) {
     SimArgs a;
     a.iterations = iterations;
@@ -472,6 +487,7 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
     if (ensure_ev_cap(h, h->ev_bound + iterations) || ensure_leap_cap(h, h->leap_bound + iterations)) return 1;
     if (prepare(h, 1)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
+    next_timer(h);
     CK(cudaEventRecord(h->ev_k0, h->stream));
     int uniform_pp = h->rep_pp_host.empty() ? 0 : h->rep_pp_host[0];  // every replicate on one parameter point?
     for (int v : h->rep_pp_host)
@@ -493,8 +509,12 @@ int vgsim_simulate_direct(vgsim_handle h, int64_t iterations, int64_t sample_siz
     if (ensure_ev_cap(h, h->ev_bound + iterations)) return 1;
     if (prepare(h, 0)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
+    next_timer(h);
     CK(cudaEventRecord(h->ev_k0, h->stream));
-    cudaError_t e = launch_direct(h->st, a, h->stream, h->num_sms);
+    int uniform_pp = h->rep_pp_host.empty() ? 0 : h->rep_pp_host[0];  // every replicate on one parameter point?
+    for (int v : h->rep_pp_host)
+        if (v != uniform_pp) uniform_pp = -1;
+    cudaError_t e = launch_direct(h->st, a, h->stream, h->num_sms, uniform_pp, h->work);
     if (e != cudaSuccess) return fail(std::string("direct kernel: ") + cudaGetErrorString(e));
     CK(cudaEventRecord(h->ev_k1, h->stream));
     h->ev_valid = true;
@@ -520,6 +540,10 @@ int vgsim_synchronize(vgsim_handle h) {
         if (all & ERR_COUNT_OVERFLOW) g_err += " [compartment count overflow]";
         if (all & ERR_BADLOG) g_err += " [bad event log]";
         if (all & ERR_TAU_STUCK) g_err += " [tau leap infeasible after 80 halvings]";
+        if (all & ERR_SIDE_TABLE) g_err += " [genealogy side table overflow]";
+        // reported once: later synchronize calls must not raise (or warn) again for the same condition
+        CK(cudaMemsetAsync(h->st.err, 0, (size_t)h->R * 4, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
     }
     return all;
 }
@@ -665,7 +689,7 @@ int vgsim_get_multievents(vgsim_handle h, int r, int64_t n, int64_t *num, double
     std::vector<int32_t> cnt((size_t)n);
     std::vector<double> tt((size_t)L * 2);
     if (vgsim_get_tau_log(h, r, L, cnt.data(), tt.data())) return 1;
-    const HostParams &P = h->hp[0];
+    const HostParams &P = h->hp[h->rep_pp_host[r]];  // suscType of THIS replicate's parameter point (sweeps)
     const int K = D.K, H = D.H, S = D.S, U = D.U;
     int64_t k = 0;
     auto put = [&](int64_t nn, double t, int ty, int a, int b, int c, int d2) {
@@ -747,6 +771,7 @@ int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step
     if (last_point && !rc) rc = dalloc(h, &d_lp, (size_t)rep_count);
     cudaError_t e = cudaSuccess;
     if (!rc) {
+        next_timer(h);
         cudaEventRecord(h->ev_k0, h->stream);  // vgsim_last_kernel_ms then reports this kernel
         e = launch_curves(h->st, rep_first, rep_count, step_num, d_inf, d_sus, d_rem, d_smp, d_tp, d_lp, h->stream, h->num_sms);
         cudaEventRecord(h->ev_k1, h->stream);
@@ -792,6 +817,16 @@ int vgsim_last_kernel_ms(vgsim_handle h, float *ms) {
     if (!h->ev_valid) return fail("no hot kernel was launched yet");
     CK(cudaEventSynchronize(h->ev_k1));
     CK(cudaEventElapsedTime(ms, h->ev_k0, h->ev_k1));
+    return 0;
+}
+
+int64_t vgsim_last_kernel_id(vgsim_handle h) { return h->timer_id; }
+
+int vgsim_kernel_ms(vgsim_handle h, int64_t id, float *ms) {
+    CK(cudaSetDevice(h->device));
+    if (id < 0 || id > h->timer_id || id + Handle::NTIMER <= h->timer_id) return fail("kernel timer id is not (or no longer) held");
+    CK(cudaEventSynchronize(h->ev_ring1[id % Handle::NTIMER]));
+    CK(cudaEventElapsedTime(ms, h->ev_ring0[id % Handle::NTIMER], h->ev_ring1[id % Handle::NTIMER]));
     return 0;
 }
 

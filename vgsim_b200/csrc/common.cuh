@@ -20,6 +20,7 @@ enum {
     ERR_COUNT_OVERFLOW = 32,  // compartment count does not fit int32
     ERR_BADLOG = 64,
     ERR_TAU_STUCK = 128,      // tau leap infeasible after 80 halvings (state itself violates the bounds)
+    ERR_SIDE_TABLE = 256,     // genealogy mutation / migration table too small (the host retries with larger tables)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -145,7 +145,7 @@ struct Out {
     }
     __device__ __forceinline__ void add_mutation(int node, int hap, int nhap, double t) {
         if (mut_n >= mut_cap) {
-            err |= ERR_ARENA;
+            err |= ERR_SIDE_TABLE;
             return;
         }
         mut_node[mut_n] = node;
@@ -156,7 +156,7 @@ struct Out {
     }
     __device__ __forceinline__ void add_migration(int node, double t, int oldp, int newp) {
         if (mig_n >= mig_cap) {
-            err |= ERR_ARENA;
+            err |= ERR_SIDE_TABLE;
             return;
         }
         mig_node[mig_n] = node;
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
             O.mig_n += __popc(m);
             if (O.mig_n > O.mig_cap) {
                 O.mig_n = O.mig_cap;
-                O.err |= ERR_ARENA;
+                O.err |= ERR_SIDE_TABLE;
             }
         }
         ga.n_nodes[r] = O.n;
@@ -542,6 +542,17 @@ int vgsim_genealogy(vgsim_handle h, const uint64_t *seeds, const double *uniform
     cudaStreamSynchronize(h->stream);
     if (cudaMemcpy(ctr.data(), h->st.counters, ctr.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess)
         return vgsim_set_error("counter read-back failed");
+    // The mutation / migration side tables grow with rate x branch length, not with the sample count (the reference
+    // appends to std::vectors, src/models.pxi): start from a size that covers the usual case and, if a replicate
+    // overflows, run the replay again with 8x larger tables.  The replay rewinds the infectious counts in place (quirk
+    // Q9), so they are saved first and put back before a retry.
+    long long *I_saved = nullptr;
+    const size_t I_n = (size_t)R * D.K * D.H;
+    if (cudaMalloc(&I_saved, I_n * 8) != cudaSuccess) return vgsim_set_error("cudaMalloc failed");
+    cudaMemcpyAsync(I_saved, h->st.I, I_n * 8, cudaMemcpyDeviceToDevice, h->stream);
+    long long table_scale = 1;
+    for (int attempt = 0;; attempt++, table_scale *= 8) {
+    if (attempt > 0) cudaMemcpyAsync(h->st.I, I_saved, I_n * 8, cudaMemcpyDeviceToDevice, h->stream);
     free_gen(h);
     GenealogyBuffers &G = h->gen;
     G.h_node_off.assign(R + 1, 0);
@@ -553,8 +564,8 @@ int vgsim_genealogy(vgsim_handle h, const uint64_t *seeds, const double *uniform
         long long sC = ctr[(size_t)r * NCOUNT + C_S];
         long long nodes = sC >= 2 ? 2 * sC - 1 : 0;
         G.h_node_off[r + 1] = G.h_node_off[r] + nodes;
-        G.h_mut_off[r + 1] = G.h_mut_off[r] + (sC >= 2 ? 8 * sC + 64 : 0);
-        G.h_mig_off[r + 1] = G.h_mig_off[r] + (sC >= 2 ? 3 * sC + 8 : 0);
+        G.h_mut_off[r + 1] = G.h_mut_off[r] + (sC >= 2 ? (8 * sC + 64) * table_scale : 0);
+        G.h_mig_off[r + 1] = G.h_mig_off[r] + (sC >= 2 ? (3 * sC + 8) * table_scale : 0);
         arena_off[r + 1] = arena_off[r] + (sC >= 2 ? 2 * (2 * sC + 4 * KH) : 0);
         if (2 * sC + 4 * KH > 1000000000LL) return vgsim_set_error("sample count too large for int32 lineage arena");
     }
@@ -627,7 +638,28 @@ int vgsim_genealogy(vgsim_handle h, const uint64_t *seeds, const double *uniform
     gfree(h, dstream);
     gfree(h, doff);
     gfree(h, dused);
-    if (e != cudaSuccess) return vgsim_set_error(cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        cudaFree(I_saved);
+        return vgsim_set_error(cudaGetErrorString(e));
+    }
+    // side-table overflow?  clear the bit and go round again with larger tables
+    std::vector<int> errs(R);
+    cudaMemcpy(errs.data(), h->st.err, (size_t)R * 4, cudaMemcpyDeviceToHost);
+    bool overflow = false;
+    for (int &v : errs)
+        if (v & ERR_SIDE_TABLE) {
+            overflow = true;
+            v &= ~ERR_SIDE_TABLE;
+        }
+    if (!overflow) break;
+    cudaMemcpy(h->st.err, errs.data(), (size_t)R * 4, cudaMemcpyHostToDevice);
+    if (attempt >= 3) {
+        cudaFree(I_saved);
+        return vgsim_set_error("genealogy side tables overflow even at 512x the default capacity");
+    }
+    }
+    cudaFree(I_saved);
+    GenealogyBuffers &G = h->gen;
     G.valid = true;
     return 0;
 }

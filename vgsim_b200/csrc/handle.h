@@ -52,9 +52,15 @@ struct Handle {
     bool async_host = false;  // vgsim_set_async: host-buffer copies are enqueued without blocking the calling thread
     GenealogyBuffers gen;
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
+    int *work = nullptr;           // [4] atomic work counters of the kernels that hand out replicates dynamically
     int *tau_order = nullptr;      // [2R] scratch of the tau kernel's size-sorted schedule (weights, order)
     std::vector<int> rep_pp_host;  // host copy of the replicate -> parameter point map
-    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the last hot kernel on the handle's stream
+    // event pairs that bracket the hot kernels on the handle's stream: a ring, so that a pipelined driver can read the
+    // duration of launch `id` after the fact (vgsim_kernel_ms) instead of blocking on every launch
+    static const int NTIMER = 64;
+    cudaEvent_t ev_ring0[NTIMER] = {}, ev_ring1[NTIMER] = {};
+    long long timer_id = -1;  // id of the last hot-kernel launch
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // the pair of the last launch
     bool ev_valid = false;
     std::vector<void *> allocs;
 };
@@ -67,7 +73,7 @@ cudaError_t launch_propensities(const DevState &st, int r, double *out, double *
                                 cudaStream_t stream);
 cudaError_t launch_prepare(const DevState &st, int first, int tau_mode, cudaStream_t stream);
 cudaError_t launch_refresh(const DevState &st, cudaStream_t stream);
-cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms);
+cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int uniform_pp, int *work);
 cudaError_t launch_curves(const DevState &st, int rep_first, int rep_count, int step_num, long long *inf, long long *sus,
                           long long *removed, long long *sampled, double *time_points, int *last_point,
                           cudaStream_t stream, int num_sms);

@@ -76,6 +76,21 @@ __device__ __forceinline__ long long poisson_ptrs_impl(double lam, const PhiloxC
     }
     return (long long)floor(lam + 0.5);  // unreachable in practice (acceptance ~0.9 per trial)
 }
+// Trial 0 of poisson_ptrs_impl with the quick acceptance test only: true and k when it accepts (the same k the complete
+// sampler returns), false when the draw needs the slow test or another trial (the caller then runs the complete sampler,
+// which repeats trial 0 and goes on).
+__device__ __forceinline__ bool poisson_ptrs_quick(double lam, const PhiloxCtx &ctx, int lane, long long &k) {
+    const double slam = sqrt(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    const uint4 w = ctx.draw(2u + (uint32_t)lane);
+    const double U = u53(w.x, w.y) - 0.5;
+    const double V = u53(w.z, w.w);
+    const double us = 0.5 - fabs(U);
+    k = (long long)floor((2.0 * a / us + b) * U + lam + 0.43);
+    return us >= 0.07 && V <= vr;
+}
 // out-of-line copy for call sites that sit inside divergent code (team kernel, per-channel parity paths); the warp
 // kernel's drain calls the inline body once, with its lanes converged
 static __device__ __noinline__ long long poisson_ptrs(double lam, const PhiloxCtx ctx, int lane) {

@@ -31,7 +31,7 @@ struct WarpLayout {
     int p_b, p_d, p_sr, p_tmq, p_q, p_sigT, p_sb, p_T, p_sm, p_mdiag, p_sizeD, p_startN, p_endN, p_g, p_qmax, par_bytes;
     // inside a warp slice (bytes)
     int w_par, w_cd, w_c, w_maxEBM, w_eff, w_Sx, w_Bp, w_Rp, w_I, w_chk, w_upd, w_act, w_dSx, w_lock, w_tot, w_dstart,
-        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qlam, w_qhi, w_qoc, w_xq, w_cnt, w_tally, w_hidx, w_qtab;
+        w_colcnt, w_colmask, w_rowmask, w_hlist, w_qlam, w_qhi, w_qoc, w_xq, w_sqp, w_cnt, w_tally, w_hidx, w_qtab;
     int qtab_cap;      // doubles in the per-leap Q table (0: always recompute)
     int qcap, xcap;
     int has_eff, use_masks;
@@ -96,6 +96,7 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     else take(L.w_colcnt, H * 4, 4);
     take(L.w_hlist, H * 4, 4);
     take(L.w_qhi, L.qcap * 4, 4); take(L.w_qoc, L.qcap * 4, 4); take(L.w_xq, 2 * L.xcap * 4, 4);
+    take(L.w_sqp, 2 * 64 * 4, 4);  // parked totals: (owner | kind, n) pairs, TW_SQCAP of them
     take(L.w_cnt, 8 * 4, 4);
     take(L.w_hidx, H * 2, 2);
     const int fixed_bytes = (o + 15) & ~15;
@@ -181,7 +182,7 @@ struct WS {
     WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp;
     WIval I;
     WQval Qm;
-    WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, xq, cnt;
+    WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, xq, sqp, cnt;
     WArr<unsigned short> act, hidx;
     WArr<double> qtab, qlam;
     int qtab_cap;
@@ -212,7 +213,7 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     s.Iraw = Wi(L.w_I); s.I.raw = s.Iraw;
     s.chkI = Wi(L.w_chk); s.updI = Wi(L.w_upd); s.act.off = wb + L.w_act; s.act.scale = ws; s.dSx = Wi(L.w_dSx); s.lock = Wi(L.w_lock);
     s.tot = Wi(L.w_tot); s.dstart = Wi(L.w_dstart); s.colcnt = Wi(L.w_colcnt); s.colmask = Wi(L.w_colmask);
-    s.hlist = Wi(L.w_hlist); s.qhi = Wi(L.w_qhi); s.qoc = Wi(L.w_qoc); s.xq = Wi(L.w_xq); s.cnt = Wi(L.w_cnt);
+    s.hlist = Wi(L.w_hlist); s.qhi = Wi(L.w_qhi); s.qoc = Wi(L.w_qoc); s.xq = Wi(L.w_xq); s.sqp = Wi(L.w_sqp); s.cnt = Wi(L.w_cnt);
     s.tally64.off = wb + L.w_tally; s.tally64.scale = ws;
     s.q.slot = s.tally64; s.q.o_q = D.o_q;
     s.hidx.off = wb + L.w_hidx; s.hidx.scale = ws;
@@ -489,8 +490,8 @@ __device__ __forceinline__ double warp_min_d(double v) {
 
 // Drifts and tau (ChooseTau :2432-2450) of the warp's state; same sums as the team kernel's drifts_and_tau.
 template <class WSQ>
-__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WSQ &s, const double *eff, int nhap, RowWiper &wp,
-                                                   int wk, int n32, bool &dense_pass) {
+__device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WSQ &s, const double *eff, int nhap, int nAct,
+                                                   RowWiper &wp, int wk, int n32, bool &dense_pass) {
     const int K = D.K, H = D.H, S = D.S, KS = K * S;
     const int lane = threadIdx.x & 31;
     // ---- A. pressure / return-flow sums per (deme, group): 8 lanes per sum, fixed butterfly
@@ -540,20 +541,53 @@ __device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WSQ &s, 
         const int cell = p * H + h;
         candidate(drift_I_cell(cell, D, s, eff), s.I[cell]);
     }
-    // ---- B1b. every other cell: mutation inflow only (its count is 0).  Such a cell proposes tau = 1 / inflow, which
-    //           can only undercut tmin <= 1 when inflow > 1; inflow <= qmax * (infectious total of the deme), so when that
-    //           bound is below 1 in every deme the whole pass cannot change tau and is skipped (the usual case: per-site
-    //           mutation rates are orders of magnitude below 1 / deme prevalence).
-    int need = 0;
+    // ---- B1b. cells whose haplotype is present nowhere: count 0, drift = mutation inflow from the <= 3U one-substitution
+    //           neighbours present in the deme.  Such a cell proposes tau = 1 / inflow, which undercuts tmin <= 1 only when
+    //           inflow > 1, i.e. only when at least one neighbour contributes more than 1 / (3U); a neighbour (p, src)
+    //           contributes at most qmax * I[p,src].  So only the neighbours of "big" cells (qmax * I * 3U >= 1) have to be
+    //           looked at -- a handful of (cell, neighbour) pairs instead of a pass over all K x H cells; skipping the rest
+    //           is exact (their proposal is >= 1 and tau = min(1, ...)).  Pairs reached twice just repeat a candidate.
+    dense_pass = false;
+    {
+        const int U = D.U, n3 = 3 * U;
+        const int per = n3 > 0 ? 32 / n3 : 0;  // big cells handled per round
+        const double q3 = s.qmax[0] * (double)n3;
+        if (per > 0) {
 #pragma unroll 1
-    for (int p = lane; p < K; p += 32) need |= s.qmax[0] * (double)s.tot[p] >= 0.999;
-    dense_pass = __any_sync(0xffffffffu, need) != 0;
-    if (dense_pass) {
+            for (int base = 0; base < nAct; base += 32) {
+                const int a = base + lane;
+                const int cell = a < nAct ? (int)s.act[a] : 0;
+                const bool big = a < nAct && q3 * s.I[cell] >= 0.999;
+                unsigned bm = __ballot_sync(0xffffffffu, big);
 #pragma unroll 1
-        for (int i = lane; i < K * H; i += 32) {
-            wp.some(wk, n32);
-            if (s.colcnt[i & (H - 1)] != 0) continue;
-            candidate(drift_I_cell(i, D, s, eff), 0.0);
+                while (bm) {
+                    // this round's big cells: the first `per` set bits
+                    const int slot = lane / n3, j = lane - slot * n3;
+                    unsigned m = bm;
+                    for (int k = 0; k < slot && m; k++) m &= m - 1;
+                    const int src_lane = m ? __ffs(m) - 1 : 0;
+                    const int bc = __shfl_sync(0xffffffffu, cell, src_lane);
+                    if (m && slot < per) {
+                        const int p = bc >> D.hshift, h = bc & (H - 1);
+                        const int u = j / 3, al = 1 + (j - u * 3);
+                        const int hn = h ^ (al << (2 * u));
+                        if (s.colcnt[hn] == 0) candidate(drift_I_cell(p * H + hn, D, s, eff), 0.0);
+                    }
+                    for (int k = 0; k < per && bm; k++) bm &= bm - 1;
+                }
+            }
+        } else if (U > 0) {  // more than 10 sites: one big cell per round, its neighbours strided over the lanes
+#pragma unroll 1
+            for (int a = 0; a < nAct; a++) {
+                const int bc = s.act[a];
+                if (!(q3 * s.I[bc] >= 0.999)) continue;
+                const int p = bc >> D.hshift, h = bc & (H - 1);
+                for (int j = lane; j < n3; j += 32) {
+                    const int u = j / 3, al = 1 + (j - u * 3);
+                    const int hn = h ^ (al << (2 * u));
+                    if (s.colcnt[hn] == 0) candidate(drift_I_cell(p * H + hn, D, s, eff), 0.0);
+                }
+            }
         }
     }
     // ---- B2. susceptible drifts
@@ -587,7 +621,7 @@ __device__ __forceinline__ int warp_sum32(int v) {
 #define TW_XCAP 64
 
 struct DrawState {  // warp-uniform registers of one attempt at a leap
-    int ninv, nptr, nxm, nxg;
+    int ninv, nptr, nxm, nxg, nsq;
 };
 
 // Philox domain and word index of the draw (owner, l)
@@ -725,55 +759,117 @@ __device__ __forceinline__ int tw_split_event(int owner, int kind, int e, const 
 }
 
 // Finish every queued draw and book the counts; all lanes walk the same code.
+//   * inversion entries in rounds of 32.  A channel's count is booked at once; an aggregated total that came out
+//     non-zero is parked as a (owner | kind, n) pair, and the pairs are split 32 at a time -- as soon as 32 are there,
+//     and the rest when the leap's last drain runs (`final`) -- so that the split walks run with the lanes full
+//     (they ran with 1.5 of 32 lanes when every drain split its own few totals, ncu profiles/r2_c_*);
+//   * PTRS entries in two passes: trial 0 with the quick acceptance test for everybody (~87 % are done), then the
+//     complete sampler (same trials, same result) for the rest, compacted -- the slow acceptance test with its three
+//     logarithms no longer runs with a couple of lanes per round.
+#define TW_SQCAP 64
 template <class WSQ>
 __device__ __forceinline__ void w_drain(int *row, const Dims &D, const WSQ &s, const double *eff, const DrawGeom &g,
-                                        const WarpLayout &L, PhiloxCtx &ctx, LeapTally &tr, DrawState &q) {
+                                        const WarpLayout &L, PhiloxCtx &ctx, LeapTally &tr, DrawState &q, bool final) {
     const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
     __syncwarp();
     // ---- inversion entries: channels with lambda < 10 and aggregated totals
 #pragma unroll 1
-    for (int k0 = 0; k0 < q.ninv; k0 += 32) {
-        const int k = k0 + lane;
-        const bool valid = k < q.ninv;
-        const double lam = valid ? s.qlam[k] : 0.0;
-        const uint32_t hi = valid ? (uint32_t)s.qhi[k] : 0u;
-        const unsigned oc = valid ? (unsigned)s.qoc[k] : 0u;
-        const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
-        int dom, qq;
-        tw_addr(owner, l, D, g, dom, qq);
-        int n = 0;
-        if (valid) {
-            ctx.c0 = (uint32_t)owner;
-            ctx.dom0 = (uint32_t)dom;
-            n = (int)poisson_inversion_impl(lam, hi, ctx, qq);
+    for (int k0 = 0;; k0 += 32) {
+        const bool more = k0 < q.ninv;
+        if (more) {
+            const int k = k0 + lane;
+            const bool valid = k < q.ninv;
+            const double lam = valid ? s.qlam[k] : 0.0;
+            const uint32_t hi = valid ? (uint32_t)s.qhi[k] : 0u;
+            const unsigned oc = valid ? (unsigned)s.qoc[k] : 0u;
+            const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
+            int dom, qq;
+            tw_addr(owner, l, D, g, dom, qq);
+            int n = 0;
+            if (valid) {
+                ctx.c0 = (uint32_t)owner;
+                ctx.dom0 = (uint32_t)dom;
+                n = (int)poisson_inversion_impl(lam, hi, ctx, qq);
+            }
+            const bool tot = l >= TW_L_TOT_MUT;
+            if (n != 0 && !tot) {
+                Channel ch;
+                const int c = tw_channel_ids(owner, l, D, s, L, ch);
+                row[c] = n;
+                book(ch, n, s, tr);
+            }
+            const bool park = tot && n != 0;
+            const unsigned pm = __ballot_sync(0xffffffffu, park);
+            if (park) {
+                const int e = q.nsq + __popc(pm & lt);
+                s.sqp[2 * e] = (int)oc;
+                s.sqp[2 * e + 1] = n;
+            }
+            q.nsq += __popc(pm);
+            __syncwarp();
         }
-        const bool tot = l >= TW_L_TOT_MUT;
-        if (n != 0 && !tot) {
-            Channel ch;
-            const int c = tw_channel_ids(owner, l, D, s, L, ch);
-            row[c] = n;
-            book(ch, n, s, tr);
-        }
-        const int ns = tot ? n : 0;
+        // split one round of parked totals (taken from the end of the list)
+        if (q.nsq >= 32 || (!more && final && q.nsq > 0)) {
+            const int take = q.nsq < 32 ? q.nsq : 32;
+            const int e = q.nsq - take + lane;
+            const bool valid = lane < take;
+            const unsigned oc = valid ? (unsigned)s.sqp[2 * e] : 0u;
+            const int ns = valid ? s.sqp[2 * e + 1] : 0;
+            const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
 #pragma unroll 1
-        for (int e = 0; __any_sync(0xffffffffu, e < ns); e++) {
-            if (e < ns) {
-                const int ls = tw_split_event(owner, l == TW_L_TOT_MUT ? 2 : 3, e, D, s, eff, g, ctx);
-                if (ls >= 0) {
-                    Channel ch;
-                    const int c = tw_channel_ids(owner, ls, D, s, L, ch);
-                    atomicAdd(&row[c], 1);
-                    book(ch, 1, s, tr);
+            for (int ev = 0; __any_sync(0xffffffffu, ev < ns); ev++) {
+                if (ev < ns) {
+                    const int ls = tw_split_event(owner, l == TW_L_TOT_MUT ? 2 : 3, ev, D, s, eff, g, ctx);
+                    if (ls >= 0) {
+                        Channel ch;
+                        const int c = tw_channel_ids(owner, ls, D, s, L, ch);
+                        atomicAdd(&row[c], 1);
+                        book(ch, 1, s, tr);
+                    }
                 }
             }
+            q.nsq -= take;
+            __syncwarp();
         }
+        if (!more && !(final && q.nsq > 0)) break;
     }
-    // ---- PTRS entries (lambda >= 10) sit at the top of the queue
+    // ---- PTRS entries (lambda >= 10) sit at the top of the queue.  Pass 1: trial 0, quick acceptance only; the others
+    //      leave their entry index in the (otherwise unused) word slot of the queue's top, compacted
+    int nfail = 0;
 #pragma unroll 1
     for (int k0 = 0; k0 < q.nptr; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < q.nptr;
         const int e = s.qcap - 1 - k;
+        const double lam = valid ? s.qlam[e] : 100.0;
+        const unsigned oc = valid ? (unsigned)s.qoc[e] : 0u;
+        const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
+        int dom, qq;
+        tw_addr(owner, l, D, g, dom, qq);
+        ctx.c0 = (uint32_t)owner;
+        ctx.dom0 = (uint32_t)dom;
+        long long kq = 0;
+        const bool ok = valid && poisson_ptrs_quick(lam, ctx, qq, kq);
+        if (ok && kq != 0) {
+            Channel ch;
+            const int c = tw_channel_ids(owner, l, D, s, L, ch);
+            row[c] = (int)kq;
+            book(ch, (int)kq, s, tr);
+        }
+        const bool fail = valid && !ok;
+        const unsigned fm = __ballot_sync(0xffffffffu, fail);
+        __syncwarp();  // every lane has read its queue words before the slots below are reused
+        if (fail) s.qhi[s.qcap - 1 - (nfail + __popc(fm & lt))] = e;
+        nfail += __popc(fm);
+    }
+    __syncwarp();
+    // ---- pass 2: the complete sampler for the entries trial 0 did not settle
+#pragma unroll 1
+    for (int k0 = 0; k0 < nfail; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < nfail;
+        const int e = valid ? s.qhi[s.qcap - 1 - k] : s.qcap - 1;
         const double lam = valid ? s.qlam[e] : 100.0;
         const unsigned oc = valid ? (unsigned)s.qoc[e] : 0u;
         const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
@@ -1150,7 +1246,7 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                         pre_row = -1;
                     }
                     bool dense_pass;
-                    double tau = w_drifts_and_tau(D, s, eff, nhap, wp, wk, n32, dense_pass);
+                    double tau = w_drifts_and_tau(D, s, eff, nhap, nAct, wp, wk, n32, dense_pass);
                     const int wkl = dense_pass ? wk : wk2;  // the empty-cell drift pass was skipped: its share of the wipe moves on
                     TW_MARK(1)
                     if (meet && (gsync & 2)) TW_GEN_SYNC();
@@ -1184,7 +1280,7 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                         // whenever the next round could overflow the slow-path queue and after the last round.
                         const int nItems = nAct * g.NB1 + K * g.G2;
                         DrawState dq;
-                        dq.ninv = dq.nptr = dq.nxm = dq.nxg = 0;
+                        dq.ninv = dq.nptr = dq.nxm = dq.nxg = dq.nsq = 0;
                         int pbase = 0, xbase = 0, xlimit = 0;
                         bool flush = false;  // the iteration after the last round only drains
 #pragma unroll 1
@@ -1194,7 +1290,7 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                             int pushes = 0;
                             if (!flush)
                                 pushes = w_round((inx ? xbase : pbase) + lane, inx ? 1 : 0, nAct, tau, variant, D, s, eff, g, L, ctx, dq, ro);
-                            if (flush || dq.ninv + dq.nptr + pushes > s.qcap) w_drain(row, D, s, eff, g, L, ctx, tr, dq);
+                            if (flush || dq.ninv + dq.nptr + pushes > s.qcap) w_drain(row, D, s, eff, g, L, ctx, tr, dq, flush);
                             if (flush) break;
                             w_push(ro, s, dq);
                             if (inx) {

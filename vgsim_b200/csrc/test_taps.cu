@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "samplers.cuh"
 #include "genrng.cuh"
+#include "choose.cuh"
 
 namespace vg {
 __global__ void poisson_tap_kernel(const double *lam, long long n, uint64_t seed, long long *out) {
@@ -78,5 +79,42 @@ extern "C" int vgsim_test_hypergeometric(const int64_t *good, const int64_t *bad
     cudaMemcpy(&u, dused, 8, cudaMemcpyDeviceToHost);
     if (words_used) *words_used = u;
     cudaFree(dg); cudaFree(db); cudaFree(ds); cudaFree(dout); cudaFree(dused); cudaFree(dw);
+    return e == cudaSuccess ? 0 : 1;
+}
+
+// ---- cumulative search tap (choose.cuh): one warp per query
+namespace vg {
+__global__ void choose_tap_kernel(const double *w, int n, const double *x, int m, int skip, int small, long long *idx,
+                                  double *before, double *wsel, double *resid) {
+    const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= m) return;
+    const Pick p = small ? small_pick([&](int i) { return i == skip ? 0.0 : w[i]; }, n, x[q])
+                         : warp_pick([&](int i) { return w[i]; }, n, x[q], skip);
+    if ((threadIdx.x & 31) == 0) {
+        idx[q] = p.i;
+        before[q] = p.before;
+        wsel[q] = p.w;
+        resid[q] = p.i >= 0 ? p.resid(x[q]) : -1.0;
+    }
+}
+}  // namespace vg
+
+extern "C" int vgsim_test_choose(const double *w, int n, const double *x, int m, int skip, int small, int64_t *idx,
+                                 double *before, double *wsel, double *resid) {
+    double *dw = nullptr, *dx = nullptr, *db = nullptr, *dws = nullptr, *dr = nullptr;
+    long long *di = nullptr;
+    if (cudaMalloc(&dw, (size_t)(n > 0 ? n : 1) * 8) != cudaSuccess || cudaMalloc(&dx, (size_t)m * 8) != cudaSuccess ||
+        cudaMalloc(&db, (size_t)m * 8) != cudaSuccess || cudaMalloc(&dws, (size_t)m * 8) != cudaSuccess ||
+        cudaMalloc(&dr, (size_t)m * 8) != cudaSuccess || cudaMalloc(&di, (size_t)m * 8) != cudaSuccess)
+        return 1;
+    cudaMemcpy(dw, w, (size_t)n * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(dx, x, (size_t)m * 8, cudaMemcpyHostToDevice);
+    vg::choose_tap_kernel<<<(m + 3) / 4, 128>>>(dw, n, dx, m, skip, small, di, db, dws, dr);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaMemcpy(idx, di, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(before, db, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(wsel, dws, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(resid, dr, (size_t)m * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dw); cudaFree(dx); cudaFree(db); cudaFree(dws); cudaFree(dr); cudaFree(di);
     return e == cudaSuccess ? 0 : 1;
 }
