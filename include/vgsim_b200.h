@@ -76,7 +76,10 @@ int vgsim_upload_params(vgsim_handle h, int pp, const double *b, const double *d
                         const double *contact_density, const double *cd_before, const double *cd_after,
                         const double *startLD, const double *endLD, const double *sampling_multiplier,
                         const int64_t *sizes, const int32_t *cd_reset_mask);
-/* replicate -> parameter point map (default: all 0).  Parameter sweeps (BASELINE config 5). */
+/* replicate -> parameter point map (default: all 0).  Parameter sweeps (BASELINE config 5).  Before the first simulate
+ * call the live contact density of every replicate is (re)seeded from its point's uploaded value, whichever of
+ * vgsim_upload_params / vgsim_set_replicate_params comes first; after it the map may still change, but contact
+ * densities are run state (lockdowns) and are left alone. */
 int vgsim_set_replicate_params(vgsim_handle h, const int32_t *replicate_to_param /*[R]*/);
 
 /* susceptible / infectious compartments (src/_BirthDeath.pyx:150,178; set_susceptible/set_infectious

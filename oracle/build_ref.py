@@ -8,6 +8,7 @@ directory under /tmp, cythonized there, and only the BUILT artefacts land in
 oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun):
 
     oracle/_ref/VGsim/_BirthDeath*.so      the reference engine (src/_BirthDeath.pyx + *.pxi)
+    oracle/_ref/VGsim/{_interface,IO}.pyc  the reference's Python wrapper and writers, byte-compiled (sourceless)
     oracle/_ref/mc_lib/rndm*.so            shim for the un-vendored third-party dependency
     oracle/_ref/{prettytable,tskit,matplotlib}   import stubs (diagnostics only, never called)
 
@@ -37,8 +38,10 @@ def main():
     os.makedirs(pkg)
     for f in ("_BirthDeath.pyx", "fast_choose.pxi", "events.pxi", "models.pxi"):
         shutil.copy(os.path.join(REF, "src", f), pkg)
-    # the engine is driven directly (BirthDeathModel); the pure-Python wrapper of the
-    # reference is not needed and is NOT staged.
+    # the engine is driven directly (BirthDeathModel).  The reference's pure-Python wrapper and writers
+    # (src/_interface.py, src/IO.py) are byte-compiled below into sourceless .pyc files: the parity tests run the
+    # reference's own Simulator class over the new engine (drop-in proof) and its own Newick / TSV writers
+    # (writer parity) on the GPU box, where /root/reference does not exist.
     open(os.path.join(pkg, "__init__.py"), "w").write(
         "from ._BirthDeath import BirthDeathModel\n")
     mc = os.path.join(work, "mc_lib")
@@ -107,6 +110,10 @@ def main():
     for so in glob.glob(os.path.join(pkg, "*.so")):
         shutil.copy(so, os.path.join(OUT, "VGsim"))
     shutil.copy(os.path.join(pkg, "__init__.py"), os.path.join(OUT, "VGsim"))
+    import py_compile
+    for f in ("_interface.py", "IO.py"):
+        py_compile.compile(os.path.join(REF, "src", f), cfile=os.path.join(OUT, "VGsim", f + "c"), dfile="VGsim/" + f,
+                           doraise=True)
     for so in glob.glob(os.path.join(mc, "*.so")):
         shutil.copy(so, os.path.join(OUT, "mc_lib"))
     shutil.copy(os.path.join(mc, "__init__.py"), os.path.join(OUT, "mc_lib"))

@@ -182,3 +182,14 @@ def _t3small(e):
 
 
 SCENARIOS["t3small"] = ((2, 4, 3), _t3small)
+
+
+def _s8hi(e):
+    """Scenario 8 with a mutation rate high enough that sampled lineages carry several mutations per branch (the
+    writers' multiple-mutations-per-node path) and dense sampling."""
+    e.set_mutation_rate(0.6, None, None)
+    e.set_mutation_probabilities([1, 0, 0, 1], None, None)
+    e.set_sampling_rate(0.2, None)
+
+
+SCENARIOS["s8hi"] = ((2, 1, 1), _s8hi)

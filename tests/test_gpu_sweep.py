@@ -65,3 +65,32 @@ def test_sharding_does_not_change_results():
     np.testing.assert_array_equal(whole, halves)
     np.testing.assert_array_equal(whole, thirds)
     assert (whole[:, :, 10] == 12).any() and (whole[:, :, 13] > 1).any()   # leaps were taken, trees were built
+
+
+def test_contact_density_follows_the_parameter_point():
+    """A sweep over contact density: every replicate's LIVE contact density is its own point's, in either order of
+    vgsim_upload_params / vgsim_set_replicate_params (round-1 advisor finding: the upload seeded only replicates already
+    mapped to the point, so points 1.. never reached the device when the map came last)."""
+    from vgsim_b200 import _capi
+    dims, setup = SCENARIOS[NAME]
+    cds = [0.4, 0.9, 1.7, 2.5]
+
+    def mk(cd):
+        return lambda e: e.set_contact_density(float(cd), None)
+    sw = Sweep(dims, setup, [mk(c) for c in cds], replicates_per_point=5, seed=3)
+    _, _, cd, lock = sw.h.get_state(full=True)
+    assert np.array_equal(cd, np.repeat(np.asarray(cds), 5)[:, None] * np.ones((1, dims[1])))
+    # the other order, straight through the C ABI: uploads first, map last
+    U, K, S = dims
+    e = Eng(U, K, S, 1, False, False, int(1e6), 0.0)
+    setup(e)
+    h = _capi.Handle(U, K, S, 8, 2, None)
+    for pp, c in enumerate((0.3, 2.2)):
+        e.set_contact_density(c, None)
+        h.upload_params(pp, e.param_arrays())
+    h.set_replicate_params(np.array([0, 1, 1, 0, 1, 0, 0, 1], np.int32))
+    _, _, cd, _ = h.get_state(full=True)
+    assert np.array_equal(cd[:, 0], np.where(np.array([0, 1, 1, 0, 1, 0, 0, 1]) == 1, 2.2, 0.3))
+    # and the rates the kernels use follow: the direct-method birth rate scales with the contact density
+    r0, r1 = h.rates(0)["ev"][0, 0, 0], h.rates(1)["ev"][0, 0, 0]
+    assert abs(r1 / r0 - 2.2 / 0.3) < 1e-9

@@ -23,13 +23,18 @@ from . import _params as P
 _GENOME_TEXT = ('Incorrect value of number of sites or genome length. Genome length should be more or equal number of sites.')
 
 
-def _refuse_recombination(probability):
+_RECOMB_TEXT = ('recombination / coinfection (recombination_probability > 0) is out of scope of the device path: the forward '
+                'kernels do not generate recombinant births')
+
+
+def _warn_recombination(probability):
     """The reference's Birth() takes its recombination branch whenever rn < recombination_probability
-    (src/_BirthDeath.pyx:575-596); that experimental branch (logs one haplotype, infects another, ignored by
-    the genealogy) is not part of the device path, so a non-zero probability is refused instead of silently ignored."""
+    (src/_BirthDeath.pyx:575-596).  That experimental branch (logs one haplotype, infects another, ignored by
+    the genealogy) is not part of the device path.  The value is stored (the reference's interface tests read it back),
+    setting it warns, and simulate() refuses to run with it instead of silently producing a non-recombinant run."""
     if probability > 0:
-        raise NotImplementedError('recombination / coinfection (recombination_probability > 0) is out of scope of the '
-                                  'device path: the forward kernels do not generate recombinant births')
+        import warnings
+        warnings.warn(_RECOMB_TEXT + '; simulate() will raise NotImplementedError', stacklevel=3)
 
 
 BIRTH, DEATH, SAMPLING, MUTATION, SUSCCHANGE, MIGRATION, MULTITYPE = range(7)  # src/events.pxi:2-8
@@ -59,7 +64,7 @@ class BirthDeathModel:
         self._sites_axis = P.Axis(self.sites, 'mutation site')
 
         self.recombination = P.quantity(recombination_probability, 'recombination probability', upper=1)
-        _refuse_recombination(recombination_probability)
+        _warn_recombination(recombination_probability)
         self._genome_length = P.count(genome_length, 'genome length')
         self.sitesPosition = np.zeros(self.sites, dtype=np.int64)
         if self.sites > self._genome_length:
@@ -191,7 +196,7 @@ class BirthDeathModel:
 
     def set_coinfection_parameters(self, recombination):
         self.recombination = P.quantity(recombination, 'recombination probability', upper=1)
-        _refuse_recombination(recombination)
+        _warn_recombination(recombination)
 
     def set_transmission_rate(self, rate, haplotype):
         P.quantity(rate, 'transmission rate')
@@ -378,6 +383,8 @@ class BirthDeathModel:
         return self._handle
 
     def _sync_params(self):
+        if self.recombination > 0:
+            raise NotImplementedError(_RECOMB_TEXT)
         h = self._ensure_handle()
         if self._dirty:
             # only demes addressed by set_contact_density since the last upload have their LIVE density overwritten
@@ -582,11 +589,10 @@ class BirthDeathModel:
     def export_migrations(self, name_file, file_path, replicate=0):
         self._require_tree()
         node, t, oldp, newp = self._handle.get_migrations(replicate)
+        from . import io as _io
         fn = (file_path + '/' if file_path is not None else '') + name_file + '.tsv'
         with open(fn, 'w') as f:
-            f.write("Node\tTime\tOld_population\tNew_population\n")
-            for i in range(len(node)):
-                f.write(str(int(node[i])) + '\t' + str(float(t[i])) + '\t' + str(int(oldp[i])) + '\t' + str(int(newp[i])) + "\n")
+            f.writelines(_io.migration_lines(node, t, oldp, newp))
 
     def output_sample_data(self, replicate=0):
         ev = self.get_chain_events(replicate)

@@ -157,13 +157,28 @@ int vgsim_set_seeds(vgsim_handle h, const uint64_t *seeds) {
     return 0;
 }
 
+__global__ void seed_cd_kernel(DevState st) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= st.R * st.D.K) return;
+    int r = i / st.D.K, p = i - r * st.D.K;
+    st.cd[i] = st.params[(size_t)st.rep_pp[r] * st.D.blob + st.D.o_cd0 + p];
+}
+
 int vgsim_set_replicate_params(vgsim_handle h, const int32_t *map) {
     for (int r = 0; r < h->R; r++)
         if (map[r] < 0 || map[r] >= h->n_pp) return fail("replicate_to_param entry out of range");
     CK(cudaSetDevice(h->device));
     CK(cudaMemcpyAsync((void *)h->st.rep_pp, map, (size_t)h->R * 4, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
     h->rep_pp_host.assign(map, map + h->R);
+    // Before the first simulation the live contact density of every replicate follows its (new) parameter point, so the
+    // order of vgsim_upload_params and vgsim_set_replicate_params does not matter; afterwards it is run state (a deme
+    // may be in lockdown) and is left alone.
+    if (!h->st.first_simulation) {
+        seed_cd_kernel<<<(h->R * h->D.K + 255) / 256, 256, 0, h->stream>>>(h->st);
+        h->launches++;
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -80,6 +80,7 @@ __device__ __forceinline__ Pick small_pick(WF wf, int n, double x) {
     out.i = last.i = -1;
     out.before = out.w = last.before = last.w = 0.0;
     double acc = 0.0;
+#pragma unroll
     for (int i = 0; i < n; i++) {
         const double w = wf(i);
         if (w > 0.0) {

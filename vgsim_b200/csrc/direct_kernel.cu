@@ -130,20 +130,26 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // Q[p,h] = sum_s Sx[p,s] sigma[s,h]: the susceptible pressure on haplotype h in deme p (inner sum of BirthRate, :382-392)
+// SC: the number of susceptibility groups when it is a compile-time constant (1..4: the loops over groups unroll and
+// their address arithmetic folds), 0: taken from D at run time.
+template <int SC>
 __device__ __forceinline__ double dir_Q(const Dims &D, const DirShared &s, int p, int h) {
+    const int S = SC > 0 ? SC : D.S;
     double Q = 0.0;
-    for (int sn = 0; sn < D.S; sn++) Q += s.Sx[p * D.S + sn] * s.sig[sn * D.H + h];
+#pragma unroll
+    for (int sn = 0; sn < S; sn++) Q += s.Sx[p * S + sn] * s.sig[sn * D.H + h];
     return Q;
 }
 
 // hapPopRate[p,:] and its sum from the current compartments (UpdateRates(pi, infect=True), :516-546); every lane
 // returns infectPopRate[p].  Ends without a barrier: the caller syncs before anyone reads hp.
+template <int SC>
 __device__ __forceinline__ double dir_refresh_hp(const Dims &D, const DirShared &s, int p) {
     const int lane = threadIdx.x & 31, H = D.H;
     const double cp = s.c[p];
     double acc = 0.0;
     for (int h = lane; h < H; h += 32) {
-        const double te = s.b[h] * (dir_Q(D, s, p, h) * cp) + s.base[p * H + h];
+        const double te = s.b[h] * (dir_Q<SC>(D, s, p, h) * cp) + s.base[p * H + h];
         const double v = te * s.I[p * H + h];
         s.hp[p * H + h] = v;
         acc += v;
@@ -151,9 +157,12 @@ __device__ __forceinline__ double dir_refresh_hp(const Dims &D, const DirShared 
     return warp_sum(acc);
 }
 
+template <int SC>
 __device__ __forceinline__ double dir_imm(const Dims &D, const DirShared &s, int p) {
+    const int S = SC > 0 ? SC : D.S;
     double im = 0.0;
-    for (int sn = 0; sn < D.S; sn++) im += s.Tc[sn] * s.Sx[p * D.S + sn];
+#pragma unroll
+    for (int sn = 0; sn < S; sn++) im += s.Tc[sn] * s.Sx[p * S + sn];
     return im;
 }
 
@@ -174,6 +183,7 @@ __device__ __forceinline__ void dir_totals(const Dims &D, const DirShared &s, do
 
 // everything derived from the compartments (UpdateAllRates, :279-351, state-dependent part): per-deme totals, hp, inf,
 // imm, pr, the totals and globalInfectious
+template <int SC>
 __device__ __forceinline__ void dir_refresh_all(const Dims &D, const DirShared &s, double &Rt, double &A, double &B,
                                                 double &ginf) {
     const int lane = threadIdx.x & 31, K = D.K, H = D.H, S = D.S;
@@ -185,8 +195,8 @@ __device__ __forceinline__ void dir_refresh_all(const Dims &D, const DirShared &
         for (int sn = lane; sn < S; sn += 32) ts += s.Sx[p * S + sn];
         ti = warp_sum(ti);
         ts = warp_sum(ts);
-        const double inf = dir_refresh_hp(D, s, p);
-        const double imm = dir_imm(D, s, p);
+        const double inf = dir_refresh_hp<SC>(D, s, p);
+        const double imm = dir_imm<SC>(D, s, p);
         if (lane == 0) {
             s.totInf[p] = ti;
             s.totSus[p] = ts;
@@ -202,11 +212,12 @@ __device__ __forceinline__ void dir_refresh_all(const Dims &D, const DirShared &
 }
 
 // 16 warps per CTA (one CTA per SM): the event loop is one dependent chain per replicate
+template <int SC>
 __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ DevState st, const __grid_constant__ SimArgs a,
                                                          const __grid_constant__ DirLayout L, int *work) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Dims &D = st.D;
-    const int K = D.K, H = D.H, S = D.S, U = D.U;
+    const int K = D.K, H = D.H, S = SC > 0 ? SC : D.S, U = D.U;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     DirShared s;
     dir_carve(s, L, smem_raw, wib);
@@ -251,7 +262,7 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
             continue;
         }
         double Rt, mA, mB, ginf;
-        dir_refresh_all(D, s, Rt, mA, mB, ginf);
+        dir_refresh_all<SC>(D, s, Rt, mA, mB, ginf);
 
         long long cB = ctr[C_B], cD = ctr[C_D], cS = ctr[C_S], cM = ctr[C_M], cI = ctr[C_I], cGp = ctr[C_MIGP],
                   cGn = ctr[C_MIGN];
@@ -282,10 +293,14 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
             unsigned long long iter = 0;
             double Rm = K > 1 ? fmax(ginf * mA - mB, 0.0) : 0.0;
             if (Rt + Rm != 0.0 && ginf != 0.0) {
+                // the Philox block of iteration i+1 is computed at the top of iteration i: it depends on nothing, so its
+                // 10-round integer chain interleaves with the fp64 chain (log, division, scans) of the current event
+                uint4 wnext = philox4x32_10(make_uint4(0u, 0u, epoch, 0x44495245u), key);
                 while (evptr < ev_limit && (a.sample_size == -1 || cS <= a.sample_size) && (!a.has_time || t < (double)a.time)) {
                     // ---- SampleTime + GenerateEvent (:476-512): two uniforms per iteration
-                    const uint4 w = philox4x32_10(make_uint4((uint32_t)iter, (uint32_t)(iter >> 32), epoch, 0x44495245u), key);
+                    const uint4 w = wnext;
                     iter++;
+                    wnext = philox4x32_10(make_uint4((uint32_t)iter, (uint32_t)(iter >> 32), epoch, 0x44495245u), key);
                     if ((iter & 1023ull) == 0) {  // bound the drift of the incremental totals
                         dir_totals(D, s, Rt, mA, mB);
                         Rm = K > 1 ? fmax(ginf * mA - mB, 0.0) : 0.0;
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
                             const double z = ph.rest(y);  // in [0, hapPopRate[p,h]) = tEventHapPopRate * I
                             const double Ih = s.I[p * H + h];
                             const double bc = s.b[h] * s.c[p];
-                            const double Q = dir_Q(D, s, p, h);
+                            const double Q = dir_Q<SC>(D, s, p, h);
                             // eventHapPopRate[p,h,0:4] (:310-314) times the cell's count
                             const double e0 = s.b[h] * (Q * s.c[p]) * Ih, e1 = s.d[h] * Ih, e2 = s.sr[h] * s.sm[p] * Ih,
                                          e3 = s.tm[h] * Ih;
@@ -443,8 +458,8 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
                         // ---- UpdateRates (:516-546): the touched deme, then the totals by increments
                         __syncwarp();
                         const int p = touched;
-                        const double inf = dir_refresh_hp(D, s, p);
-                        const double imm = dir_imm(D, s, p);
+                        const double inf = dir_refresh_hp<SC>(D, s, p);
+                        const double imm = dir_imm<SC>(D, s, p);
                         const double pr_old = s.pr[p];
                         __syncwarp();
                         if (lane == 0) {
@@ -485,7 +500,7 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
                                 swaps += flips;
                                 __syncwarp();
                                 update_contact_rates(WarpGroup(), D, pp, s.cd, eff, s.c, s.maxEBM);
-                                dir_refresh_all(D, s, Rt, mA, mB, ginf);
+                                dir_refresh_all<SC>(D, s, Rt, mA, mB, ginf);
                                 Rm = K > 1 ? fmax(ginf * mA - mB, 0.0) : 0.0;
                             }
                         }
@@ -503,7 +518,7 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
                 __syncwarp();
                 for (int i = lane; i < K * H; i += 32) s.I[i] = (double)st.initI[(size_t)r * K * H + i];
                 for (int i = lane; i < K * S; i += 32) s.Sx[i] = (double)st.initSx[(size_t)r * K * S + i];
-                dir_refresh_all(D, s, Rt, mA, mB, ginf);
+                dir_refresh_all<SC>(D, s, Rt, mA, mB, ginf);
                 int flips = 0;
                 if (lane == 0)
                     for (int p = 0; p < K; p++)
@@ -514,7 +529,7 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
                     swaps += flips;
                     __syncwarp();
                     update_contact_rates(WarpGroup(), D, pp, s.cd, eff, s.c, s.maxEBM);
-                    dir_refresh_all(D, s, Rt, mA, mB, ginf);
+                    dir_refresh_all<SC>(D, s, Rt, mA, mB, ginf);
                 }
                 good_attempt = 0;
             } else {
@@ -569,11 +584,11 @@ __global__ void rates_tap_kernel(const __grid_constant__ DevState st, const __gr
     }
     __syncwarp();
     double Rt, A, B, ginf;
-    dir_refresh_all(D, s, Rt, A, B, ginf);
+    dir_refresh_all<0>(D, s, Rt, A, B, ginf);
     __syncwarp();
     for (int i = lane; i < K * H; i += 32) {
         const int p = i / H, h = i - p * H;
-        ev[i * 4 + 0] = s.b[h] * (dir_Q(D, s, p, h) * s.c[p]);
+        ev[i * 4 + 0] = s.b[h] * (dir_Q<0>(D, s, p, h) * s.c[p]);
         ev[i * 4 + 1] = s.d[h];
         ev[i * 4 + 2] = s.sr[h] * s.sm[p];
         ev[i * 4 + 3] = s.tm[h];
@@ -596,14 +611,17 @@ __global__ void rates_tap_kernel(const __grid_constant__ DevState st, const __gr
 cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int uniform_pp, int *work) {
     DirLayout L = dir_layout(st.D, uniform_pp >= 0, uniform_pp >= 0 ? uniform_pp : 0, 227 * 1024, 16);
     if (L.nwarps < 1) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    const void *kern = st.D.S == 1 ? (const void *)direct_kernel<1> : st.D.S == 2 ? (const void *)direct_kernel<2>
+                     : st.D.S == 3 ? (const void *)direct_kernel<3> : st.D.S == 4 ? (const void *)direct_kernel<4>
+                                                                                  : (const void *)direct_kernel<0>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(work, 0, sizeof(int), stream);
     if (e != cudaSuccess) return e;
     int grid = (st.R + L.nwarps - 1) / L.nwarps;
     if (grid > num_sms) grid = num_sms;
-    direct_kernel<<<grid, L.nwarps * 32, L.total_bytes, stream>>>(st, a, L, work);
-    return cudaGetLastError();
+    void *args[] = {(void *)&st, (void *)&a, (void *)&L, (void *)&work};
+    return cudaLaunchKernel(kern, dim3(grid), dim3(L.nwarps * 32), args, L.total_bytes, stream);
 }
 
 cudaError_t launch_rates_tap(const DevState &st, int r, double *ev, double *hp, double *popRate, double *migPop,

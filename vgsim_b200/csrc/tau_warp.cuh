@@ -19,6 +19,17 @@
 // parity tap (variant bit 2 / VGSIM_TAU_KERNEL=team).
 #pragma once
 
+// compile-time A/B switches (defaults = the product; scripts/build_variant.sh builds the alternatives)
+#ifndef TW_B1B_ENUM
+#define TW_B1B_ENUM 1   // 0: dense pass over all K x H cells for the empty-cell drifts
+#endif
+#ifndef TW_PARK
+#define TW_PARK 1       // 0: split every drain round's totals at once
+#endif
+#ifndef TW_WIPE_CLEAR
+#define TW_WIPE_CLEAR 1 // the next row's wipe is also spread over the loop that clears the per-leap deltas (0: A/B)
+#endif
+
 namespace vg {
 
 
@@ -95,8 +106,8 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     if (L.use_masks) L.w_colcnt = L.w_colmask;  // "present anywhere" is colmask != 0 on the mask path
     else take(L.w_colcnt, H * 4, 4);
     take(L.w_hlist, H * 4, 4);
-    take(L.w_qhi, L.qcap * 4, 4); take(L.w_qoc, L.qcap * 4, 4); take(L.w_xq, 2 * L.xcap * 4, 4);
-    take(L.w_sqp, 2 * 64 * 4, 4);  // parked totals: (owner | kind, n) pairs, TW_SQCAP of them
+    take(L.w_qhi, L.qcap * 4, 4); take(L.w_qoc, L.qcap * 4, 4); take(L.w_xq, 2 * L.xcap * 2, 4);  // uint16 cell ids
+    take(L.w_sqp, 64 * 4, 4);  // parked totals: owner | kind | n in one word, TW_SQCAP of them
     take(L.w_cnt, 8 * 4, 4);
     take(L.w_hidx, H * 2, 2);
     const int fixed_bytes = (o + 15) & ~15;
@@ -182,8 +193,8 @@ struct WS {
     WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp;
     WIval I;
     WQval Qm;
-    WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, xq, sqp, cnt;
-    WArr<unsigned short> act, hidx;
+    WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, sqp, cnt;
+    WArr<unsigned short> act, hidx, xq;
     WArr<double> qtab, qlam;
     int qtab_cap;
     WArr<long long> tally64;
@@ -213,7 +224,7 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     s.Iraw = Wi(L.w_I); s.I.raw = s.Iraw;
     s.chkI = Wi(L.w_chk); s.updI = Wi(L.w_upd); s.act.off = wb + L.w_act; s.act.scale = ws; s.dSx = Wi(L.w_dSx); s.lock = Wi(L.w_lock);
     s.tot = Wi(L.w_tot); s.dstart = Wi(L.w_dstart); s.colcnt = Wi(L.w_colcnt); s.colmask = Wi(L.w_colmask);
-    s.hlist = Wi(L.w_hlist); s.qhi = Wi(L.w_qhi); s.qoc = Wi(L.w_qoc); s.xq = Wi(L.w_xq); s.sqp = Wi(L.w_sqp); s.cnt = Wi(L.w_cnt);
+    s.hlist = Wi(L.w_hlist); s.qhi = Wi(L.w_qhi); s.qoc = Wi(L.w_qoc); s.xq.off = wb + L.w_xq; s.xq.scale = ws; s.sqp = Wi(L.w_sqp); s.cnt = Wi(L.w_cnt);
     s.tally64.off = wb + L.w_tally; s.tally64.scale = ws;
     s.q.slot = s.tally64; s.q.o_q = D.o_q;
     s.hidx.off = wb + L.w_hidx; s.hidx.scale = ws;
@@ -547,46 +558,63 @@ __device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WSQ &s, 
     //           contributes at most qmax * I[p,src].  So only the neighbours of "big" cells (qmax * I * 3U >= 1) have to be
     //           looked at -- a handful of (cell, neighbour) pairs instead of a pass over all K x H cells; skipping the rest
     //           is exact (their proposal is >= 1 and tau = min(1, ...)).  Pairs reached twice just repeat a candidate.
+    // Sparse states (few infectious cells) enumerate; dense ones (measured: from ~1/8 of the cells on) are cheaper with
+    // the plain pass over all K x H cells, which is skipped when qmax * (deme prevalence) < 1 in every deme.
+    if (TW_B1B_ENUM && nAct * 8 <= K * H) {
     dense_pass = false;
-    {
-        const int U = D.U, n3 = 3 * U;
-        const int per = n3 > 0 ? 32 / n3 : 0;  // big cells handled per round
-        const double q3 = s.qmax[0] * (double)n3;
-        if (per > 0) {
+        {
+            const int U = D.U, n3 = 3 * U;
+            const int per = n3 > 0 ? 32 / n3 : 0;  // big cells handled per round
+            const double q3 = s.qmax[0] * (double)n3;
+            if (per > 0) {
 #pragma unroll 1
-            for (int base = 0; base < nAct; base += 32) {
-                const int a = base + lane;
-                const int cell = a < nAct ? (int)s.act[a] : 0;
-                const bool big = a < nAct && q3 * s.I[cell] >= 0.999;
-                unsigned bm = __ballot_sync(0xffffffffu, big);
+                for (int base = 0; base < nAct; base += 32) {
+                    const int a = base + lane;
+                    const int cell = a < nAct ? (int)s.act[a] : 0;
+                    const bool big = a < nAct && q3 * s.I[cell] >= 0.999;
+                    unsigned bm = __ballot_sync(0xffffffffu, big);
 #pragma unroll 1
-                while (bm) {
-                    // this round's big cells: the first `per` set bits
-                    const int slot = lane / n3, j = lane - slot * n3;
-                    unsigned m = bm;
-                    for (int k = 0; k < slot && m; k++) m &= m - 1;
-                    const int src_lane = m ? __ffs(m) - 1 : 0;
-                    const int bc = __shfl_sync(0xffffffffu, cell, src_lane);
-                    if (m && slot < per) {
-                        const int p = bc >> D.hshift, h = bc & (H - 1);
+                    while (bm) {
+                        // this round's big cells: the first `per` set bits
+                        const int slot = lane / n3, j = lane - slot * n3;
+                        unsigned m = bm;
+                        for (int k = 0; k < slot && m; k++) m &= m - 1;
+                        const int src_lane = m ? __ffs(m) - 1 : 0;
+                        const int bc = __shfl_sync(0xffffffffu, cell, src_lane);
+                        if (m && slot < per) {
+                            const int p = bc >> D.hshift, h = bc & (H - 1);
+                            const int u = j / 3, al = 1 + (j - u * 3);
+                            const int hn = h ^ (al << (2 * u));
+                            if (s.colcnt[hn] == 0) candidate(drift_I_cell(p * H + hn, D, s, eff), 0.0);
+                        }
+                        for (int k = 0; k < per && bm; k++) bm &= bm - 1;
+                    }
+                }
+            } else if (U > 0) {  // more than 10 sites: one big cell per round, its neighbours strided over the lanes
+#pragma unroll 1
+                for (int a = 0; a < nAct; a++) {
+                    const int bc = s.act[a];
+                    if (!(q3 * s.I[bc] >= 0.999)) continue;
+                    const int p = bc >> D.hshift, h = bc & (H - 1);
+                    for (int j = lane; j < n3; j += 32) {
                         const int u = j / 3, al = 1 + (j - u * 3);
                         const int hn = h ^ (al << (2 * u));
                         if (s.colcnt[hn] == 0) candidate(drift_I_cell(p * H + hn, D, s, eff), 0.0);
                     }
-                    for (int k = 0; k < per && bm; k++) bm &= bm - 1;
                 }
             }
-        } else if (U > 0) {  // more than 10 sites: one big cell per round, its neighbours strided over the lanes
+        }
+    } else {
+    int need = 0;
 #pragma unroll 1
-            for (int a = 0; a < nAct; a++) {
-                const int bc = s.act[a];
-                if (!(q3 * s.I[bc] >= 0.999)) continue;
-                const int p = bc >> D.hshift, h = bc & (H - 1);
-                for (int j = lane; j < n3; j += 32) {
-                    const int u = j / 3, al = 1 + (j - u * 3);
-                    const int hn = h ^ (al << (2 * u));
-                    if (s.colcnt[hn] == 0) candidate(drift_I_cell(p * H + hn, D, s, eff), 0.0);
-                }
+        for (int p = lane; p < K; p += 32) need |= s.qmax[0] * (double)s.tot[p] >= 0.999;
+        dense_pass = __any_sync(0xffffffffu, need) != 0;
+        if (dense_pass) {
+#pragma unroll 1
+            for (int i = lane; i < K * H; i += 32) {
+                wp.some(wk, n32);
+                if (s.colcnt[i & (H - 1)] != 0) continue;
+                candidate(drift_I_cell(i, D, s, eff), 0.0);
             }
         }
     }
@@ -763,9 +791,7 @@ __device__ __forceinline__ int tw_split_event(int owner, int kind, int e, const 
 //     non-zero is parked as a (owner | kind, n) pair, and the pairs are split 32 at a time -- as soon as 32 are there,
 //     and the rest when the leap's last drain runs (`final`) -- so that the split walks run with the lanes full
 //     (they ran with 1.5 of 32 lanes when every drain split its own few totals, ncu profiles/r2_c_*);
-//   * PTRS entries in two passes: trial 0 with the quick acceptance test for everybody (~87 % are done), then the
-//     complete sampler (same trials, same result) for the rest, compacted -- the slow acceptance test with its three
-//     logarithms no longer runs with a couple of lanes per round.
+//   * PTRS entries in rounds of 32, one inlined copy of the sampler.
 #define TW_SQCAP 64
 template <class WSQ>
 __device__ __forceinline__ void w_drain(int *row, const Dims &D, const WSQ &s, const double *eff, const DrawGeom &g,
@@ -801,26 +827,24 @@ __device__ __forceinline__ void w_drain(int *row, const Dims &D, const WSQ &s, c
             }
             const bool park = tot && n != 0;
             const unsigned pm = __ballot_sync(0xffffffffu, park);
-            if (park) {
+            if (park) {  // one word: owner | kind << 20 | n << 21 (n < 256: the inversion sampler's cap)
                 const int e = q.nsq + __popc(pm & lt);
-                s.sqp[2 * e] = (int)oc;
-                s.sqp[2 * e + 1] = n;
+                s.sqp[e] = (int)((unsigned)owner | (l == TW_L_TOT_MIG ? 1u << 20 : 0u) | ((unsigned)n << 21));
             }
             q.nsq += __popc(pm);
             __syncwarp();
         }
         // split one round of parked totals (taken from the end of the list)
-        if (q.nsq >= 32 || (!more && final && q.nsq > 0)) {
+        if (q.nsq >= (TW_PARK ? 32 : 1) || (!more && final && q.nsq > 0)) {
             const int take = q.nsq < 32 ? q.nsq : 32;
             const int e = q.nsq - take + lane;
             const bool valid = lane < take;
-            const unsigned oc = valid ? (unsigned)s.sqp[2 * e] : 0u;
-            const int ns = valid ? s.sqp[2 * e + 1] : 0;
-            const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
+            const unsigned pw = valid ? (unsigned)s.sqp[e] : 0u;
+            const int owner = (int)(pw & 0xfffffu), kind = (pw >> 20) & 1u ? 3 : 2, ns = (int)(pw >> 21);
 #pragma unroll 1
             for (int ev = 0; __any_sync(0xffffffffu, ev < ns); ev++) {
                 if (ev < ns) {
-                    const int ls = tw_split_event(owner, l == TW_L_TOT_MUT ? 2 : 3, ev, D, s, eff, g, ctx);
+                    const int ls = tw_split_event(owner, kind, ev, D, s, eff, g, ctx);
                     if (ls >= 0) {
                         Channel ch;
                         const int c = tw_channel_ids(owner, ls, D, s, L, ch);
@@ -834,42 +858,14 @@ __device__ __forceinline__ void w_drain(int *row, const Dims &D, const WSQ &s, c
         }
         if (!more && !(final && q.nsq > 0)) break;
     }
-    // ---- PTRS entries (lambda >= 10) sit at the top of the queue.  Pass 1: trial 0, quick acceptance only; the others
-    //      leave their entry index in the (otherwise unused) word slot of the queue's top, compacted
-    int nfail = 0;
+    // ---- PTRS entries (lambda >= 10) sit at the top of the queue.  (A two-pass variant -- trial 0 with the quick
+    //      acceptance test for everybody, then the complete sampler for the compacted rest -- measured SLOWER: 15.8 vs
+    //      13.8 ms at t = 90, gpurun r2_e: the second pass repeats trial 0 and the queue traffic outweighs the lanes won.)
 #pragma unroll 1
     for (int k0 = 0; k0 < q.nptr; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < q.nptr;
         const int e = s.qcap - 1 - k;
-        const double lam = valid ? s.qlam[e] : 100.0;
-        const unsigned oc = valid ? (unsigned)s.qoc[e] : 0u;
-        const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
-        int dom, qq;
-        tw_addr(owner, l, D, g, dom, qq);
-        ctx.c0 = (uint32_t)owner;
-        ctx.dom0 = (uint32_t)dom;
-        long long kq = 0;
-        const bool ok = valid && poisson_ptrs_quick(lam, ctx, qq, kq);
-        if (ok && kq != 0) {
-            Channel ch;
-            const int c = tw_channel_ids(owner, l, D, s, L, ch);
-            row[c] = (int)kq;
-            book(ch, (int)kq, s, tr);
-        }
-        const bool fail = valid && !ok;
-        const unsigned fm = __ballot_sync(0xffffffffu, fail);
-        __syncwarp();  // every lane has read its queue words before the slots below are reused
-        if (fail) s.qhi[s.qcap - 1 - (nfail + __popc(fm & lt))] = e;
-        nfail += __popc(fm);
-    }
-    __syncwarp();
-    // ---- pass 2: the complete sampler for the entries trial 0 did not settle
-#pragma unroll 1
-    for (int k0 = 0; k0 < nfail; k0 += 32) {
-        const int k = k0 + lane;
-        const bool valid = k < nfail;
-        const int e = valid ? s.qhi[s.qcap - 1 - k] : s.qcap - 1;
         const double lam = valid ? s.qlam[e] : 100.0;
         const unsigned oc = valid ? (unsigned)s.qoc[e] : 0u;
         const int owner = (int)(oc & 0xfffffu), l = (int)(oc >> 20);
@@ -995,11 +991,11 @@ __device__ __forceinline__ int w_round(int item, int mode, int nAct, double tau,
         const bool xg = kind == 0 && lam[3] > 0.0 && ((variant & 1) || lam[3] > TAU_THETA_MIG);
         const unsigned bm = __ballot_sync(0xffffffffu, xm), bg = __ballot_sync(0xffffffffu, xg);
         if (xm) {
-            s.xq[q.nxm + __popc(bm & lt)] = owner;
+            s.xq[q.nxm + __popc(bm & lt)] = (unsigned short)owner;
             lam[2] = 0.0;
         }
         if (xg) {
-            s.xq[TW_XCAP + q.nxg + __popc(bg & lt)] = owner;
+            s.xq[TW_XCAP + q.nxg + __popc(bg & lt)] = (unsigned short)owner;
             lam[3] = 0.0;
         }
         q.nxm += __popc(bm);
@@ -1247,7 +1243,7 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                     }
                     bool dense_pass;
                     double tau = w_drifts_and_tau(D, s, eff, nhap, nAct, wp, wk, n32, dense_pass);
-                    const int wkl = dense_pass ? wk : wk2;  // the empty-cell drift pass was skipped: its share of the wipe moves on
+                    const int wkl = TW_WIPE_CLEAR ? 1 : (dense_pass ? wk : wk2);  // the empty-cell drift pass was skipped: its share of the wipe moves on
                     TW_MARK(1)
                     if (meet && (gsync & 2)) TW_GEN_SYNC();
                     if (prof && lane == 0) tmark = clock64();
@@ -1259,7 +1255,10 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                             int4 *z = reinterpret_cast<int4 *>(s.chkI.ptr());
                             const int n16 = (int)((s.updI.off - s.chkI.off) + KH * 4 + 15) >> 4;
 #pragma unroll 1
-                            for (int i = lane; i < n16; i += 32) z[i] = make_int4(0, 0, 0, 0);
+                            for (int i = lane; i < n16; i += 32) {
+                                z[i] = make_int4(0, 0, 0, 0);
+                                if (TW_WIPE_CLEAR) wp.some(1, n32);
+                            }
 #pragma unroll 1
                             for (int i = lane; i < KS; i += 32) s.dSx[i] = 0;
                         }

@@ -108,6 +108,15 @@ def mutation_lines(mut, len_prufer):
     return lines
 
 
+def migration_lines(node, time, old_pop, new_pop):
+    """Lines of migrations.tsv (reference export_migrations, src/_BirthDeath.pyx:1743-1754): header, then one
+    'node<TAB>time<TAB>old deme<TAB>new deme' row per Migrations record, the time printed as Python prints a float."""
+    lines = ["Node\tTime\tOld_population\tNew_population\n"]
+    for i in range(len(node)):
+        lines.append(str(int(node[i])) + '\t' + str(float(time[i])) + '\t' + str(int(old_pop[i])) + '\t' + str(int(new_pop[i])) + "\n")
+    return lines
+
+
 def writeMutations(mut, len_prufer, name_file, file_path):
     fn = (file_path + '/' if file_path is not None else '') + name_file + ".tsv"
     with open(fn, 'w') as f:

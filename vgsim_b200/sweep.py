@@ -27,13 +27,14 @@ class Sweep:
         self.engine = BirthDeathModel(U, K, S, seed, False, False, int(1e6), 0.0)   # host-side validation + arrays only
         base_setup(self.engine)
         self.h = _capi.Handle(U, K, S, self.R, n_pts, device)
+        # the map first: an upload seeds the live contact density of the replicates that are mapped to its point
+        self.h.set_replicate_params(np.repeat(np.arange(n_pts, dtype=np.int32), self.rpp))
         for i in range(n_pts):
             e = self.engine
             saved = {k: v.copy() for k, v in e.param_arrays().items()}
             points[self.lo + i](e)
             self.h.upload_params(i, e.param_arrays())
             self._restore(e, saved)
-        self.h.set_replicate_params(np.repeat(np.arange(n_pts, dtype=np.int32), self.rpp))
         gid = np.arange(self.lo * self.rpp, self.hi * self.rpp, dtype=np.uint64)
         self.h.set_seeds((np.uint64(seed) + gid).astype(np.uint64))
         Sx, I = self.engine._susceptible, self.engine._infectious
