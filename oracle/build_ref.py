@@ -8,7 +8,7 @@ directory under /tmp, cythonized there, and only the BUILT artefacts land in
 oracle/_ref/ (git-ignored, but shipped to the GPU box by gpurun):
 
     oracle/_ref/VGsim/_BirthDeath*.so      the reference engine (src/_BirthDeath.pyx + *.pxi)
-    oracle/_ref/VGsim/{_interface,IO}.pyc  the reference's Python wrapper and writers, byte-compiled (sourceless)
+    oracle/_ref/VGsim/{_interface,IO}.pyc.bin  the reference's Python wrapper and writers, byte-compiled (sourceless)
     oracle/_ref/mc_lib/rndm*.so            shim for the un-vendored third-party dependency
     oracle/_ref/{prettytable,tskit,matplotlib}   import stubs (diagnostics only, never called)
 
@@ -112,7 +112,8 @@ def main():
     shutil.copy(os.path.join(pkg, "__init__.py"), os.path.join(OUT, "VGsim"))
     import py_compile
     for f in ("_interface.py", "IO.py"):
-        py_compile.compile(os.path.join(REF, "src", f), cfile=os.path.join(OUT, "VGsim", f + "c"), dfile="VGsim/" + f,
+        # stored as *.pyc.bin: file-sync tools (the GPU-box snapshot among them) tend to drop *.pyc
+        py_compile.compile(os.path.join(REF, "src", f), cfile=os.path.join(OUT, "VGsim", f + "c.bin"), dfile="VGsim/" + f,
                            doraise=True)
     for so in glob.glob(os.path.join(mc, "*.so")):
         shutil.copy(so, os.path.join(OUT, "mc_lib"))

@@ -1,9 +1,18 @@
 #!/usr/bin/env python
-"""One GPU's share of BASELINE.json configs[4]: the R0 x migration sweep of SURVEY §8(d) config 5 -- 256 x 256 grid,
-model of config 4 with K = 10, one replicate per point, 8,192 points per GPU (rank `r` of 8 takes rows 32r..32r+31
-of the R0 grid).  Direct method for `iters` events, then `leaps` tau leaps, genealogy, summaries.  One JSON line.
+"""BASELINE.json configs[4]: the R0 x migration sweep of SURVEY 8(d) config 5 -- 256 x 256 grid = 65,536 parameter
+points, model of config 4 with K = 10, one replicate per point, sharded over the ranks (8,192 points per GPU at 8 GPUs;
+rank r takes rows 32r..32r+31 of the R0 grid).  Per rank: direct method for `iters` events, `leaps` tau leaps,
+genealogy of every replicate, tree statistics reduced on the device (VGSIM_NSUMMARY doubles per replicate); then ONE
+NCCL all-gather of the summaries -- the only collective of the path -- timed with CUDA events.
 
-    python scripts/run_sweep.py [rank] [world] [iters] [leaps]"""
+What "1e6-sample genealogies" means here (hard parts): 65,536 trees of 1e6 samples each would be 1.3e11 nodes
+(0.5 TB of parent indices alone), so the requirement is read per GPU: each rank's pass builds the genealogies of >= 1e6
+sampled cases in total (about 140 per replicate x 8,192 replicates), keeps the trees in HBM for the exporters, and
+ships only the fixed-size summary rows.
+
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 scripts/run_sweep.py [iters] [leaps]
+    python scripts/run_sweep.py [iters] [leaps]          (one GPU = rank 0 of VGSIM_SWEEP_WORLD, default 8)
+Rank 0 prints one JSON record (per-rank phase times, gather time, grid sanity checks)."""
 import json
 import os
 import sys
@@ -13,16 +22,27 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 from scenarios import SCENARIOS  # noqa: E402
+from vgsim_b200 import _capi, _shard  # noqa: E402
 from vgsim_b200.sweep import Sweep  # noqa: E402
 
-rank = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-iters = int(sys.argv[3]) if len(sys.argv) > 3 else 20000
-leaps = int(sys.argv[4]) if len(sys.argv) > 4 else 64
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+leaps = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+distributed = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
+rank = int(os.environ.get("RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", os.environ.get("VGSIM_SWEEP_WORLD", "8")))
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local_rank)
+dev = torch.device("cuda", local_rank)
+if distributed:
+    dist.init_process_group("nccl", device_id=dev)
+
 dims, setup = SCENARIOS["table3_k10"]
-B = np.linspace(1.2, 4.0, 256) * (0.099 + 0.001)
-MIG = np.logspace(-4, -1, 256)
+N0, N1 = 256, 256
+B = np.linspace(1.2, 4.0, N0) * (0.099 + 0.001)
+MIG = np.logspace(-4, -1, N1)
 
 
 def mk(b, m):
@@ -33,27 +53,70 @@ def mk(b, m):
 
 
 pts = [mk(b, m) for b in B for m in MIG]
-out = {"config": "sweep 256x256 (R0 x total migration), table-3 model K=10, rank %d of %d" % (rank, world)}
 t0 = time.time()
-sw = Sweep(dims, setup, pts, 1, seed=31337, rank=rank, world=world)
-out["setup_s"] = time.time() - t0
-out["replicates"] = sw.R
-t0 = time.time(); sw.simulate(iters, 10 ** 9, -1, "direct"); out["direct_s"] = time.time() - t0
-out["direct_kernel_ms"] = sw.h.last_kernel_ms()
+sw = Sweep(dims, setup, pts, 1, seed=31337, rank=rank, world=world, device=local_rank)
+rec = {"rank": rank, "replicates": sw.R, "setup_s": time.time() - t0}
+t0 = time.time(); sw.simulate(iters, 10 ** 9, -1, "direct"); rec["direct_s"] = time.time() - t0
+rec["direct_kernel_ms"] = sw.h.last_kernel_ms()
 c = sw.counters()
-out["direct_events"] = int(c["events"].sum())
-t0 = time.time(); sw.simulate(leaps, 10 ** 9, -1, "tau"); out["tau_s"] = time.time() - t0
-out["tau_kernel_ms"] = sw.h.last_kernel_ms()
+rec["direct_events"] = int(c["events"].sum())
+t0 = time.time(); sw.simulate(leaps, 10 ** 9, -1, "tau"); rec["tau_s"] = time.time() - t0
+rec["tau_kernel_ms"] = sw.h.last_kernel_ms()
 c2 = sw.counters()
 ev = sum(int(c2[k].sum() - c[k].sum()) for k in ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus"))
-out.update(tau_leaps=int(c2["leaps"].sum()), tau_events=ev, tau_events_per_s=ev / (out["tau_kernel_ms"] * 1e-3),
+rec.update(tau_leaps=int(c2["leaps"].sum()), tau_events=ev, tau_events_per_s=ev / (rec["tau_kernel_ms"] * 1e-3),
            samples_total=int(c2["sCounter"].sum()), device_errors=int(sw.h.synchronize(strict=False)))
-t0 = time.time(); sw.genealogy(); out["genealogy_s"] = time.time() - t0
-s = sw.summaries()[:, 0]
-rows = s.reshape(-1, 256, s.shape[1])          # [R0 rows of this rank][migration][summary]
-out["tree_nodes_total"] = float(s[:, 13].sum())
-out["final_time_by_R0_row_first_last"] = [float(np.median(rows[0, :, 12])), float(np.median(rows[-1, :, 12]))]
-out["migration_rows_by_mig_first_last"] = [float(rows[:, :16, 18].mean()), float(rows[:, -16:, 18].mean())]
-assert out["final_time_by_R0_row_first_last"][0] > out["final_time_by_R0_row_first_last"][1], "higher R0 must get there sooner"
-assert out["migration_rows_by_mig_first_last"][0] < out["migration_rows_by_mig_first_last"][1], "more migration, more migrant lineages"
-print(json.dumps(out))
+t0 = time.time(); sw.genealogy(); rec["genealogy_s"] = time.time() - t0
+
+# ---- the collective: all-gather of the per-replicate summary rows (device buffers, NCCL over NVLink)
+sptr = sw.h.summaries_dev_ptr()
+
+
+class _Dev:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+local = torch.as_tensor(_Dev(sptr, (sw.R, _capi.NSUMMARY)), device=dev).clone()
+torch.cuda.synchronize(dev)
+rec["tree_nodes_total"] = float(local[:, 13].sum().item())
+gather_ms = None
+allsum = local
+if distributed:
+    for _ in range(2):          # warm-up (communicator setup), then the timed gather
+        allsum = _shard.gather_summaries(local, world)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    allsum = _shard.gather_summaries(local, world)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gather_ms = float(t.item())
+    recs = [None] * world
+    dist.all_gather_object(recs, rec)
+else:
+    recs = [rec]
+
+if rank == 0:
+    s = allsum.cpu().numpy()
+    out = {"config": "sweep %dx%d (R0 x total migration), table-3 model K=10, %d ranks%s" % (
+               N0, N1, world, "" if distributed else " (only rank 0's share was run)"),
+           "points_total": N0 * N1, "points_gathered": int(s.shape[0]), "iters_direct": iters, "tau_leaps_per_replicate": leaps,
+           "summary_bytes_gathered": int(s.nbytes), "allgather_ms_max_over_ranks": gather_ms, "ranks": recs,
+           "totals": {k: float(sum(r[k] for r in recs)) for k in ("direct_events", "tau_events", "samples_total", "tree_nodes_total")},
+           "slowest_rank_s": {k: max(r[k] for r in recs) for k in ("setup_s", "direct_s", "tau_s", "genealogy_s")},
+           "genealogy_note": "per rank >= 1e6 sampled cases in aggregate; trees stay in HBM, summaries are gathered"}
+    if s.shape[0] == N0 * N1:
+        rows = s.reshape(N0, N1, s.shape[1])
+        out["final_time_by_R0_row_first_last"] = [float(np.median(rows[0, :, 12])), float(np.median(rows[-1, :, 12]))]
+        out["migration_rows_by_mig_first_last"] = [float(rows[:, :16, 18].mean()), float(rows[:, -16:, 18].mean())]
+        assert out["final_time_by_R0_row_first_last"][0] > out["final_time_by_R0_row_first_last"][1], "higher R0 must get there sooner"
+        assert out["migration_rows_by_mig_first_last"][0] < out["migration_rows_by_mig_first_last"][1], "more migration, more migrant lineages"
+        assert np.all(s[:, 9] > 0) and int((s[:, 13] > 0).sum()) > 0.9 * N0 * N1
+    print(json.dumps(out))
+if distributed:
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,18 +1,18 @@
 #!/usr/bin/env python
 """Golden vectors for the Newick / TSV writers: the UNMODIFIED reference engine (oracle/_ref, built by
 oracle/build_ref.py) simulates scenario 9, builds the genealogy, and the reference's own writers (src/IO.py:144-255,
-byte-compiled into oracle/_ref/VGsim/IO.pyc) and its export_migrations (src/_BirthDeath.pyx:1743-1754) write the four
+byte-compiled into oracle/_ref/VGsim/IO.pyc.bin) and its export_migrations (src/_BirthDeath.pyx:1743-1754) write the four
 files.  Stored: the writers' INPUT arrays (npz) and their output text.  tests/test_writers_parity.py feeds the arrays to
 vgsim_b200.io and compares the text byte for byte.  Run here (needs oracle/_ref), commit the outputs."""
 import os, sys, tempfile
 import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle", "_ref")]
-sys.setrecursionlimit(100000)
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 from oracle import oracle as O
 from scenarios import SCENARIOS
-import VGsim.IO as RIO
+from test_writers_parity import ref_io
+RIO = ref_io()
 
 for name, seed, n_iter, gseed in (("s9", 2020, 6000, 7), ("s5", 11, 4000, 3), ("s8", 5, 30000, 9), ("s8hi", 5, 3000, 9)):
     (U, K, S), setup = SCENARIOS[name]

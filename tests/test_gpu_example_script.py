@@ -2,7 +2,7 @@
 direct Gillespie to t = 110, parameter changes, the tau call (which takes 0 leaps: quirk Q5, the default
 sample_size = iterations = 1000 is already exceeded), genealogy, and the three exports -- once through
 `vgsim_b200.Simulator` and once through the REFERENCE'S OWN `Simulator` class (src/_interface.py, byte-compiled into
-oracle/_ref/VGsim/_interface.pyc by oracle/build_ref.py) with the one-line engine substitution INTEGRATION.md describes.
+oracle/_ref/VGsim/_interface.pyc.bin by oracle/build_ref.py) with the one-line engine substitution INTEGRATION.md describes.
 Both runs use the same seed and the same engine, so their output files must be identical: that is the drop-in claim."""
 import importlib
 import os
@@ -120,14 +120,14 @@ def test_example_script_runs_on_the_device(tmp_path, capsys):
     assert all(leaf_pop[i] != 2 for i in np.flatnonzero(kids == 0))
 
 
-@pytest.mark.skipif(not os.path.exists(os.path.join(REF_PKG, "_interface.pyc")), reason="oracle/_ref (reference build) not present")
+@pytest.mark.skipif(not os.path.exists(os.path.join(REF_PKG, "_interface.pyc.bin")), reason="oracle/_ref (reference build) not present")
 def test_reference_simulator_class_over_the_new_engine(tmp_path):
     """The reference's Simulator (unmodified bytecode of src/_interface.py + src/IO.py) with `_BirthDeath` replaced by the
     three-line stub of INTEGRATION.md section 1 gives the same files as vgsim_b200.Simulator."""
     pkg = tmp_path / "VGsim_dropin"
     pkg.mkdir()
-    shutil.copy(os.path.join(REF_PKG, "_interface.pyc"), pkg / "_interface.pyc")
-    shutil.copy(os.path.join(REF_PKG, "IO.pyc"), pkg / "IO.pyc")
+    shutil.copy(os.path.join(REF_PKG, "_interface.pyc.bin"), pkg / "_interface.pyc")
+    shutil.copy(os.path.join(REF_PKG, "IO.pyc.bin"), pkg / "IO.pyc")
     (pkg / "_BirthDeath.py").write_text(
         "# INTEGRATION.md section 1: the engine the reference's wrapper binds\n"
         "from vgsim_b200._engine import BirthDeathModel  # ctypes -> libvgsim_b200.so (sm_100a CUDA)\n")

@@ -8,7 +8,7 @@ Three layers:
   * live (where oracle/_ref exists): the reference engine + reference writers on fresh seeds vs our writers on the
     same arrays;
   * device (-m gpu): trees, mutations and migrations from the CUDA path, exported through `Simulator.export_*`, vs the
-    reference's writers (byte-compiled into oracle/_ref/VGsim/IO.pyc by oracle/build_ref.py) fed with the same arrays.
+    reference's writers (byte-compiled into oracle/_ref/VGsim/IO.pyc.bin by oracle/build_ref.py) fed with the same arrays.
 """
 import glob
 import os
@@ -22,15 +22,22 @@ from vgsim_b200 import io as vio
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-HAVE_REF_IO = os.path.exists(os.path.join(REF_DIR, "VGsim", "IO.pyc"))
+HAVE_REF_IO = os.path.exists(os.path.join(REF_DIR, "VGsim", "IO.pyc.bin"))
 
 
 def ref_io():
-    if REF_DIR not in sys.path:
-        sys.path.insert(0, REF_DIR)
+    """The reference's src/IO.py, loaded from the sourceless bytecode oracle/build_ref.py leaves in oracle/_ref."""
+    import importlib.machinery
+    import importlib.util
     sys.setrecursionlimit(100000)   # the reference's Vertex builds itself recursively, one level per tree level
-    import VGsim.IO as RIO
-    return RIO
+    if "vgsim_reference_IO" in sys.modules:
+        return sys.modules["vgsim_reference_IO"]
+    loader = importlib.machinery.SourcelessFileLoader("vgsim_reference_IO", os.path.join(REF_DIR, "VGsim", "IO.pyc.bin"))
+    spec = importlib.util.spec_from_loader("vgsim_reference_IO", loader)
+    mod = importlib.util.module_from_spec(spec)
+    loader.exec_module(mod)
+    sys.modules["vgsim_reference_IO"] = mod
+    return mod
 
 
 def ours(tmp, tree, times, pops, mut, mig):

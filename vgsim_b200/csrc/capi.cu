@@ -104,7 +104,8 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
         dalloc(h, &st.initSx, R * K * S) || dalloc(h, &st.cd, R * K) || dalloc(h, &st.lock, R * K) ||
         dalloc(h, &st.eff, R * K * K) || dalloc(h, &st.ceff, R * K) || dalloc(h, &st.maxEBM, R * K) ||
         dalloc(h, &st.time, R) || dalloc(h, &st.counters, R * NCOUNT) || dalloc(h, &st.epoch, R) ||
-        dalloc(h, &st.err, R) || dalloc(h, &st.loc_n, R) || dalloc(h, &st.ev_base, R)) {
+        dalloc(h, &st.err, R) || dalloc(h, &st.loc_n, R) || dalloc(h, &st.ev_base, R) || dalloc(h, &st.dense_base, R) ||
+        dalloc(h, &st.sp_n, R)) {
         vgsim_destroy(h);
         return 1;
     }
@@ -358,6 +359,8 @@ __global__ void reset_kernel(DevState st) {  // one warp per replicate
         st.err[r] = 0;
         st.loc_n[r] = 0;
         st.ev_base[r] = 0;
+        st.dense_base[r] = 0;
+        st.sp_n[r] = 0;
     }
 }
 
@@ -383,6 +386,7 @@ int vgsim_reset(vgsim_handle h) {
     CK(cudaGetLastError());
     h->ev_bound = 0;
     h->leap_bound = 0;
+    h->dense_bound = 0;
     st.first_simulation = 0;
     h->gen.valid = false;
     return 0;
@@ -394,6 +398,8 @@ __global__ void recycle_log_kernel(DevState st) {
     st.ev_base[r] += st.counters[(size_t)r * NCOUNT + C_EVPTR];
     st.counters[(size_t)r * NCOUNT + C_EVPTR] = 0;
     st.counters[(size_t)r * NCOUNT + C_LEAPS] = 0;
+    st.dense_base[r] = 0;
+    st.sp_n[r] = 0;
 }
 
 int vgsim_recycle_log(vgsim_handle h) {
@@ -403,6 +409,7 @@ int vgsim_recycle_log(vgsim_handle h) {
     CK(cudaGetLastError());
     h->ev_bound = 0;
     h->leap_bound = 0;
+    h->dense_bound = 0;
     h->gen.valid = false;
     return 0;
 }
@@ -454,13 +461,33 @@ static int ensure_ev_cap(Handle *h, long long need) {
     st.ev_cap = nc;
     return 0;
 }
-static int ensure_leap_cap(Handle *h, long long need) {
+static int ensure_leap_cap(Handle *h, long long need) {  // tau_tt and the archive's offsets: all leaps of a replicate
     DevState &st = h->st;
     if (need <= st.leap_cap) return 0;
     long long nc = need;
-    if (grow2d(h, &st.tau_counts, st.leap_cap, nc, h->leap_bound, (size_t)st.D.Pp)) return 1;
     if (grow2d(h, &st.tau_tt, st.leap_cap, nc, h->leap_bound, 2)) return 1;
+    // sp_off rows have one more entry than there are leaps: grow with the row strides old_cap + 1 -> new_cap + 1
+    {
+        int *nb;
+        if (dalloc(h, &nb, (size_t)h->R * (nc + 1))) return 1;
+        if (st.sp_off && h->leap_bound > 0)
+            if (cudaMemcpy2DAsync(nb, (nc + 1) * 4, st.sp_off, (st.leap_cap + 1) * 4, (h->leap_bound + 1) * 4, h->R,
+                                  cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess)
+                return fail("cudaMemcpy2D (archive offsets)");
+        if (st.sp_off) {
+            cudaStreamSynchronize(h->stream);
+            dfree(h, st.sp_off);
+        }
+        st.sp_off = nb;
+    }
     st.leap_cap = nc;
+    return 0;
+}
+static int ensure_dense_cap(Handle *h, long long need) {  // dense count rows: the leaps not archived yet
+    DevState &st = h->st;
+    if (need <= st.dense_cap) return 0;
+    if (grow2d(h, &st.tau_counts, st.dense_cap, need, h->dense_bound, (size_t)st.D.Pp)) return 1;
+    st.dense_cap = need;
     return 0;
 }
 
@@ -499,7 +526,9 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
                        int64_t attempts) {
     CK(cudaSetDevice(h->device));
     if (iterations < 0) return fail("iterations must be >= 0");
-    if (ensure_ev_cap(h, h->ev_bound + iterations) || ensure_leap_cap(h, h->leap_bound + iterations)) return 1;
+    if (ensure_ev_cap(h, h->ev_bound + iterations) || ensure_leap_cap(h, h->leap_bound + iterations) ||
+        ensure_dense_cap(h, h->dense_bound + iterations))
+        return 1;
     if (prepare(h, 1)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
     next_timer(h);
@@ -514,6 +543,58 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
     h->launches++;
     h->ev_bound += iterations;
     h->leap_bound += iterations;
+    h->dense_bound += iterations;
+    return 0;
+}
+
+// The dense rows of every replicate go into the sparse archive (non-zero counts only, ascending channel order, 8 bytes
+// each) and the dense capacity is free again: long tau runs proceed in leap blocks without the log growing by
+// 4P bytes per leap (4,096 T3 replicates x 1,200 leaps would be 520 GB; 256 world-shape replicates x 2,000 leaps 1 TB).
+// Genealogy, curves and the exporters read archived leaps from the archive, the others from their dense rows.
+int vgsim_archive_tau_log(vgsim_handle h) {
+    CK(cudaSetDevice(h->device));
+    DevState &st = h->st;
+    if (h->dense_bound == 0 || st.dense_cap == 0) return 0;
+    const size_t R = h->R;
+    int *cnt = nullptr, *need = nullptr;
+    CK(cudaMalloc(&cnt, R * st.dense_cap * 4));
+    CK(cudaMalloc(&need, R * 4));
+    cudaError_t e = launch_archive_count(st, cnt, need, h->stream);
+    h->launches += 2;
+    std::vector<int> hneed(R), hn(R);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hneed.data(), need, R * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hn.data(), st.sp_n, R * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) {
+        cudaFree(cnt);
+        cudaFree(need);
+        return fail(std::string("archive (count): ") + cudaGetErrorString(e));
+    }
+    long long want = 0;
+    for (size_t r = 0; r < R; r++) want = std::max(want, (long long)hn[r] + hneed[r]);
+    if (want > 2147483647LL) {
+        cudaFree(cnt);
+        cudaFree(need);
+        return fail("archive: more than 2^31 entries in one replicate");
+    }
+    if (want > st.sp_cap) {
+        long long nc = std::max(want + want / 2, (long long)1024);   // room for the next blocks too
+        long long keep = 0;
+        for (size_t r = 0; r < R; r++) keep = std::max(keep, (long long)hn[r]);
+        if (grow2d(h, &st.sp_ent, st.sp_cap, nc, keep, 1)) {
+            cudaFree(cnt);
+            cudaFree(need);
+            return 1;
+        }
+        st.sp_cap = nc;
+    }
+    e = launch_archive_write(st, cnt, need, h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(cnt);
+    cudaFree(need);
+    if (e != cudaSuccess) return fail(std::string("archive (write): ") + cudaGetErrorString(e));
+    h->dense_bound = 0;
     return 0;
 }
 
@@ -686,12 +767,29 @@ int vgsim_get_tau_log(vgsim_handle h, int r, int64_t leaps, int32_t *counts, dou
     if (leaps != c[C_LEAPS]) return fail("leap count mismatch (expected counters[10])");
     if (leaps == 0) return 0;
     const Dims &D = h->D;
-    if (counts)
-        CK(cudaMemcpy2DAsync(counts, (size_t)D.P * 4, h->st.tau_counts + (size_t)r * h->st.leap_cap * D.Pp,
-                             (size_t)D.Pp * 4, (size_t)D.P * 4, leaps, cudaMemcpyDeviceToHost, h->stream));
+    const DevState &st = h->st;
+    long long base = 0;
+    CK(cudaMemcpyAsync(&base, st.dense_base + r, 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (counts) {
+        if (leaps > base)  // the leaps that still have their dense row
+            CK(cudaMemcpy2DAsync(counts + (size_t)base * D.P, (size_t)D.P * 4, st.tau_counts + (size_t)r * st.dense_cap * D.Pp,
+                                 (size_t)D.Pp * 4, (size_t)D.P * 4, leaps - base, cudaMemcpyDeviceToHost, h->stream));
+        if (base > 0) {    // archived leaps: scatter the (channel, count) entries back into dense rows
+            std::vector<int> off(base + 1);
+            CK(cudaMemcpyAsync(off.data(), st.sp_off + (size_t)r * (st.leap_cap + 1), (base + 1) * 4, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            std::vector<int2> ent(off[base]);
+            if (off[base] > 0)
+                CK(cudaMemcpyAsync(ent.data(), st.sp_ent + (size_t)r * st.sp_cap, (size_t)off[base] * 8, cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            memset(counts, 0, (size_t)base * D.P * 4);
+            for (long long l = 0; l < base; l++)
+                for (int k = off[l]; k < off[l + 1]; k++) counts[(size_t)l * D.P + ent[k].x] = ent[k].y;
+        }
+    }
     if (time_tau)
-        CK(cudaMemcpyAsync(time_tau, h->st.tau_tt + (size_t)r * h->st.leap_cap * 2, leaps * 16, cudaMemcpyDeviceToHost,
-                           h->stream));
+        CK(cudaMemcpyAsync(time_tau, st.tau_tt + (size_t)r * st.leap_cap * 2, leaps * 16, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -146,9 +146,17 @@ struct DevState {
     double *ev_time;           // [R][ev_cap]
     unsigned long long *ev_desc;
     // dense tau log
-    long long leap_cap;
-    int *tau_counts;           // [R][leap_cap][Pp]
+    long long leap_cap;        // leaps per replicate that tau_tt / sp_off can hold (dense + archived)
+    long long dense_cap;       // dense rows per replicate
+    int *tau_counts;           // [R][dense_cap][Pp]: leap L of replicate r is row L - dense_base[r]
     double *tau_tt;            // [R][leap_cap][2]  (time after the leap, tau)
+    // sparse archive of the dense rows (vgsim_archive_tau_log): the non-zero counts of leap L < dense_base[r], in
+    // ascending channel order, are sp_ent[r * sp_cap + sp_off[r][L] .. sp_off[r][L + 1])
+    long long *dense_base;     // [R] leaps already archived (0: everything is dense)
+    int2 *sp_ent;              // [R][sp_cap] (channel, count)
+    long long sp_cap;
+    int *sp_off;               // [R][leap_cap + 1]
+    int *sp_n;                 // [R] entries in use
     // lockdown records
     int loc_cap;
     int *loc_n;                // [R]

@@ -293,23 +293,30 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
             unsigned long long iter = 0;
             double Rm = K > 1 ? fmax(ginf * mA - mB, 0.0) : 0.0;
             if (Rt + Rm != 0.0 && ginf != 0.0) {
-                // the Philox block of iteration i+1 is computed at the top of iteration i: it depends on nothing, so its
-                // 10-round integer chain interleaves with the fp64 chain (log, division, scans) of the current event
-                uint4 wnext = philox4x32_10(make_uint4(0u, 0u, epoch, 0x44495245u), key);
+                // Random numbers for 32 iterations at a time, one iteration per LANE: lane l holds the exponential variate
+                // and the choice uniform of iteration base + l (iteration i always uses Philox block i, so the stream does
+                // not depend on this batching).  One Philox call, one log per 32 events and lane instead of one per event.
+                double Emine = 0.0, u2mine = 0.0;
                 while (evptr < ev_limit && (a.sample_size == -1 || cS <= a.sample_size) && (!a.has_time || t < (double)a.time)) {
                     // ---- SampleTime + GenerateEvent (:476-512): two uniforms per iteration
-                    const uint4 w = wnext;
+                    const int slot = (int)(iter & 31ull);
+                    if (slot == 0) {
+                        const unsigned long long it = iter + (unsigned)lane;
+                        const uint4 w = philox4x32_10(make_uint4((uint32_t)it, (uint32_t)(it >> 32), epoch, 0x44495245u), key);
+                        double u1 = u53(w.x, w.y);
+                        if (u1 <= 0.0) u1 = 1.0 / 9007199254740992.0;
+                        Emine = -log(u1);
+                        u2mine = u53(w.z, w.w);
+                    }
+                    const double E = __shfl_sync(0xffffffffu, Emine, slot);
+                    const double u2 = __shfl_sync(0xffffffffu, u2mine, slot);
                     iter++;
-                    wnext = philox4x32_10(make_uint4((uint32_t)iter, (uint32_t)(iter >> 32), epoch, 0x44495245u), key);
                     if ((iter & 1023ull) == 0) {  // bound the drift of the incremental totals
                         dir_totals(D, s, Rt, mA, mB);
                         Rm = K > 1 ? fmax(ginf * mA - mB, 0.0) : 0.0;
                     }
-                    double u1 = u53(w.x, w.y);
-                    const double u2 = u53(w.z, w.w);
-                    if (u1 <= 0.0) u1 = 1.0 / 9007199254740992.0;
                     const double R = Rt + Rm;
-                    t += -log(u1) / R;
+                    t += E / R;
                     const double x = u2 * R;
                     int touched = -1;   // deme whose rates changed (or, for a rejected migration, the target deme)
                     double dS = 0.0, dI = 0.0;  // change of the touched deme's susceptible / infectious totals
@@ -349,9 +356,17 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
                             // eventHapPopRate[p,h,0:4] (:310-314) times the cell's count
                             const double e0 = s.b[h] * (Q * s.c[p]) * Ih, e1 = s.d[h] * Ih, e2 = s.sr[h] * s.sm[p] * Ih,
                                          e3 = s.tm[h] * Ih;
-                            const Pick pe = small_pick([&](int i) { return i == 0 ? e0 : i == 1 ? e1 : i == 2 ? e2 : e3; }, 4, z);
-                            const int e = pe.i;
-                            if (e < 0) { errbits |= ERR_ZERO_WEIGHT; break; }
+                            // the four event rates: z in [0, e0+e1+e2+e3); an event with zero weight owns an empty interval,
+                            // so the strict comparisons never pick it; a z that rounding pushed past the total falls to
+                            // the last positive weight (fastChoose's catch-all)
+                            const double c1 = e0 + e1, c2 = c1 + e2;
+                            int e = z < e0 ? 0 : z < c1 ? 1 : z < c2 ? 2 : 3;
+                            if (e == 3 && !(e3 > 0.0)) e = e2 > 0.0 ? 2 : e1 > 0.0 ? 1 : 0;
+                            Pick pe;
+                            pe.i = e;
+                            pe.before = e == 0 ? 0.0 : e == 1 ? e0 : e == 2 ? c1 : c2;
+                            pe.w = e == 0 ? e0 : e == 1 ? e1 : e == 2 ? e2 : e3;
+                            if (!(pe.w > 0.0)) { errbits |= ERR_ZERO_WEIGHT; break; }
                             if (e == 0) {
                                 // ---- Birth (:568-605): the group of the newly infected, weights Sx[p,s] sigma[s,h]
                                 const double sc = bc * Ih;

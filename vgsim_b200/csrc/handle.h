@@ -46,6 +46,7 @@ struct Handle {
     DevState st;
     std::vector<HostParams> hp;
     long long ev_bound = 0, leap_bound = 0;  // host upper bounds of log rows / leaps per replicate
+    long long dense_bound = 0;               // ... of leaps whose dense row has not been archived
     long long launches = 0;
     int tau_variant = 0;  // 0 = aggregated small groups (product), 1 = one Poisson draw per channel (parity tap)
     bool state_set = false;
@@ -71,6 +72,8 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
 cudaError_t tau_phase_cycles(unsigned long long *out16, int reset);
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream);
+cudaError_t launch_archive_count(const DevState &st, int *cnt, int *need, cudaStream_t stream);
+cudaError_t launch_archive_write(const DevState &st, const int *cnt, const int *need, cudaStream_t stream);
 cudaError_t launch_prepare(const DevState &st, int first, int tau_mode, cudaStream_t stream);
 cudaError_t launch_refresh(const DevState &st, cudaStream_t stream);
 cudaError_t launch_direct(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int uniform_pp, int *work);

@@ -66,7 +66,8 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     L.use_masks = (H <= 64 && K <= 32) ? 1 : 0;
     L.has_eff = tau_eff_in_smem(D) ? 1 : 0;
 #ifndef VGSIM_TW_QCAP
-#define VGSIM_TW_QCAP 128   // >= 128: one round can push 4 entries per lane
+#define VGSIM_TW_QCAP 96    // >= 64: half a round (two words per lane) must fit an empty queue.  96 leaves the per-leap Q
+                            // table room for ~17 present haplotypes at the T3 shape (4.58 -> 4.44 ms at t = 60 against 128)
 #endif
     L.qcap = VGSIM_TW_QCAP;
     L.xcap = 64;
@@ -891,6 +892,7 @@ struct RoundOut {  // what a lane's block leaves for the queue
     double lam[4];
     uint4 w4;
     unsigned mi[4], mp[4];  // per word: lanes that push an inversion / a PTRS entry
+    int need[2];            // queue entries of words 0-1 / words 2-3 (each <= 64: a half always fits an empty queue)
     int owner, lb;          // local channel of word w = lb + w; lb < 0: block 0 of a cell (0, 1, the two totals)
 };
 
@@ -1009,7 +1011,7 @@ __device__ __forceinline__ int w_round(int item, int mode, int nAct, double tau,
     }
     ro.owner = owner;
     ro.lb = kind == 0 ? -1 : lb;
-    int pushes = 0;
+    ro.need[0] = ro.need[1] = 0;
 #pragma unroll
     for (int w = 0; w < 4; w++) {
         const uint32_t hi = w == 0 ? ro.w4.x : w == 1 ? ro.w4.y : w == 2 ? ro.w4.z : ro.w4.w;
@@ -1020,29 +1022,35 @@ __device__ __forceinline__ int w_round(int item, int mode, int nAct, double tau,
         const bool ptr = lm >= 10.0;
         ro.mi[w] = __ballot_sync(0xffffffffu, inv);
         ro.mp[w] = __ballot_sync(0xffffffffu, ptr);
-        pushes += __popc(ro.mi[w]) + __popc(ro.mp[w]);
+        ro.need[w >> 1] += __popc(ro.mi[w]) + __popc(ro.mp[w]);
     }
-    return pushes;
+    return ro.need[0] + ro.need[1];
 }
 
-// store the round's unsettled draws (the caller has made room): inversion entries from the bottom, PTRS from the top
+// store the unsettled draws of one half of the round (words 2*half, 2*half+1; the caller has made room): inversion
+// entries from the bottom, PTRS from the top.  (Explicit selects instead of indexing with `half`: the per-word arrays
+// must stay in registers.)
 template <class WSQ>
-__device__ __forceinline__ void w_push(const RoundOut &ro, const WSQ &s, DrawState &q) {
+__device__ __forceinline__ void w_push(const RoundOut &ro, int half, const WSQ &s, DrawState &q) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
-        const bool inv = (ro.mi[w] & me) != 0, ptr = (ro.mp[w] & me) != 0;
+    for (int ww = 0; ww < 2; ww++) {
+        const int w = 2 * half + ww;
+        const unsigned mi = half ? (ww ? ro.mi[3] : ro.mi[2]) : (ww ? ro.mi[1] : ro.mi[0]);
+        const unsigned mp = half ? (ww ? ro.mp[3] : ro.mp[2]) : (ww ? ro.mp[1] : ro.mp[0]);
+        const double lm = half ? (ww ? ro.lam[3] : ro.lam[2]) : (ww ? ro.lam[1] : ro.lam[0]);
+        const uint32_t hi = half ? (ww ? ro.w4.w : ro.w4.z) : (ww ? ro.w4.y : ro.w4.x);
+        const bool inv = (mi & me) != 0, ptr = (mp & me) != 0;
         if (inv || ptr) {
-            const uint32_t hi = w == 0 ? ro.w4.x : w == 1 ? ro.w4.y : w == 2 ? ro.w4.z : ro.w4.w;
-            const int e = inv ? q.ninv + __popc(ro.mi[w] & lt) : s.qcap - 1 - (q.nptr + __popc(ro.mp[w] & lt));
+            const int e = inv ? q.ninv + __popc(mi & lt) : s.qcap - 1 - (q.nptr + __popc(mp & lt));
             const int l = (ro.lb < 0) ? (w < 2 ? w : w == 2 ? TW_L_TOT_MUT : TW_L_TOT_MIG) : ro.lb + w;
-            s.qlam[e] = ro.lam[w];
+            s.qlam[e] = lm;
             s.qhi[e] = (int)hi;
             s.qoc[e] = (int)((unsigned)ro.owner | ((unsigned)l << 20));
         }
-        q.ninv += __popc(ro.mi[w]);
-        q.nptr += __popc(ro.mp[w]);
+        q.ninv += __popc(mi);
+        q.nptr += __popc(mp);
     }
 }
 
@@ -1286,12 +1294,19 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                         for (;;) {
                             const bool inx = xbase < xlimit;
                             RoundOut ro;
-                            int pushes = 0;
+                            ro.need[0] = ro.need[1] = 0;
                             if (!flush)
-                                pushes = w_round((inx ? xbase : pbase) + lane, inx ? 1 : 0, nAct, tau, variant, D, s, eff, g, L, ctx, dq, ro);
-                            if (flush || dq.ninv + dq.nptr + pushes > s.qcap) w_drain(row, D, s, eff, g, L, ctx, tr, dq, flush);
+                                w_round((inx ? xbase : pbase) + lane, inx ? 1 : 0, nAct, tau, variant, D, s, eff, g, L, ctx, dq, ro);
+                            // the round's entries go in as two halves (words 0-1, words 2-3: at most 64 each), draining
+                            // first whenever the next half does not fit; the iteration after the last round only drains
+#pragma unroll 1
+                            for (int half = 0; half < 2; half++) {
+                                const bool whole = half == 0 && dq.ninv + dq.nptr + ro.need[0] + ro.need[1] <= s.qcap;
+                                if ((flush && half == 0) || (!whole && dq.ninv + dq.nptr + (half ? ro.need[1] : ro.need[0]) > s.qcap))
+                                    w_drain(row, D, s, eff, g, L, ctx, tr, dq, flush);
+                                if (!flush) w_push(ro, half, s, dq);
+                            }
                             if (flush) break;
-                            w_push(ro, s, dq);
                             if (inx) {
                                 xbase += 32;
                                 if (xbase >= xlimit) {
