@@ -106,6 +106,16 @@ int vgsim_reset(vgsim_handle h);
  * must have read the block first; events.ptr and the leap count restart at 0. */
 int vgsim_recycle_log(vgsim_handle h);
 
+/* Long runs with the whole log kept: move the dense count rows of every replicate (4P bytes per leap) into a sparse
+ * archive -- the non-zero counts as (channel, count) pairs in ascending channel order, 8 bytes each -- and free the dense
+ * capacity for the next block of leaps.  The event log, leap times, counters and state are untouched; vgsim_genealogy,
+ * vgsim_epidemic_curves, vgsim_get_tau_log and vgsim_get_multievents read archived leaps from the archive and give the
+ * same results as on the dense rows.  (The reference appends 56 bytes per channel and leap, zeros included,
+ * src/_BirthDeath.pyx:2536-2593; the dense row stays the roofline yardstick) */
+int vgsim_archive_tau_log(vgsim_handle h);
+/* Size of the archive: (channel, count) entries over all replicates, the largest replicate's, and the leaps archived. */
+int vgsim_archive_stats(vgsim_handle h, int64_t *entries_total, int64_t *entries_max, int64_t *leaps_archived);
+
 /* SimulatePopulation (src/_BirthDeath.pyx:396-429): batched direct Gillespie, one warp per
  * replicate.  `epidemic_time` is a C float like the reference's (quirk Q1); -1 = no limit;
  * sample_size -1 = no limit.  Appends up to `iterations` rows to each replicate's event log. */
@@ -115,6 +125,13 @@ int vgsim_simulate_direct(vgsim_handle h, int64_t iterations, int64_t sample_siz
  * per replicate; appends up to `iterations` leaps (MULTITYPE rows + dense count blocks). */
 int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
                        int64_t attempts);
+/* The same call run as blocks of `leap_block` leaps with vgsim_archive_tau_log between blocks: the dense rows never
+ * exceed one block per replicate (a 2,000-leap run of the K = 100 world model would need 4 GB of dense rows per replicate).
+ * One call to the reference's eyes: FirstInfection (:2302-2303) only before the first block, the stop conditions of
+ * :2312 carry over, the run ends when no replicate used up its block.  leap_block is raised to 101 when iterations > 100
+ * so that the extinction retry of :2331 sees the same condition in every block. */
+int vgsim_simulate_tau_blocks(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
+                              int64_t attempts, int64_t leap_block);
 /* Block until everything queued on the handle's stream has finished; returns the sticky device
  * error flags of the last kernels (0 = ok). */
 int vgsim_synchronize(vgsim_handle h);

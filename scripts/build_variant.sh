@@ -6,7 +6,7 @@ cd "$(dirname "$0")/.."
 tag=$1; shift
 out=/tmp/vgsim_variant_$tag; mkdir -p $out
 pids=()
-for f in capi tau_kernel prep_kernels direct_kernel genealogy_kernel curves_kernel test_taps; do
+for f in capi tau_kernel prep_kernels direct_kernel genealogy_kernel curves_kernel archive_kernel test_taps; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c vgsim_b200/csrc/$f.cu -o $out/$f.o &
   pids+=($!)
 done

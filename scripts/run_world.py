@@ -2,12 +2,14 @@
 """BASELINE.json configs[3] ("world-scale tau-leap: 100 demes with full migration matrix, 1e8 individuals, 1e5-sample
 genealogy") end to end on one GPU, with size-independent checks.  Prints one JSON line.
 
-    python scripts/run_world.py [replicates] [max_leaps] [samples]
+    python scripts/run_world.py [replicates] [max_leaps] [samples] [t_direct] [leap_block]
 
 Model: SURVEY §8(d) config 4 = data/Table 3/Table 3.py with K=100 (tests/scenarios.py "w"): direct method until the
 epidemic has taken off (t = 40; the reference restarts any run with <= 100 log rows), then tau-leaping until
 `samples` cases are sampled, genealogy over the mixed log, epidemic curves.  The dense log of a replicate is
-leaps x 1.97 MB, so the replicate count is bounded by HBM (32 replicates x 1,200 leaps = 76 GB), not by time."""
+leaps x 1.97 MB (32 replicates x 1,200 leaps = 76 GB), so the stated size (256 replicates, 1e5 samples = ~2,000 leaps
+each) runs in leap blocks: finished blocks are kept as the sparse archive (vgsim_simulate_tau_blocks), leap_block 0 =
+one dense call."""
 import json
 import os
 import sys
@@ -24,12 +26,13 @@ R = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 MAXL = int(sys.argv[2]) if len(sys.argv) > 2 else 1200
 NS = int(sys.argv[3]) if len(sys.argv) > 3 else 100000
 T_DIRECT = float(sys.argv[4]) if len(sys.argv) > 4 else 40.0
+BLOCK = int(sys.argv[5]) if len(sys.argv) > 5 else 101
 (U, K, S), setup = SCENARIOS["w"]
 e = Eng(U, K, S, 4242, False, False, int(1e6), 0.0, replicates=R)
 setup(e)
 out = {"config": "world: K=%d demes x H=%d x S=%d, 1e6 per deme, %d replicates" % (K, 4 ** U, S, R)}
 t0 = time.time()
-e.SimulatePopulation(10 ** 7, 10 ** 9, T_DIRECT, 200)
+e.SimulatePopulation(200000, 10 ** 9, T_DIRECT, 200)
 h = e._handle
 out["direct_s"] = time.time() - t0
 out["direct_kernel_ms"] = h.last_kernel_ms()
@@ -37,9 +40,12 @@ c = e.counters()
 out["direct_events_mean"] = float(c["events"].mean())
 out["P"] = int(h.P)
 t0 = time.time()
-e.SimulatePopulation_tau(MAXL, NS, -1, 200)
+e.SimulatePopulation_tau(MAXL, NS, -1, 200, leap_block=BLOCK if BLOCK > 0 else None)
 out["tau_s"] = time.time() - t0
-out["tau_kernel_ms"] = h.last_kernel_ms()
+out["tau_kernel_ms"] = h.last_kernel_ms()  # blocks: first block's start to last block's end, archive passes included
+out["leap_block"] = BLOCK
+st = h.archive_stats()
+out["archive"] = dict(st, bytes_total=8 * st["entries_total"], dense_bytes_replaced=st["leaps_archived"] * 4 * int(h.P))
 c = e.counters()
 ev = sum(int(c[k].sum()) for k in ("bCounter", "dCounter", "sCounter", "mCounter", "iCounter", "migPlus"))
 leaps = int(c["leaps"].sum())
@@ -69,11 +75,18 @@ out["genealogy_s"] = time.time() - t0
 out["genealogy_flags"] = flags
 sm = h.summaries()
 nodes, roots = sm[:, 13], sm[:, 16]
-assert np.array_equal(nodes, 2 * c["sCounter"] - 1), "tree size != 2n-1"
+# n sampled leaves coalesced into `roots` trees have 2n - roots nodes (2n-1 when fully coalesced; a replicate whose replay
+# clamped a coalescence count, genealogy flag 16, can be left with a few roots)
+if not np.array_equal(nodes, 2 * c["sCounter"] - roots):
+    bad = np.nonzero(nodes != 2 * c["sCounter"] - roots)[0]
+    out["FAILED_tree_size"] = {"replicates": bad[:8].tolist(), "nodes": nodes[bad[:8]].tolist(), "roots": roots[bad[:8]].tolist(),
+                               "samples": c["sCounter"][bad[:8]].tolist(), "n_bad": int(len(bad))}
+    print(json.dumps(out))
+    sys.exit(1)
 out.update(tree_nodes_mean=float(nodes.mean()), fully_coalesced=int((roots == 1).sum()), tree_height_mean=float(sm[:, 14].mean()),
            mutation_rows_mean=float(sm[:, 17].mean()), migration_rows_mean=float(sm[:, 18].mean()))
 parent, pop, tm = h.get_tree(0)
 assert (parent == -1).sum() == roots[0] and np.all(parent[parent >= 0] > np.nonzero(parent >= 0)[0]), "parents are created after children"
 assert np.all(tm[parent[parent >= 0]] <= tm[np.nonzero(parent >= 0)[0]] + 1e-12), "a parent is not later than its child"
-out["checks"] += ["tree has 2n-1 nodes", "parent index > child index and parent time <= child time (replicate 0)"]
+out["checks"] += ["every tree has 2n - roots nodes", "parent index > child index and parent time <= child time (replicate 0)"]
 print(json.dumps(out))

@@ -51,8 +51,11 @@ def _load():
         "vgsim_set_async": (c_int, [P, c_int]),
         "vgsim_wait": (c_int, [P]),
         "vgsim_recycle_log": (c_int, [P]),
+        "vgsim_archive_tau_log": (c_int, [P]),
+        "vgsim_archive_stats": (c_int, [P, ctypes.POINTER(c_int64), ctypes.POINTER(c_int64), ctypes.POINTER(c_int64)]),
         "vgsim_simulate_direct": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
         "vgsim_simulate_tau": (c_int, [P, c_int64, c_int64, c_float, c_int64]),
+        "vgsim_simulate_tau_blocks": (c_int, [P, c_int64, c_int64, c_float, c_int64, c_int64]),
         "vgsim_synchronize": (c_int, [P]),
         "vgsim_prop_num": (c_int64, [P]),
         "vgsim_propensities": (c_int, [P, c_int, P, P, P, P]),
@@ -182,6 +185,15 @@ class Handle:
     def wait(self):
         _ck(lib.vgsim_wait(self._h))
 
+    def archive_tau_log(self):
+        """Dense tau rows -> sparse archive (non-zero counts only); frees the dense capacity for the next leap block."""
+        _ck(lib.vgsim_archive_tau_log(self._h))
+
+    def archive_stats(self):
+        a, b, c = c_int64(), c_int64(), c_int64()
+        _ck(lib.vgsim_archive_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"entries_total": a.value, "entries_max": b.value, "leaps_archived": c.value}
+
     def recycle_log(self):
         _ck(lib.vgsim_recycle_log(self._h))
 
@@ -208,6 +220,12 @@ class Handle:
 
     def simulate_tau(self, iterations, sample_size=-1, time=-1.0, attempts=200, sync=True):
         _ck(lib.vgsim_simulate_tau(self._h, iterations, sample_size, time, attempts))
+        if sync:
+            self.synchronize()
+
+    def simulate_tau_blocks(self, iterations, sample_size=-1, time=-1.0, attempts=200, leap_block=128, sync=True):
+        """simulate_tau in blocks of `leap_block` leaps, finished blocks moved to the sparse archive."""
+        _ck(lib.vgsim_simulate_tau_blocks(self._h, iterations, sample_size, time, attempts, leap_block))
         if sync:
             self.synchronize()
 

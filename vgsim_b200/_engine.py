@@ -416,10 +416,14 @@ class BirthDeathModel:
         self._refresh_host_state()
         self._print_stop_reason(sample_size, time)
 
-    def SimulatePopulation_tau(self, iterations, sample_size, time, attempts):
-        """Tau-leaping, reference src/_BirthDeath.pyx:2293-2346."""
+    def SimulatePopulation_tau(self, iterations, sample_size, time, attempts, leap_block=None):
+        """Tau-leaping, reference src/_BirthDeath.pyx:2293-2346.  `leap_block` (not in the reference): run the call in
+        blocks of that many leaps and keep finished blocks as a sparse archive instead of dense count rows."""
         h = self._sync_params()
-        h.simulate_tau(int(iterations), int(sample_size), float(time), int(attempts))
+        if leap_block is None:
+            h.simulate_tau(int(iterations), int(sample_size), float(time), int(attempts))
+        else:
+            h.simulate_tau_blocks(int(iterations), int(sample_size), float(time), int(attempts), int(leap_block))
         self.first_simulation = True
         self._genealogy_done = False
         self._refresh_host_state()

@@ -455,7 +455,7 @@ static int grow2d(Handle *h, T **buf, long long old_cap, long long new_cap, long
 static int ensure_ev_cap(Handle *h, long long need) {
     DevState &st = h->st;
     if (need <= st.ev_cap) return 0;
-    long long nc = need;
+    long long nc = std::max(need, std::min(st.ev_cap + st.ev_cap / 2, need + (1LL << 16)));  // blocked runs: not one regrow per block
     if (grow2d(h, &st.ev_time, st.ev_cap, nc, h->ev_bound, 1)) return 1;
     if (grow2d(h, &st.ev_desc, st.ev_cap, nc, h->ev_bound, 1)) return 1;
     st.ev_cap = nc;
@@ -464,7 +464,7 @@ static int ensure_ev_cap(Handle *h, long long need) {
 static int ensure_leap_cap(Handle *h, long long need) {  // tau_tt and the archive's offsets: all leaps of a replicate
     DevState &st = h->st;
     if (need <= st.leap_cap) return 0;
-    long long nc = need;
+    long long nc = std::max(need, std::min(st.leap_cap + st.leap_cap / 2, need + (1LL << 16)));
     if (grow2d(h, &st.tau_tt, st.leap_cap, nc, h->leap_bound, 2)) return 1;
     // sp_off rows have one more entry than there are leaps: grow with the row strides old_cap + 1 -> new_cap + 1
     {
@@ -488,6 +488,28 @@ static int ensure_dense_cap(Handle *h, long long need) {  // dense count rows: t
     if (need <= st.dense_cap) return 0;
     if (grow2d(h, &st.tau_counts, st.dense_cap, need, h->dense_bound, (size_t)st.D.Pp)) return 1;
     st.dense_cap = need;
+    return 0;
+}
+
+// The host-side bounds grow by `iterations` per call (the device decides how many rows a replicate really writes); at a
+// point where the stream is idle anyway they are brought back to the true maxima, so that the next call sizes the log
+// for what is there plus what it may add -- a direct call of 10^7 iterations that stopped after 1,500 events must not
+// make every later call carry 10^7 rows of capacity per replicate.
+static int tighten_bounds(Handle *h) {
+    const size_t R = h->R;
+    std::vector<long long> ctr(R * NCOUNT), base(R);
+    CK(cudaMemcpyAsync(ctr.data(), h->st.counters, R * NCOUNT * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(base.data(), h->st.dense_base, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    long long ev = 0, lp = 0, dn = 0;
+    for (size_t r = 0; r < R; r++) {
+        ev = std::max(ev, ctr[r * NCOUNT + C_EVPTR]);
+        lp = std::max(lp, ctr[r * NCOUNT + C_LEAPS]);
+        dn = std::max(dn, ctr[r * NCOUNT + C_LEAPS] - base[r]);
+    }
+    h->ev_bound = std::min(h->ev_bound, ev);
+    h->leap_bound = std::min(h->leap_bound, lp);
+    h->dense_bound = std::min(h->dense_bound, dn);
     return 0;
 }
 
@@ -517,33 +539,81 @@ static SimArgs make_args(int64_t iterations, int64_t sample_size, float t, int64
     a.time = t;
     a.has_time = !(t == -1.0f);
     a.attempts = attempts < 1 ? 1 : attempts;
+    a.cont = 0;
     return a;
 }
 
 extern "C" {
 
-int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
-                       int64_t attempts) {
-    CK(cudaSetDevice(h->device));
-    if (iterations < 0) return fail("iterations must be >= 0");
+// one launch of the tau kernel for `iterations` more leaps per replicate.  tau_mode 1: a call of SimulatePopulation_tau
+// (FirstInfection when nobody is infectious, :2302-2303); 2: the continuation of one (vgsim_simulate_tau_blocks).
+static int tau_call(Handle *h, int64_t iterations, int64_t sample_size, float epidemic_time, int64_t attempts, int tau_mode,
+                    bool timed) {
     if (ensure_ev_cap(h, h->ev_bound + iterations) || ensure_leap_cap(h, h->leap_bound + iterations) ||
         ensure_dense_cap(h, h->dense_bound + iterations))
         return 1;
-    if (prepare(h, 1)) return 1;
+    if (prepare(h, tau_mode)) return 1;
     SimArgs a = make_args(iterations, sample_size, epidemic_time, attempts);
-    next_timer(h);
-    CK(cudaEventRecord(h->ev_k0, h->stream));
+    a.cont = tau_mode == 2;
+    if (timed) {
+        next_timer(h);
+        CK(cudaEventRecord(h->ev_k0, h->stream));
+    }
     int uniform_pp = h->rep_pp_host.empty() ? 0 : h->rep_pp_host[0];  // every replicate on one parameter point?
     for (int v : h->rep_pp_host)
         if (v != uniform_pp) uniform_pp = -1;
     cudaError_t e = launch_tau(h->st, a, h->stream, h->num_sms, h->tau_variant, uniform_pp, h->tau_order);
     if (e != cudaSuccess) return fail(std::string("tau kernel: ") + cudaGetErrorString(e));
-    CK(cudaEventRecord(h->ev_k1, h->stream));
-    h->ev_valid = true;
+    if (timed) {
+        CK(cudaEventRecord(h->ev_k1, h->stream));
+        h->ev_valid = true;
+    }
     h->launches++;
     h->ev_bound += iterations;
     h->leap_bound += iterations;
     h->dense_bound += iterations;
+    return 0;
+}
+
+int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
+                       int64_t attempts) {
+    CK(cudaSetDevice(h->device));
+    if (iterations < 0) return fail("iterations must be >= 0");
+    return tau_call(h, iterations, sample_size, epidemic_time, attempts, 1, true);
+}
+
+// One SimulatePopulation_tau call of `iterations` leaps run as blocks of `leap_block` leaps; the dense rows of a finished
+// block go to the sparse archive before the next block starts, so the dense log never holds more than one block per
+// replicate.  The blocks are one call to the reference's eyes: FirstInfection only before the first, the stop conditions
+// carry over, the run ends when no replicate used up its block.  The timer pair spans the whole run (tau kernels and
+// the archive passes between them).
+int vgsim_simulate_tau_blocks(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time, int64_t attempts,
+                              int64_t leap_block) {
+    CK(cudaSetDevice(h->device));
+    if (iterations < 0) return fail("iterations must be >= 0");
+    if (leap_block < 1) return fail("leap_block must be >= 1");
+    // the extinction retry looks at the call's `iterations > 100` (:2331): a block must not hide that from the kernel
+    if (iterations > 100 && leap_block <= 100) leap_block = 101;
+    next_timer(h);
+    cudaEvent_t k0 = h->ev_k0, k1 = h->ev_k1;
+    CK(cudaEventRecord(k0, h->stream));
+    if (tighten_bounds(h)) return 1;
+    int64_t done = 0;
+    bool first = true;
+    while (done < iterations || first) {
+        const int64_t n = std::min<int64_t>(leap_block, iterations - done);
+        if (tau_call(h, n, sample_size, epidemic_time, first ? attempts : 1, first ? 1 : 2, false)) return 1;
+        first = false;
+        done += n;
+        if (done >= iterations) break;
+        if (tighten_bounds(h)) return 1;
+        if (h->dense_bound < n) break;  // no replicate used up its block: every one of them met a stop condition
+        if (vgsim_archive_tau_log(h)) return 1;
+    }
+    CK(cudaEventRecord(k1, h->stream));
+    h->ev_k0 = k0;
+    h->ev_k1 = k1;
+    h->ev_valid = true;
     return 0;
 }
 
@@ -556,45 +626,58 @@ int vgsim_archive_tau_log(vgsim_handle h) {
     DevState &st = h->st;
     if (h->dense_bound == 0 || st.dense_cap == 0) return 0;
     const size_t R = h->R;
-    int *cnt = nullptr, *need = nullptr;
-    CK(cudaMalloc(&cnt, R * st.dense_cap * 4));
-    CK(cudaMalloc(&need, R * 4));
+    if (h->arch_cnt_cap < R * st.dense_cap) {
+        if (h->arch_cnt) dfree(h, h->arch_cnt);
+        h->arch_cnt = nullptr;
+        h->arch_cnt_cap = 0;
+        if (dalloc(h, &h->arch_cnt, R * st.dense_cap)) return 1;
+        h->arch_cnt_cap = R * st.dense_cap;
+    }
+    if (!h->arch_need && dalloc(h, &h->arch_need, R)) return 1;
+    int *cnt = h->arch_cnt, *need = h->arch_need;
     cudaError_t e = launch_archive_count(st, cnt, need, h->stream);
     h->launches += 2;
     std::vector<int> hneed(R), hn(R);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hneed.data(), need, R * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(hn.data(), st.sp_n, R * 4, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) {
-        cudaFree(cnt);
-        cudaFree(need);
-        return fail(std::string("archive (count): ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(std::string("archive (count): ") + cudaGetErrorString(e));
+    long long want = 0, keep = 0;
+    for (size_t r = 0; r < R; r++) {
+        want = std::max(want, (long long)hn[r] + hneed[r]);
+        keep = std::max(keep, (long long)hn[r]);
     }
-    long long want = 0;
-    for (size_t r = 0; r < R; r++) want = std::max(want, (long long)hn[r] + hneed[r]);
-    if (want > 2147483647LL) {
-        cudaFree(cnt);
-        cudaFree(need);
-        return fail("archive: more than 2^31 entries in one replicate");
-    }
+    if (want > 2147483647LL) return fail("archive: more than 2^31 entries in one replicate");
     if (want > st.sp_cap) {
-        long long nc = std::max(want + want / 2, (long long)1024);   // room for the next blocks too
-        long long keep = 0;
-        for (size_t r = 0; r < R; r++) keep = std::max(keep, (long long)hn[r]);
-        if (grow2d(h, &st.sp_ent, st.sp_cap, nc, keep, 1)) {
-            cudaFree(cnt);
-            cudaFree(need);
-            return 1;
-        }
+        // room for the blocks to come: the archive of a growing epidemic grows faster than linearly
+        long long nc = std::max(2 * want, (long long)1024);
+        if (grow2d(h, &st.sp_ent, st.sp_cap, nc, keep, 1)) return 1;
         st.sp_cap = nc;
     }
     e = launch_archive_write(st, cnt, need, h->stream);
-    h->launches++;
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(cnt);
-    cudaFree(need);
+    h->launches += 2;
     if (e != cudaSuccess) return fail(std::string("archive (write): ") + cudaGetErrorString(e));
     h->dense_bound = 0;
+    return 0;
+}
+
+int vgsim_archive_stats(vgsim_handle h, int64_t *entries_total, int64_t *entries_max, int64_t *leaps_archived) {
+    CK(cudaSetDevice(h->device));
+    const size_t R = h->R;
+    std::vector<int> n(R);
+    std::vector<long long> base(R);
+    CK(cudaMemcpyAsync(n.data(), h->st.sp_n, R * 4, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(base.data(), h->st.dense_base, R * 8, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    int64_t tot = 0, mx = 0, la = 0;
+    for (size_t r = 0; r < R; r++) {
+        tot += n[r];
+        mx = std::max<int64_t>(mx, n[r]);
+        la += base[r];
+    }
+    if (entries_total) *entries_total = tot;
+    if (entries_max) *entries_max = mx;
+    if (leaps_archived) *leaps_archived = la;
     return 0;
 }
 
@@ -622,6 +705,7 @@ int vgsim_simulate_direct(vgsim_handle h, int64_t iterations, int64_t sample_siz
 int vgsim_synchronize(vgsim_handle h) {
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
+    if (tighten_bounds(h)) return 1;
     std::vector<int> err(h->R);
     CK(cudaMemcpy(err.data(), h->st.err, (size_t)h->R * 4, cudaMemcpyDeviceToHost));
     int all = 0;

@@ -172,6 +172,8 @@ struct SimArgs {
     float time;     // C float like the reference (quirk Q1)
     int has_time;
     long long attempts;
+    int cont;       // 1: a later block of one SimulatePopulation_tau call (vgsim_simulate_tau_blocks) -- the first attempt
+                    // keeps the epoch of the block before, so that the blocks draw what the single call would have drawn
 };
 
 }  // namespace vg

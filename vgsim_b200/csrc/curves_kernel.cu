@@ -150,7 +150,22 @@ __global__ void __launch_bounds__(512, 1) curves_kernel(const DevState st, const
                     }
                     continue;
                 }
-                const int4 *row = reinterpret_cast<const int4 *>(st.tau_counts + ((size_t)r * st.leap_cap + unpack_multi(dk)) * D.Pp);
+                const long long leap = unpack_multi(dk), dbase = st.dense_base[r];
+                if (leap < dbase) {  // archived leap: (channel, count) pairs, applied 32 at a time (order does not matter here)
+                    const int *soff = st.sp_off + (size_t)r * (st.leap_cap + 1);
+                    const int2 *ent = st.sp_ent + (size_t)r * st.sp_cap;
+                    const int e1 = soff[leap + 1];
+                    __syncwarp();
+                    for (int e = soff[leap] + lane; e < e1; e += 32) {
+                        const int2 en = __ldcs(ent + e);
+                        int mty, mh, mp, mnh, mnp;
+                        decode_record(en.x, D, pp, mty, mh, mp, mnh, mnp);
+                        curve_apply(mty, mh, mp, mnh, mnp, (long long)en.y, H, S, I, Sx, rem, smp);
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                const int4 *row = reinterpret_cast<const int4 *>(st.tau_counts + ((size_t)r * st.dense_cap + (leap - dbase)) * D.Pp);
                 const int n16 = D.Pp >> 2;
                 int qn = 0;  // entries in the warp's queue (uniform)
                 auto flush = [&]() {  // decode + apply the queued non-zero counts, 32 at a time with every lane busy

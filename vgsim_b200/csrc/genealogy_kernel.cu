@@ -318,7 +318,122 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                     I[ct] -= 1;
                 } else if (ty == EV_MULTITYPE) {  // :869-993
                     const long long leap = unpack_multi(d);
-                    const int *row = st.tau_counts + ((size_t)r * st.leap_cap + leap) * D.Pp;
+                    // one record (channel rc, count num) of the leap: :869-993
+                    auto record = [&](int rc, long long num) {
+                    int mty, mh, mp, mnh, mnp;
+                    decode_record(rc, D, pp, mty, mh, mp, mnh, mnp);
+                    const int cell = mp * H + mh;  // the cell that receives the parked (new) lineages
+                    int nnl = 0;
+                    if (mty == EV_BIRTH) {  // :879-915
+                        int lbs = L.size(cell);
+                        const long long lbs_e = I[cell];
+                        long long k = 0;
+                        if (lbs != 0)
+                            k = hypergeometric(g, (long long)(((double)lbs * ((double)lbs - 1.0)) / 2.0),
+                                               ((lbs_e * (lbs_e - 1)) / 2) - (((long long)lbs * (lbs - 1)) / 2), num);
+                        for (long long i = 0; i < k; i++) {
+                            if (lbs < 2) {  // the reference runs into UB here; clamp and count
+                                clamped++;
+                                break;
+                            }
+                            int n1 = (int)floor((double)lbs * g.next_double());
+                            int n2 = (int)floor((double)(lbs - 1) * g.next_double());
+                            if (n2 >= n1) n2 += 1;
+                            int id1 = L.get(cell, n1), id2 = L.get(cell, n2);
+                            int id3 = O.new_node(mp, et);
+                            nl[nnl++] = id3;
+                            if (n1 == lbs - 1) {
+                                L.pop(cell);
+                                L.set(cell, n2, L.get(cell, lbs - 2));
+                                L.pop(cell);
+                            } else if (n2 == lbs - 1) {
+                                L.pop(cell);
+                                L.set(cell, n1, L.get(cell, lbs - 2));
+                                L.pop(cell);
+                            } else {
+                                L.set(cell, n1, L.get(cell, lbs - 1));
+                                L.pop(cell);
+                                L.set(cell, n2, L.get(cell, lbs - 2));
+                                L.pop(cell);
+                            }
+                            O.parent[id1] = id3;
+                            O.parent[id2] = id3;
+                            lbs -= 2;
+                        }
+                        I[cell] -= num;
+                    } else if (mty == EV_DEATH) {  // :916-917
+                        I[cell] += num;
+                    } else if (mty == EV_SAMPLING) {  // :918-925
+                        I[cell] += num;
+                        for (long long i = 0; i < num; i++) nl[nnl++] = O.new_node(mp, et);
+                    } else if (mty == EV_MUTATION) {  // :926-941
+                        const int cnew = mp * H + mnh;
+                        int lbs = L.size(cnew);
+                        long long k = 0;
+                        if (lbs != 0) k = hypergeometric(g, lbs, I[cnew] - lbs, num);
+                        for (long long i = 0; i < k; i++) {
+                            int n1 = (int)floor((double)lbs * g.next_double());
+                            int id1 = L.get(cnew, n1);
+                            L.remove_at(cnew, n1);
+                            nl[nnl++] = id1;
+                            O.add_mutation(id1, mh, mnh, et);
+                            lbs -= 1;
+                        }
+                        I[cnew] -= num;
+                        I[cell] += num;
+                    } else if (mty == EV_MIGRATION) {  // :944-982  (mp = source, mnp = target)
+                        const int ct = mnp * H + mh;
+                        int lbs = L.size(ct);
+                        if (lbs != 0) {
+                            long long k = hypergeometric(g, lbs, I[ct] - lbs, num);
+                            int lbss = L.size(cell);
+                            long long k2 = 0;
+                            if (!(k == 0 || lbss == 0)) k2 = hypergeometric(g, lbss, I[cell] - lbss, k);
+                            for (long long i = 0; i < k2; i++) {
+                                int nt = (int)floor((double)lbs * g.next_double());
+                                int ns = (int)floor((double)lbss * g.next_double());
+                                int idt = L.get(ct, nt), ids = L.get(cell, ns);
+                                int id3 = O.new_node(mp, et);
+                                L.remove_at(cell, ns);
+                                L.remove_at(ct, nt);
+                                nl[nnl++] = id3;
+                                O.parent[idt] = id3;
+                                O.parent[ids] = id3;
+                                O.add_migration(idt, et, mp, mnp);
+                                lbss -= 1;
+                                lbs -= 1;
+                            }
+                            for (long long i = 0; i < k - k2; i++) {
+                                int nt = (int)floor((double)lbs * g.next_double());
+                                nl[nnl++] = L.get(ct, nt);
+                                L.remove_at(ct, nt);
+                                lbs -= 1;
+                            }
+                        }
+                        I[ct] -= num;
+                    }
+                    // merge the parked lineages back, last parked first (:987-993; only this record's
+                    // receiving cell can hold any — untouched cells have nothing parked and no delta)
+                    for (int i = nnl - 1; i >= 0; i--) L.push(cell, nl[i]);
+                    if (g.err | L.err | O.err) bad = 1;
+                    };
+                    const long long dbase = st.dense_base[r];
+                    if (leap < dbase) {
+                        // archived leap: its non-zero counts are (channel, count) pairs in ascending channel order
+                        const int *soff = st.sp_off + (size_t)r * (st.leap_cap + 1);
+                        const int2 *ent = st.sp_ent + (size_t)r * st.sp_cap;
+                        const int e0 = soff[leap], e1 = soff[leap + 1];
+                        for (int eb = e0; eb < e1 && !bad; eb += 32) {
+                            const int2 mine = eb + lane < e1 ? __ldcs(ent + eb + lane) : make_int2(0, 0);
+                            const int nn = e1 - eb < 32 ? e1 - eb : 32;
+                            for (int k = 0; k < nn; k++) {
+                                const int rc = __shfl_sync(0xffffffffu, mine.x, k), rn = __shfl_sync(0xffffffffu, mine.y, k);
+                                record(rc, (long long)rn);
+                                if (bad) break;
+                            }
+                        }
+                    } else {
+                    const int *row = st.tau_counts + ((size_t)r * st.dense_cap + (leap - dbase)) * D.Pp;
                     // the row is scanned in ascending channel order, 128 counts (one int4 per lane) per step; eight steps'
                     // worth of loads (4 KB per warp) are in flight at a time -- one dependent 128-byte load per step made
                     // the scan latency-bound (11 s for 32 world-shape replicates x 1,200 leaps of 493,400 channels)
@@ -345,106 +460,12 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                             for (int e4 = 0; e4 < 4; e4++) {
                             const long long num = e4 == 0 ? q0 : e4 == 1 ? q1 : e4 == 2 ? q2 : q3;
                             if (num == 0) continue;
-                            int mty, mh, mp, mnh, mnp;
-                            decode_record((base4 + b) * 4 + e4, D, pp, mty, mh, mp, mnh, mnp);
-                            const int cell = mp * H + mh;  // the cell that receives the parked (new) lineages
-                            int nnl = 0;
-                            if (mty == EV_BIRTH) {  // :879-915
-                                int lbs = L.size(cell);
-                                const long long lbs_e = I[cell];
-                                long long k = 0;
-                                if (lbs != 0)
-                                    k = hypergeometric(g, (long long)(((double)lbs * ((double)lbs - 1.0)) / 2.0),
-                                                       ((lbs_e * (lbs_e - 1)) / 2) - (((long long)lbs * (lbs - 1)) / 2), num);
-                                for (long long i = 0; i < k; i++) {
-                                    if (lbs < 2) {  // the reference runs into UB here; clamp and count
-                                        clamped++;
-                                        break;
-                                    }
-                                    int n1 = (int)floor((double)lbs * g.next_double());
-                                    int n2 = (int)floor((double)(lbs - 1) * g.next_double());
-                                    if (n2 >= n1) n2 += 1;
-                                    int id1 = L.get(cell, n1), id2 = L.get(cell, n2);
-                                    int id3 = O.new_node(mp, et);
-                                    nl[nnl++] = id3;
-                                    if (n1 == lbs - 1) {
-                                        L.pop(cell);
-                                        L.set(cell, n2, L.get(cell, lbs - 2));
-                                        L.pop(cell);
-                                    } else if (n2 == lbs - 1) {
-                                        L.pop(cell);
-                                        L.set(cell, n1, L.get(cell, lbs - 2));
-                                        L.pop(cell);
-                                    } else {
-                                        L.set(cell, n1, L.get(cell, lbs - 1));
-                                        L.pop(cell);
-                                        L.set(cell, n2, L.get(cell, lbs - 2));
-                                        L.pop(cell);
-                                    }
-                                    O.parent[id1] = id3;
-                                    O.parent[id2] = id3;
-                                    lbs -= 2;
-                                }
-                                I[cell] -= num;
-                            } else if (mty == EV_DEATH) {  // :916-917
-                                I[cell] += num;
-                            } else if (mty == EV_SAMPLING) {  // :918-925
-                                I[cell] += num;
-                                for (long long i = 0; i < num; i++) nl[nnl++] = O.new_node(mp, et);
-                            } else if (mty == EV_MUTATION) {  // :926-941
-                                const int cnew = mp * H + mnh;
-                                int lbs = L.size(cnew);
-                                long long k = 0;
-                                if (lbs != 0) k = hypergeometric(g, lbs, I[cnew] - lbs, num);
-                                for (long long i = 0; i < k; i++) {
-                                    int n1 = (int)floor((double)lbs * g.next_double());
-                                    int id1 = L.get(cnew, n1);
-                                    L.remove_at(cnew, n1);
-                                    nl[nnl++] = id1;
-                                    O.add_mutation(id1, mh, mnh, et);
-                                    lbs -= 1;
-                                }
-                                I[cnew] -= num;
-                                I[cell] += num;
-                            } else if (mty == EV_MIGRATION) {  // :944-982  (mp = source, mnp = target)
-                                const int ct = mnp * H + mh;
-                                int lbs = L.size(ct);
-                                if (lbs != 0) {
-                                    long long k = hypergeometric(g, lbs, I[ct] - lbs, num);
-                                    int lbss = L.size(cell);
-                                    long long k2 = 0;
-                                    if (!(k == 0 || lbss == 0)) k2 = hypergeometric(g, lbss, I[cell] - lbss, k);
-                                    for (long long i = 0; i < k2; i++) {
-                                        int nt = (int)floor((double)lbs * g.next_double());
-                                        int ns = (int)floor((double)lbss * g.next_double());
-                                        int idt = L.get(ct, nt), ids = L.get(cell, ns);
-                                        int id3 = O.new_node(mp, et);
-                                        L.remove_at(cell, ns);
-                                        L.remove_at(ct, nt);
-                                        nl[nnl++] = id3;
-                                        O.parent[idt] = id3;
-                                        O.parent[ids] = id3;
-                                        O.add_migration(idt, et, mp, mnp);
-                                        lbss -= 1;
-                                        lbs -= 1;
-                                    }
-                                    for (long long i = 0; i < k - k2; i++) {
-                                        int nt = (int)floor((double)lbs * g.next_double());
-                                        nl[nnl++] = L.get(ct, nt);
-                                        L.remove_at(ct, nt);
-                                        lbs -= 1;
-                                    }
-                                }
-                                I[ct] -= num;
-                            }
-                            // merge the parked lineages back, last parked first (:987-993; only this record's
-                            // receiving cell can hold any — untouched cells have nothing parked and no delta)
-                            for (int i = nnl - 1; i >= 0; i--) L.push(cell, nl[i]);
-                            if (g.err | L.err | O.err) bad = 1;
+                            record((base4 + b) * 4 + e4, num);
                             if (bad) break;
                             }  // e4
                             if (bad) break;
                         }
+                    }
                     }
                 } else {
                     bad = 1;

@@ -55,6 +55,8 @@ struct Handle {
     double *summaries = nullptr;  // [R][VGSIM_NSUMMARY]
     int *work = nullptr;           // [4] atomic work counters of the kernels that hand out replicates dynamically
     int *tau_order = nullptr;      // [2R] scratch of the tau kernel's size-sorted schedule (weights, order)
+    int *arch_cnt = nullptr, *arch_need = nullptr;  // scratch of vgsim_archive_tau_log: non-zero counts per dense row / per replicate
+    size_t arch_cnt_cap = 0;
     std::vector<int> rep_pp_host;  // host copy of the replicate -> parameter point map
     // event pairs that bracket the hot kernels on the handle's stream: a ring, so that a pipelined driver can read the
     // duration of launch `id` after the fact (vgsim_kernel_ms) instead of blocking on every launch

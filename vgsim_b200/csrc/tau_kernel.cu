@@ -924,15 +924,16 @@ __global__ void __launch_bounds__(TAU_TEAM * TEAMS, 1) tau_kernel(const __grid_c
         unsigned epoch = st.epoch[r];
         long long good_attempt = ctr[C_GOOD];
         const long long ev_limit = evptr + a.iterations;  // events.ptr < events.size (:2312), intended capacity
-        int *tau_counts = st.tau_counts + (size_t)r * st.leap_cap * D.Pp;
+        long long dbase = st.dense_base[r];  // leaps whose rows went to the archive: leap L is dense row L - dbase
+        int *tau_counts = st.tau_counts + (size_t)r * st.dense_cap * D.Pp;
         bool lists_ready = true;  // false: segcnt is current but act/dstart/masks still have to be written
 
         for (long long attempt = 0; attempt < a.attempts; attempt++) {
-            epoch++;
+            if (!(a.cont && attempt == 0)) epoch++;
             if (s.flags[8] != 0) {
-                while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
+                while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap && leaps - dbase < st.dense_cap &&
                        (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
-                    int *row = tau_counts + (size_t)leaps * D.Pp;
+                    int *row = tau_counts + (size_t)(leaps - dbase) * D.Pp;
                     // A leap is one GENERATION of the CTA: every team passes exactly five CTA-wide barriers (here, after
                     // Q, after the pressure sums, inside the tau minimum, after the apply pass), so all teams of the SM
                     // enter every long phase together and share its instruction fetch.  The barriers inside the
@@ -1163,7 +1164,12 @@ __global__ void __launch_bounds__(TAU_TEAM * TEAMS, 1) tau_kernel(const __grid_c
                 lockdown_pass(st, r, D, s, pp, eff_g, t, s.tot);
                 team_sync();
                 good_attempt = 0;
-                if (tid == 0) ctr[C_MIGN] = 0;
+                dbase = 0;  // the archive of the wiped leaps goes with them
+                if (tid == 0) {
+                    ctr[C_MIGN] = 0;
+                    st.dense_base[r] = 0;
+                    st.sp_n[r] = 0;
+                }
             } else {
                 good_attempt = attempt + 1;
                 break;

@@ -1027,30 +1027,25 @@ __device__ __forceinline__ int w_round(int item, int mode, int nAct, double tau,
     return ro.need[0] + ro.need[1];
 }
 
-// store the unsettled draws of one half of the round (words 2*half, 2*half+1; the caller has made room): inversion
-// entries from the bottom, PTRS from the top.  (Explicit selects instead of indexing with `half`: the per-word arrays
-// must stay in registers.)
-template <class WSQ>
-__device__ __forceinline__ void w_push(const RoundOut &ro, int half, const WSQ &s, DrawState &q) {
+// store the unsettled draws of words [W0, W1) of the round (the caller has made room): inversion entries from the
+// bottom, PTRS from the top
+template <int W0, int W1, class WSQ>
+__device__ __forceinline__ void w_push(const RoundOut &ro, const WSQ &s, DrawState &q) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u, me = 1u << lane;
 #pragma unroll
-    for (int ww = 0; ww < 2; ww++) {
-        const int w = 2 * half + ww;
-        const unsigned mi = half ? (ww ? ro.mi[3] : ro.mi[2]) : (ww ? ro.mi[1] : ro.mi[0]);
-        const unsigned mp = half ? (ww ? ro.mp[3] : ro.mp[2]) : (ww ? ro.mp[1] : ro.mp[0]);
-        const double lm = half ? (ww ? ro.lam[3] : ro.lam[2]) : (ww ? ro.lam[1] : ro.lam[0]);
-        const uint32_t hi = half ? (ww ? ro.w4.w : ro.w4.z) : (ww ? ro.w4.y : ro.w4.x);
-        const bool inv = (mi & me) != 0, ptr = (mp & me) != 0;
+    for (int w = W0; w < W1; w++) {
+        const bool inv = (ro.mi[w] & me) != 0, ptr = (ro.mp[w] & me) != 0;
         if (inv || ptr) {
-            const int e = inv ? q.ninv + __popc(mi & lt) : s.qcap - 1 - (q.nptr + __popc(mp & lt));
+            const uint32_t hi = w == 0 ? ro.w4.x : w == 1 ? ro.w4.y : w == 2 ? ro.w4.z : ro.w4.w;
+            const int e = inv ? q.ninv + __popc(ro.mi[w] & lt) : s.qcap - 1 - (q.nptr + __popc(ro.mp[w] & lt));
             const int l = (ro.lb < 0) ? (w < 2 ? w : w == 2 ? TW_L_TOT_MUT : TW_L_TOT_MIG) : ro.lb + w;
-            s.qlam[e] = lm;
+            s.qlam[e] = ro.lam[w];
             s.qhi[e] = (int)hi;
             s.qoc[e] = (int)((unsigned)ro.owner | ((unsigned)l << 20));
         }
-        q.ninv += __popc(mi);
-        q.nptr += __popc(mp);
+        q.ninv += __popc(ro.mi[w]);
+        q.nptr += __popc(ro.mp[w]);
     }
 }
 
@@ -1223,14 +1218,15 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
         unsigned epoch = st.epoch[r];
         long long good_attempt = ctr[C_GOOD];
         const long long ev_limit = evptr + a.iterations;
-        int *tau_counts = st.tau_counts + (size_t)r * st.leap_cap * D.Pp;
+        long long dbase = st.dense_base[r];  // leaps whose rows went to the archive: leap L is dense row L - dbase
+        int *tau_counts = st.tau_counts + (size_t)r * st.dense_cap * D.Pp;
 
         for (long long attempt = 0; attempt < a.attempts; attempt++) {
-            epoch++;
+            if (!(a.cont && attempt == 0)) epoch++;
             if (nAct != 0) {
-                while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap &&
+                while (evptr < ev_limit && evptr < st.ev_cap && leaps < st.leap_cap && leaps - dbase < st.dense_cap &&
                        (a.sample_size == -1 || sC < a.sample_size) && (!a.has_time || t < (double)a.time)) {
-                    int *row = tau_counts + (size_t)leaps * D.Pp;
+                    int *row = tau_counts + (size_t)(leaps - dbase) * D.Pp;
                     const bool meet = gsync && (L.gevery <= 1 || gen % L.gevery == 0);
                     gen++;
                     if (meet) {
@@ -1242,7 +1238,7 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                     //         leap of the call, Restart), then start on the next row; 1-2. drifts and tau
                     if (pre_row != (int)leaps) wp.begin(row);
                     wp.finish(n32);
-                    if (leaps + 1 < st.leap_cap && evptr + 1 < ev_limit && evptr + 1 < st.ev_cap) {
+                    if (leaps + 1 < st.leap_cap && leaps + 1 - dbase < st.dense_cap && evptr + 1 < ev_limit && evptr + 1 < st.ev_cap) {
                         wp.begin(row + D.Pp);
                         pre_row = (int)leaps + 1;
                     } else {
@@ -1294,17 +1290,19 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                         for (;;) {
                             const bool inx = xbase < xlimit;
                             RoundOut ro;
-                            ro.need[0] = ro.need[1] = 0;
+                            int pushes = 0;
                             if (!flush)
-                                w_round((inx ? xbase : pbase) + lane, inx ? 1 : 0, nAct, tau, variant, D, s, eff, g, L, ctx, dq, ro);
-                            // the round's entries go in as two halves (words 0-1, words 2-3: at most 64 each), draining
-                            // first whenever the next half does not fit; the iteration after the last round only drains
-#pragma unroll 1
-                            for (int half = 0; half < 2; half++) {
-                                const bool whole = half == 0 && dq.ninv + dq.nptr + ro.need[0] + ro.need[1] <= s.qcap;
-                                if ((flush && half == 0) || (!whole && dq.ninv + dq.nptr + (half ? ro.need[1] : ro.need[0]) > s.qcap))
-                                    w_drain(row, D, s, eff, g, L, ctx, tr, dq, flush);
-                                if (!flush) w_push(ro, half, s, dq);
+                                pushes = w_round((inx ? xbase : pbase) + lane, inx ? 1 : 0, nAct, tau, variant, D, s, eff, g, L, ctx, dq, ro);
+                            if (flush || dq.ninv + dq.nptr + pushes > s.qcap) w_drain(row, D, s, eff, g, L, ctx, tr, dq, flush);
+                            if (flush) break;
+                            if (pushes <= s.qcap) {
+                                w_push<0, 4>(ro, s, dq);
+                            } else {
+                                // (cold) a round can leave up to 128 entries, the queue holds 96: two halves of <= 64 with a
+                                // drain in between.  Needs > 3 unsettled draws per lane on average -- dense states only.
+                                w_push<0, 2>(ro, s, dq);
+                                w_drain(row, D, s, eff, g, L, ctx, tr, dq, false);
+                                w_push<2, 4>(ro, s, dq);
                             }
                             if (flush) break;
                             if (inx) {
@@ -1411,7 +1409,12 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
                 nAct = w_lists<WSX<MASKS>, false>(D, s, nhap, wp, 0, n32);
                 flips_total += w_lockdown(st, r, D, s, pp, eff_g, t);
                 good_attempt = 0;
-                if (lane == 0) ctr[C_MIGN] = 0;
+                dbase = 0;  // the archive of the wiped leaps goes with them
+                if (lane == 0) {
+                    ctr[C_MIGN] = 0;
+                    st.dense_base[r] = 0;
+                    st.sp_n[r] = 0;
+                }
             } else {
                 good_attempt = attempt + 1;
                 break;
