@@ -567,6 +567,14 @@ def gpu_arm(args, rank, world, local_rank):
                            "events_per_s": w_ev / (w_ms * 1e-3), "leaps_per_s": w_lp / (w_ms * 1e-3),
                            "events_per_leap": w_ev / max(w_lp, 1.0), "ms_per_step": w_ms / args.steps, "kernel_ms": k_ms,
                            "achieved_GBps": ach, "frac": ach / peak})
+        if args.phases:  # timing tap: per-window critical-path cycles of the kernel's phases (lane 0 of every warp)
+            pn = (["wipe+lists+Q", "drifts+tau", "primary draws", "slow-path drain", "feasibility", "apply", "lockdown vote"]
+                  if KERNEL == "tau_kernel" else
+                  ["-", "row wipe issue + drifts + tau", "primary draws + drain", "feasibility", "apply + lists", "-", "-"])
+            for wl, rw in zip(wlines, res_w):
+                pcw = rw["phase_cycles"]
+                nlw = max(int(pcw[7]), 1)
+                wl["phase_cycles_per_leap"] = {n: round(float(pcw[i]) / nlw, 1) for i, n in enumerate(pn) if n != "-"}
         k_ms, achieved = wlines[0]["kernel_ms"], wlines[0]["achieved_GBps"]
         h2d = R * 8 + R * K * (S + H) * 8
         d2h = R * (_capi.NCOUNTERS + 1) * 8 + R * K * (S + H) * 8

@@ -30,11 +30,18 @@ BLOCK = int(sys.argv[5]) if len(sys.argv) > 5 else 101
 (U, K, S), setup = SCENARIOS["w"]
 e = Eng(U, K, S, 4242, False, False, int(1e6), 0.0, replicates=R)
 setup(e)
+def note(msg):
+    sys.stderr.write("[%7.1f s] %s\n" % (time.time() - T00, msg))
+    sys.stderr.flush()
+
+
+T00 = time.time()
 out = {"config": "world: K=%d demes x H=%d x S=%d, 1e6 per deme, %d replicates" % (K, 4 ** U, S, R)}
 t0 = time.time()
 e.SimulatePopulation(200000, 10 ** 9, T_DIRECT, 200)
 h = e._handle
 out["direct_s"] = time.time() - t0
+note("direct phase done")
 out["direct_kernel_ms"] = h.last_kernel_ms()
 c = e.counters()
 out["direct_events_mean"] = float(c["events"].mean())
@@ -44,6 +51,7 @@ e.SimulatePopulation_tau(MAXL, NS, -1, 200, leap_block=BLOCK if BLOCK > 0 else N
 out["tau_s"] = time.time() - t0
 out["tau_kernel_ms"] = h.last_kernel_ms()  # blocks: first block's start to last block's end, archive passes included
 out["leap_block"] = BLOCK
+note("tau phase done: %.0f ms" % out["tau_kernel_ms"])
 st = h.archive_stats()
 out["archive"] = dict(st, bytes_total=8 * st["entries_total"], dense_bytes_replaced=st["leaps_archived"] * 4 * int(h.P))
 c = e.counters()
@@ -59,6 +67,7 @@ Sx_f, I_f = h.get_state()
 t0 = time.time()
 cv = e.epidemic_curves(16, want=("infectious", "susceptible", "sampled"))
 out["curves_s"] = time.time() - t0
+note("curves done")
 out["curves_kernel_ms"] = h.last_kernel_ms()
 assert np.array_equal(cv["infectious"][:, -1], I_f) and np.array_equal(cv["susceptible"][:, -1], Sx_f)
 tot = cv["infectious"].sum(axis=3) + cv["susceptible"].sum(axis=3)
@@ -70,23 +79,35 @@ t0 = time.time()
 h.genealogy(99, sync=False)
 flags = int(h.synchronize(strict=False))
 out["genealogy_s"] = time.time() - t0
+note("genealogy done")
 # bit 16: a MULTITYPE BIRTH record asked for more coalescences than the cell has lineage pairs; the reference reads
 # past the end of a vector there (src/_BirthDeath.pyx:885-915), the kernel clamps and says so
 out["genealogy_flags"] = flags
 sm = h.summaries()
 nodes, roots = sm[:, 13], sm[:, 16]
-# n sampled leaves coalesced into `roots` trees have 2n - roots nodes (2n-1 when fully coalesced; a replicate whose replay
-# clamped a coalescence count, genealogy flag 16, can be left with a few roots)
-if not np.array_equal(nodes, 2 * c["sCounter"] - roots):
-    bad = np.nonzero(nodes != 2 * c["sCounter"] - roots)[0]
-    out["FAILED_tree_size"] = {"replicates": bad[:8].tolist(), "nodes": nodes[bad[:8]].tolist(), "roots": roots[bad[:8]].tolist(),
-                               "samples": c["sCounter"][bad[:8]].tolist(), "n_bad": int(len(bad))}
+# every replicate's tree: n leaves (the sampled cases), every internal node has exactly two children, a parent is created
+# after its children (larger index) and is not later in time, so `roots` trees over n leaves have 2n - roots nodes
+bad_trees = []
+for r in range(R):
+    parent, pop, tm = h.get_tree(r)
+    n_used = int(nodes[r])
+    parent, tm = parent[:n_used], tm[:n_used]
+    idx = np.nonzero(parent >= 0)[0]
+    kids = np.bincount(parent[idx], minlength=n_used)
+    ok = (np.all(parent[idx] > idx) and np.all(tm[parent[idx]] <= tm[idx] + 1e-12) and set(np.unique(kids)) <= {0, 2}
+          and int((kids == 0).sum()) == int(c["sCounter"][r]) and int((parent < 0).sum()) == int(roots[r])
+          and n_used == 2 * int(c["sCounter"][r]) - int(roots[r]))
+    if not ok:
+        bad_trees.append({"replicate": r, "nodes": n_used, "samples": int(c["sCounter"][r]), "roots": int(roots[r]),
+                          "root_count_host": int((parent < 0).sum()), "children_hist": np.bincount(kids).tolist(),
+                          "parent_not_after_child": int((parent[idx] <= idx).sum())})
+if bad_trees:
+    out["FAILED_trees"] = bad_trees[:8]
+    out["n_bad_trees"] = len(bad_trees)
     print(json.dumps(out))
     sys.exit(1)
+note("tree checks done")
 out.update(tree_nodes_mean=float(nodes.mean()), fully_coalesced=int((roots == 1).sum()), tree_height_mean=float(sm[:, 14].mean()),
            mutation_rows_mean=float(sm[:, 17].mean()), migration_rows_mean=float(sm[:, 18].mean()))
-parent, pop, tm = h.get_tree(0)
-assert (parent == -1).sum() == roots[0] and np.all(parent[parent >= 0] > np.nonzero(parent >= 0)[0]), "parents are created after children"
-assert np.all(tm[parent[parent >= 0]] <= tm[np.nonzero(parent >= 0)[0]] + 1e-12), "a parent is not later than its child"
-out["checks"] += ["every tree has 2n - roots nodes", "parent index > child index and parent time <= child time (replicate 0)"]
+out["checks"] += ["every replicate: leaves = samples, internal nodes have two children, parent index > child index, parent time <= child time, 2n - roots nodes"]
 print(json.dumps(out))

@@ -1095,7 +1095,13 @@ __global__ void summary_kernel(DevState st, const long long *node_off, const int
                 depth = (sc[p] >> 1) + 1;
                 done = true;
             }
-            while (__any_sync(0xffffffffu, !done)) {
+            // (a chain inside a chunk is at most 32 long; the bound keeps a malformed tree -- a parent that is not
+            // younger than its child -- from spinning for ever: its depths stay 0 and the error bit says so)
+            for (int it = 0; it < 33 && __any_sync(0xffffffffu, !done); it++) {
+                if (it == 32) {
+                    if (lane == 0) st.err[r] |= ERR_BADLOG;
+                    break;
+                }
                 int src = (!done) ? p - lo : lane;
                 int pd = __shfl_sync(0xffffffffu, depth, src & 31);
                 int pdone = __shfl_sync(0xffffffffu, (int)done, src & 31);

@@ -319,6 +319,23 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                 } else if (ty == EV_MULTITYPE) {  // :869-993
                     const long long leap = unpack_multi(d);
                     // one record (channel rc, count num) of the leap: :869-993
+                    // The reference's pair / lineage hypergeometrics assume lineages <= individuals in every cell.  Its own
+                    // approximation can break that (a BIRTH record that draws fewer coalescences than the rewind of `num`
+                    // births needs leaves more lineages than individuals): the next draw then has a negative `bad` count
+                    // or asks for more than the urn holds -- numpy raises there.  Here the arguments are brought back
+                    // into range (flag 16), so that every index drawn below stays inside its lineage vector.
+                    auto hyp = [&](long long good, long long bad_n, long long sample) -> long long {
+                        if (bad_n < 0) {
+                            bad_n = 0;
+                            clamped++;
+                        }
+                        if (sample > good + bad_n) {
+                            sample = good + bad_n;
+                            clamped++;
+                        }
+                        const long long k = hypergeometric(g, good, bad_n, sample);
+                        return k < 0 ? 0 : (k > good ? good : k);
+                    };
                     auto record = [&](int rc, long long num) {
                     int mty, mh, mp, mnh, mnp;
                     decode_record(rc, D, pp, mty, mh, mp, mnh, mnp);
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                         const long long lbs_e = I[cell];
                         long long k = 0;
                         if (lbs != 0)
-                            k = hypergeometric(g, (long long)(((double)lbs * ((double)lbs - 1.0)) / 2.0),
+                            k = hyp((long long)(((double)lbs * ((double)lbs - 1.0)) / 2.0),
                                                ((lbs_e * (lbs_e - 1)) / 2) - (((long long)lbs * (lbs - 1)) / 2), num);
                         for (long long i = 0; i < k; i++) {
                             if (lbs < 2) {  // the reference runs into UB here; clamp and count
@@ -370,7 +387,7 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                         const int cnew = mp * H + mnh;
                         int lbs = L.size(cnew);
                         long long k = 0;
-                        if (lbs != 0) k = hypergeometric(g, lbs, I[cnew] - lbs, num);
+                        if (lbs != 0) k = hyp(lbs, I[cnew] - lbs, num);
                         for (long long i = 0; i < k; i++) {
                             int n1 = (int)floor((double)lbs * g.next_double());
                             int id1 = L.get(cnew, n1);
@@ -385,10 +402,10 @@ __global__ void __launch_bounds__(128) genealogy_kernel(DevState st, GenArgs ga)
                         const int ct = mnp * H + mh;
                         int lbs = L.size(ct);
                         if (lbs != 0) {
-                            long long k = hypergeometric(g, lbs, I[ct] - lbs, num);
+                            long long k = hyp(lbs, I[ct] - lbs, num);
                             int lbss = L.size(cell);
                             long long k2 = 0;
-                            if (!(k == 0 || lbss == 0)) k2 = hypergeometric(g, lbss, I[cell] - lbss, k);
+                            if (!(k == 0 || lbss == 0)) k2 = hyp(lbss, I[cell] - lbss, k);
                             for (long long i = 0; i < k2; i++) {
                                 int nt = (int)floor((double)lbs * g.next_double());
                                 int ns = (int)floor((double)lbss * g.next_double());
