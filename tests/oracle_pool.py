@@ -69,6 +69,30 @@ def _work(task):
             e._susceptible[...] = Sx0
             e._infectious[...] = I0
         om = O.OracleModel.from_engine(e)
+        if kind == "curves":
+            # total infectious at fixed epidemic times and sampling-time statistics from the exported log, read on the
+            # device side's grid (value at a fixed time = the last of T+1 grid points of [0, final time] before it)
+            I0_total = int(e._infectious.sum()) or 1          # FirstInfection adds the index case
+            om.simulate(10 ** 7, sample_size=10 ** 9, epidemic_time=kw["epidemic_time"])
+            chain = om.events()
+            if chain.shape[1] <= 100:
+                continue
+            T, fixed = kw["T"], np.asarray(kw["fixed"])
+            ct = om.counters()["time"]
+            grid = np.array([i * ct / T for i in range(T + 1)])
+            at = grid[np.searchsorted(grid, fixed, side="right") - 1]
+            t, ty = chain[0], chain[1].astype(int)
+            delta = np.where((ty == 0) | (ty == 5), 1, 0) - np.where((ty == 1) | (ty == 2), 1, 0)
+            cum = np.concatenate([[0], np.cumsum(delta)])
+            inf = I0_total + cum[np.searchsorted(t, at, side="right")]
+            ts = t[ty == 2]
+            for j in range(len(fixed)):
+                put("inf_%d" % j, int(inf[j]))
+            put("samples", len(ts))
+            if len(ts):
+                put("first_sample", float(ts[0]))
+                put("mean_sample", float(ts.mean()))
+            continue
         if kind in ("direct", "tree"):
             om.simulate(kw["iterations"], sample_size=kw.get("sample_size"), epidemic_time=kw.get("epidemic_time", -1),
                         attempts=kw.get("attempts", 200))
@@ -108,7 +132,7 @@ def _work(task):
 
 
 def run(kind, name, seeds, **kw):
-    """kind: 'direct' | 'tau' | 'tree'.  Returns {statistic: np.array over runs} gathered from all workers."""
+    """kind: 'direct' | 'tau' | 'tree' | 'curves'.  Returns {statistic: np.array over runs} gathered from all workers."""
     seeds = list(seeds)
     pool = _pool()
     nchunk = max(1, min(len(seeds), 4 * pool._processes))

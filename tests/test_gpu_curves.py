@@ -9,6 +9,7 @@ import pytest
 
 from oracle import oracle as O
 from test_gpu_tau import make_engine
+import oracle_pool
 
 pytestmark = pytest.mark.gpu
 STEPS = 29
@@ -118,7 +119,7 @@ def test_curve_and_sample_time_distributions_match_oracle(name, t_end):
     and the mean / first sampling time."""
     from scipy import stats
     from test_gpu_tau import _ks_all
-    R, RO, T = 1000, 150, 64
+    R, RO, T = 1000, 400, 64
     e = make_engine(name, 9100, replicates=R)
     e.SimulatePopulation(10 ** 7, 10 ** 9, t_end, 200)
     c = e.epidemic_curves(T, want=("infectious", "sampled"))
@@ -134,26 +135,9 @@ def test_curve_and_sample_time_distributions_match_oracle(name, t_end):
         dev["inf_%d" % j] = tot[np.arange(R), idx[:, j]][alive]
     dev["samples"] = cnt["sCounter"][alive]
     keys = list(dev)
-    ora = {k: [] for k in keys}
-    ora_first, ora_mean, dev_first, dev_mean = [], [], [], []
-    for r in range(RO):
-        eo = make_engine(name, 40000 + r)
-        Sx0, I0 = first_infection(eo._susceptible, eo._infectious)
-        om = O.OracleModel.from_engine(eo)
-        om.simulate(10 ** 7, sample_size=10 ** 9, epidemic_time=t_end)
-        chain = om.events()
-        if chain.shape[1] <= 100:
-            continue
-        # same discretisation as the device side: the value at a fixed time is read at the last grid point before it
-        ct = om.counters()["time"]
-        grid = np.array([i * ct / T for i in range(T + 1)])
-        g_idx = np.searchsorted(grid, fixed, side="right") - 1
-        inf, ts = _oracle_curves(chain, int(I0.sum()), grid[g_idx])
-        for j in range(len(fixed)):
-            ora["inf_%d" % j].append(inf[j])
-        ora["samples"].append(len(ts))
-        if len(ts):
-            ora_first.append(ts[0]); ora_mean.append(ts.mean())
+    # 400 oracle runs (the configuration this test was verified with in round 1) on the host cores of the box
+    ora = oracle_pool.run("curves", name, range(40000, 40000 + RO), epidemic_time=t_end, T=T, fixed=fixed.tolist())
+    ora_first, ora_mean, dev_first, dev_mean = ora["first_sample"], ora["mean_sample"], [], []
     assert len(ora["samples"]) > 0.5 * RO
     bad = _ks_all(dev, ora, keys)
     assert not bad, bad
