@@ -260,6 +260,25 @@ class OracleRng:
 
 # --------------------------------------------------------------------------------------------------
 # The real reference (built by build_ref.py from /root/reference sources; only the built artefacts are here)
+def choose_tau(dI, dS, I, Sx):
+    """ChooseTau (src/_BirthDeath.pyx:2432-2450) on GIVEN drifts, with the reference's float epsilon product (quirk Q1).
+    Returns (tau, |drift| of the compartment that binds it, or 0 when tau stayed 1).  TEST INFRASTRUCTURE: splits a
+    tau comparison into 'same formula on the same drifts' (exact) and 'same drifts' (summation-order tolerance)."""
+    eps = np.float32(0.03)
+    tau, bind = 1.0, 0.0
+    for cnt, d in ((np.asarray(I), np.asarray(dI)), (np.asarray(Sx), np.asarray(dS))):
+        x = (eps * cnt.astype(np.float32)).astype(np.float64) / 2.0
+        ad = np.abs(d.astype(np.float64))
+        ok = ad >= 1e-8
+        if not ok.any():
+            continue
+        cand = np.where(ok, np.maximum(1.0, x) / np.where(ok, ad, 1.0), np.inf)
+        k = np.unravel_index(np.argmin(cand), cand.shape)
+        if cand[k] < tau:
+            tau, bind = float(cand[k]), float(ad[k])
+    return tau, bind
+
+
 def reference_available():
     return os.path.isdir(os.path.join(REF_DIR, "VGsim"))
 

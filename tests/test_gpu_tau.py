@@ -51,7 +51,17 @@ def test_propensities_match_oracle(name, seed, t_end):
     scale = max(np.abs(p2).sum(), 1.0)
     assert np.abs(dI - dI2).max() / scale < 1e-13
     assert np.abs(dS - dS2).max() / scale < 1e-13
-    assert abs(tau - tau2) / tau2 < 1e-9, (tau, tau2)
+    # tau = max(1, eps*count/2) / |drift| of the binding compartment (ChooseTau, :2432-2450), so its relative error IS the
+    # relative error of that one drift -- a signed sum whose error is bounded against the magnitude of its terms, not
+    # against its own (possibly cancelled) value.  Hence two exact statements instead of one loose tolerance:
+    #   (a) the device applies the reference's formula: on the device's own drifts the host restatement gives the device's
+    #       tau to the last bits;  (b) against the oracle, tau moves by no more than the drift error allows.
+    tau_h, _ = O.choose_tau(dI, dS, I, Sx)
+    assert abs(tau - tau_h) <= 4e-16 * tau_h, (tau, tau_h)
+    tau_o, bind = O.choose_tau(dI2, dS2, I, Sx)
+    assert abs(tau_o - tau2) <= 4e-16 * tau2, (tau_o, tau2)            # the restatement is the oracle's formula
+    derr = max(np.abs(dI - dI2).max(), np.abs(dS - dS2).max())
+    assert abs(tau - tau2) / tau2 <= 1e-12 + (4.0 * derr / bind if bind > 0 else 0.0), (tau, tau2, derr, bind)
 
 
 def test_default_model_propensities():

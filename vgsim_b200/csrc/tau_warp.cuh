@@ -787,6 +787,42 @@ __device__ __forceinline__ int tw_split_event(int owner, int kind, int e, const 
     return l;
 }
 
+// One round (<= 32, taken from the end of the list) of parked aggregated totals: every lane splits one total, one event
+// per iteration.  TW_SPLIT_OUTLINE 1 keeps this walk out of the drain loop's instruction footprint (a call instead of
+// ~1,200 inlined SASS instructions): in dense states, where the drain is instruction-fetch bound, totals are rare.
+#ifndef TW_SPLIT_OUTLINE
+#define TW_SPLIT_OUTLINE 0
+#endif
+template <class WSQ>
+__device__ __forceinline__ void w_split_parked_impl(int *row, const Dims &D, const WSQ &s, const double *eff, const DrawGeom &g,
+                                                    const WarpLayout &L, PhiloxCtx &ctx, LeapTally &tr, DrawState &q) {
+    const int lane = threadIdx.x & 31;
+    const int take = q.nsq < 32 ? q.nsq : 32;
+    const int e = q.nsq - take + lane;
+    const bool valid = lane < take;
+    const unsigned pw = valid ? (unsigned)s.sqp[e] : 0u;
+    const int owner = (int)(pw & 0xfffffu), kind = (pw >> 20) & 1u ? 3 : 2, ns = (int)(pw >> 21);
+#pragma unroll 1
+    for (int ev = 0; __any_sync(0xffffffffu, ev < ns); ev++) {
+        if (ev < ns) {
+            const int ls = tw_split_event(owner, kind, ev, D, s, eff, g, ctx);
+            if (ls >= 0) {
+                Channel ch;
+                const int c = tw_channel_ids(owner, ls, D, s, L, ch);
+                atomicAdd(&row[c], 1);
+                book(ch, 1, s, tr);
+            }
+        }
+    }
+    q.nsq -= take;
+    __syncwarp();
+}
+template <class WSQ>
+__device__ __noinline__ void w_split_parked(int *row, const Dims &D, const WSQ &s, const double *eff, const DrawGeom &g,
+                                            const WarpLayout &L, PhiloxCtx &ctx, LeapTally &tr, DrawState &q) {
+    w_split_parked_impl(row, D, s, eff, g, L, ctx, tr, q);
+}
+
 // Finish every queued draw and book the counts; all lanes walk the same code.
 //   * inversion entries in rounds of 32.  A channel's count is booked at once; an aggregated total that came out
 //     non-zero is parked as a (owner | kind, n) pair, and the pairs are split 32 at a time -- as soon as 32 are there,
@@ -837,25 +873,11 @@ __device__ __forceinline__ void w_drain(int *row, const Dims &D, const WSQ &s, c
         }
         // split one round of parked totals (taken from the end of the list)
         if (q.nsq >= (TW_PARK ? 32 : 1) || (!more && final && q.nsq > 0)) {
-            const int take = q.nsq < 32 ? q.nsq : 32;
-            const int e = q.nsq - take + lane;
-            const bool valid = lane < take;
-            const unsigned pw = valid ? (unsigned)s.sqp[e] : 0u;
-            const int owner = (int)(pw & 0xfffffu), kind = (pw >> 20) & 1u ? 3 : 2, ns = (int)(pw >> 21);
-#pragma unroll 1
-            for (int ev = 0; __any_sync(0xffffffffu, ev < ns); ev++) {
-                if (ev < ns) {
-                    const int ls = tw_split_event(owner, kind, ev, D, s, eff, g, ctx);
-                    if (ls >= 0) {
-                        Channel ch;
-                        const int c = tw_channel_ids(owner, ls, D, s, L, ch);
-                        atomicAdd(&row[c], 1);
-                        book(ch, 1, s, tr);
-                    }
-                }
-            }
-            q.nsq -= take;
-            __syncwarp();
+#if TW_SPLIT_OUTLINE
+            w_split_parked(row, D, s, eff, g, L, ctx, tr, q);
+#else
+            w_split_parked_impl(row, D, s, eff, g, L, ctx, tr, q);
+#endif
         }
         if (!more && !(final && q.nsq > 0)) break;
     }
