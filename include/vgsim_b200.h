@@ -129,7 +129,7 @@ int vgsim_simulate_tau(vgsim_handle h, int64_t iterations, int64_t sample_size, 
  * exceed one block per replicate (a 2,000-leap run of the K = 100 world model would need 4 GB of dense rows per replicate).
  * One call to the reference's eyes: FirstInfection (:2302-2303) only before the first block, the stop conditions of
  * :2312 carry over, the run ends when no replicate used up its block.  leap_block is raised to 101 when iterations > 100
- * so that the extinction retry of :2331 sees the same condition in every block. */
+ * so that the extinction retry of :2331 sees the same condition in every block.  The last block is archived too. */
 int vgsim_simulate_tau_blocks(vgsim_handle h, int64_t iterations, int64_t sample_size, float epidemic_time,
                               int64_t attempts, int64_t leap_block);
 /* Block until everything queued on the handle's stream has finished; returns the sticky device

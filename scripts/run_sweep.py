@@ -108,7 +108,7 @@ if rank == 0:
            "summary_bytes_gathered": int(s.nbytes), "allgather_ms_max_over_ranks": gather_ms, "ranks": recs,
            "totals": {k: float(sum(r[k] for r in recs)) for k in ("direct_events", "tau_events", "samples_total", "tree_nodes_total")},
            "slowest_rank_s": {k: max(r[k] for r in recs) for k in ("setup_s", "direct_s", "tau_s", "genealogy_s")},
-           "genealogy_note": "per rank >= 1e6 sampled cases in aggregate; trees stay in HBM, summaries are gathered"}
+           "genealogy_note": "per rank about 1e6 sampled cases in aggregate; trees stay in HBM, summaries are gathered"}
     if s.shape[0] == N0 * N1:
         rows = s.reshape(N0, N1, s.shape[1])
         out["final_time_by_R0_row_first_last"] = [float(np.median(rows[0, :, 12])), float(np.median(rows[-1, :, 12]))]

@@ -610,6 +610,9 @@ int vgsim_simulate_tau_blocks(vgsim_handle h, int64_t iterations, int64_t sample
         if (h->dense_bound < n) break;  // no replicate used up its block: every one of them met a stop condition
         if (vgsim_archive_tau_log(h)) return 1;
     }
+    // the last block as well: the readers of the log (genealogy replay, curves) then never scan a dense row -- at the world
+    // shape the rows of one block are 6-50 GB, the whole archive of the run a few hundred MB
+    if (vgsim_archive_tau_log(h)) return 1;
     CK(cudaEventRecord(k1, h->stream));
     h->ev_k0 = k0;
     h->ev_k1 = k1;
