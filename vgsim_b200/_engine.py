@@ -410,16 +410,18 @@ class BirthDeathModel:
     def SimulatePopulation(self, iterations, sample_size, time, attempts):
         """Direct (Gillespie) method, reference src/_BirthDeath.pyx:396-429."""
         h = self._sync_params()
+        size = self._log_rows() + int(iterations)      # events.size after CreateEvents(iterations)
         h.simulate_direct(int(iterations), int(sample_size), float(time), int(attempts))
         self.first_simulation = True
         self._genealogy_done = False
         self._refresh_host_state()
-        self._print_stop_reason(sample_size, time)
+        self._print_stop_reason(sample_size, time, size)
 
     def SimulatePopulation_tau(self, iterations, sample_size, time, attempts, leap_block=None):
         """Tau-leaping, reference src/_BirthDeath.pyx:2293-2346.  `leap_block` (not in the reference): run the call in
         blocks of that many leaps and keep finished blocks as a sparse archive instead of dense count rows."""
         h = self._sync_params()
+        size = self._log_rows() + int(iterations)
         if leap_block is None:
             h.simulate_tau(int(iterations), int(sample_size), float(time), int(attempts))
         else:
@@ -427,14 +429,22 @@ class BirthDeathModel:
         self.first_simulation = True
         self._genealogy_done = False
         self._refresh_host_state()
-        self._print_stop_reason(sample_size, time)
+        self._print_stop_reason(sample_size, time, size)
 
-    def _print_stop_reason(self, sample_size, time):
+    def _log_rows(self):
+        """events.ptr of replicate 0 before a call (0 before the first one)."""
+        c = getattr(self, "_counters", None)
+        return int(c['events'][0]) if c is not None and self.first_simulation else 0
+
+    def _print_stop_reason(self, sample_size, time, size):
+        """The messages of src/_BirthDeath.pyx:420-429 / :2336-2345 (single-chain use only)."""
         if self.replicates != 1:
             return
         c = self._counters
         if c['globalInfectious'][0] == 0:
             print('Simulation finished because no infections individuals remain!')
+        if int(c['events'][0]) >= size:
+            print("Achieved maximal number of iterations.")
         if c['sCounter'][0] > sample_size and sample_size != -1:
             print("Achieved sample size.")
         if c['time'][0] > time and time != -1:

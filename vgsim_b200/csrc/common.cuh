@@ -34,6 +34,9 @@ struct Dims {
     int P;        // total channels
     int Pp;       // P rounded up to a multiple of 8 (row stride of the dense log, int32 units: rows are 32-byte aligned)
     int hshift;   // log2(H)
+    // q = n / d for the runtime divisors of the channel decode (logrec.cuh): q = umulhi(n, m) with m = ceil(2^32 / d) is n / d
+    // or n / d + 1 for every n < 2^32 (the excess n * (m * d - 2^32) / (d * 2^32) is below 1), one compare fixes it up
+    unsigned mgS, mgK1, mgPD, mgS1, mgE;
     // parameter blob offsets (in doubles)
     int o_b, o_d, o_sr, o_q, o_tmq, o_sigT, o_T, o_Tc, o_m, o_A, o_sm, o_cdB, o_cdA, o_startN, o_endN,
         o_size, o_g, o_mu, o_w, o_maxB, o_cd0, blob;
@@ -52,6 +55,10 @@ __host__ __device__ inline Dims make_dims(int U, int K, int S) {
     D.NA = K * (K - 1) * S * H;
     D.P = D.NA + K * D.PD;
     D.Pp = (D.P + 7) & ~7;
+    {
+        auto magic = [](int d) { return d > 1 ? (unsigned)((0x100000000ull + (unsigned)d - 1) / (unsigned)d) : 0u; };
+        D.mgS = magic(S); D.mgK1 = magic(K - 1); D.mgPD = magic(D.PD); D.mgS1 = magic(S - 1); D.mgE = magic(D.E);
+    }
     int o = 0;
     D.o_b = o; o += H;
     D.o_d = o; o += H;
@@ -122,6 +129,17 @@ __host__ __device__ inline int mutate_hap(int h, int u, int k, int U) {
 
 // ---------------------------------------------------------------------------------------------
 // Device-resident state of a handle (all pointers are device pointers).
+// n / d through the precomputed multiplier (d >= 1; d == 1 has no multiplier)
+__host__ __device__ __forceinline__ int magic_div(int n, unsigned m, int d) {
+    if (d <= 1) return n;
+#ifdef __CUDA_ARCH__
+    int q = (int)__umulhi((unsigned)n, m);
+#else
+    int q = (int)(((unsigned long long)(unsigned)n * m) >> 32);
+#endif
+    return q * d > n ? q - 1 : q;
+}
+
 struct DevState {
     Dims D;
     int R;

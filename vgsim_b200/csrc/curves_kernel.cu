@@ -156,11 +156,20 @@ __global__ void __launch_bounds__(512, 1) curves_kernel(const DevState st, const
                     const int2 *ent = st.sp_ent + (size_t)r * st.sp_cap;
                     const int e1 = soff[leap + 1];
                     __syncwarp();
-                    for (int e = soff[leap] + lane; e < e1; e += 32) {
-                        const int2 en = __ldcs(ent + e);
-                        int mty, mh, mp, mnh, mnp;
-                        decode_record(en.x, D, pp, mty, mh, mp, mnh, mnp);
-                        curve_apply(mty, mh, mp, mnh, mnp, (long long)en.y, H, S, I, Sx, rem, smp);
+                    for (int e0 = soff[leap]; e0 < e1; e0 += 128) {  // four loads in flight per lane: one dependent 256-byte
+                        int2 en[4];                                    // load per step made the walk latency-bound
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const int e = e0 + u * 32 + lane;
+                            en[u] = e < e1 ? __ldcs(ent + e) : make_int2(-1, 0);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (en[u].x < 0) continue;
+                            int mty, mh, mp, mnh, mnp;
+                            decode_record(en[u].x, D, pp, mty, mh, mp, mnh, mnp);
+                            curve_apply(mty, mh, mp, mnh, mnp, (long long)en[u].y, H, S, I, Sx, rem, smp);
+                        }
                     }
                     __syncwarp();
                     continue;

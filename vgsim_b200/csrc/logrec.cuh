@@ -14,27 +14,27 @@ __device__ __forceinline__ void decode_record(int c, const Dims &D, const double
     if (c < D.NA) {
         int row = c >> D.hshift;
         hap = c & (H - 1);
-        int pair = row / S;
+        int pair = magic_div(row, D.mgS, S);
         nhap = row - pair * S;
-        pop = pair / (K - 1);
+        pop = magic_div(pair, D.mgK1, K - 1);
         int tpp = pair - pop * (K - 1);
         npop = tpp + (tpp >= pop ? 1 : 0);
         type = EV_MIGRATION;
         return;
     }
     int c2 = c - D.NA;
-    pop = c2 / D.PD;
+    pop = magic_div(c2, D.mgPD, D.PD);
     int r = c2 - pop * D.PD;
     npop = 0;
     if (r < D.SS1) {
-        hap = r / (S - 1);
+        hap = magic_div(r, D.mgS1, S - 1);
         int tsp = r - hap * (S - 1);
         nhap = tsp + (tsp >= hap ? 1 : 0);
         type = EV_SUSCCHANGE;
         return;
     }
     int r2 = r - D.SS1;
-    hap = r2 / D.E;
+    hap = magic_div(r2, D.mgE, D.E);
     int e = r2 - hap * D.E;
     if (e == 0) {
         type = EV_DEATH;
