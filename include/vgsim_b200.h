@@ -196,7 +196,9 @@ int vgsim_get_migrations(vgsim_handle h, int replicate, int64_t *node, double *t
  * counters, final time, and tree statistics when a genealogy exists.  out[R][VGSIM_NSUMMARY] f64:
  *   [0..11] the VGSIM_NCOUNTERS counters, [12] current time, [13] tree nodes (2n-1), [14] tree height,
  *   [15] total branch length, [16] roots (1 = fully coalesced), [17] mutation rows, [18] migration rows,
- *   [19] root time, [20] cherries, [21] Sackin index (sum of leaf depths), [22..23] reserved.
+ *   [19] root time, [20] cherries, [21] Sackin index (sum of leaf depths), [22] totalRate and [23] totalMigrationRate as
+ *   the last vgsim_simulate_direct call's incremental updates left them (UpdateRates, src/_BirthDeath.pyx:516-546; parity tap:
+ *   vgsim_rates recomputes both from the state).
  * vgsim_summaries_dev returns the DEVICE pointer of the same buffer (valid until destroy). */
 #define VGSIM_NSUMMARY 24
 int vgsim_summaries(vgsim_handle h, double *out);

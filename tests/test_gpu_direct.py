@@ -125,3 +125,26 @@ def test_direct_then_tau_continues_the_log():
     # contact density set between the calls reached the device
     _, _, cd, _ = e._handle.get_state(full=True)
     assert np.all(cd[:, 0] == 0.7) or np.any(e._handle.get_lockdowns(0)[0] == 1)
+
+
+@pytest.mark.parametrize("name,N", [("s5", 1000), ("s6", 1000), ("s9", 1000), ("t3small", 1000), ("table3_k10", 1000), ("s7", 20000)])
+def test_incremental_totals_equal_fresh_recompute(name, N):
+    """UpdateRates (src/_BirthDeath.pyx:516-546) keeps totalRate and totalMigrationRate by increments; after N events the
+    kernel's running totals must equal a fresh recompute of the whole hierarchy from the final state (vgsim_rates).
+    N = 1000 stays below the kernel's own 1,024-iteration resynchronisation, so the increments alone are checked;
+    the 20,000-event case crosses it (and lockdown flips) as well."""
+    R = 16
+    e = make_engine(name, 4242, replicates=R)
+    h = e._sync_params()
+    h.simulate_direct(N, -1, -1.0, 200)
+    s = h.summaries()
+    c = h.get_counters()
+    checked = 0
+    for r in range(R):
+        if c["globalInfectious"][r] == 0:
+            continue
+        fresh = h.rates(r)["totals"]
+        assert abs(s[r, 22] - fresh[0]) <= 1e-11 * fresh[0], (r, s[r, 22], fresh[0])
+        assert abs(s[r, 23] - fresh[1]) <= 1e-9 * max(fresh[0], fresh[1]), (r, s[r, 23], fresh[1])
+        checked += 1
+    assert checked >= R // 2

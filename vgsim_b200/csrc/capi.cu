@@ -105,7 +105,7 @@ int vgsim_create(int sites, int K, int S, int n_replicates, int n_param_points, 
         dalloc(h, &st.eff, R * K * K) || dalloc(h, &st.ceff, R * K) || dalloc(h, &st.maxEBM, R * K) ||
         dalloc(h, &st.time, R) || dalloc(h, &st.counters, R * NCOUNT) || dalloc(h, &st.epoch, R) ||
         dalloc(h, &st.err, R) || dalloc(h, &st.loc_n, R) || dalloc(h, &st.ev_base, R) || dalloc(h, &st.dense_base, R) ||
-        dalloc(h, &st.sp_n, R)) {
+        dalloc(h, &st.sp_n, R) || dalloc(h, &st.rate_tot, 2 * R)) {
         vgsim_destroy(h);
         return 1;
     }
@@ -1051,7 +1051,11 @@ __global__ void summary_kernel(DevState st, const long long *node_off, const int
         for (int i = lane; i < VGSIM_NSUMMARY; i += 32) o[i] = 0.0;
         __syncwarp();
         if (lane < NCOUNT) o[lane] = (double)st.counters[(size_t)r * NCOUNT + lane];
-        if (lane == 0) o[12] = st.time[r];
+        if (lane == 0) {
+            o[12] = st.time[r];
+            o[22] = st.rate_tot[2 * (size_t)r];
+            o[23] = st.rate_tot[2 * (size_t)r + 1];
+        }
         if (!node_off) continue;
         const int n = n_nodes[r];
         if (n == 0) continue;

@@ -156,6 +156,7 @@ struct DevState {
     double *ceff;              // [R][K]   c[p] = sum_r m[p,r]^2 cd[r]/A[r]
     double *maxEBM;            // [R][K]
     double *time;              // [R]
+    double *rate_tot;          // [R][2] the direct kernel's incrementally maintained totalRate / totalMigrationRate at its exit (parity tap)
     long long *counters;       // [R][NCOUNT]
     unsigned *epoch;           // [R] Philox stream epoch (bumped per attempt)
     int *err;                  // [R] sticky error bits

@@ -575,6 +575,10 @@ __global__ void __launch_bounds__(512, 1) direct_kernel(const __grid_constant__ 
             st.time[r] = t;
             st.epoch[r] = epoch;
             if (errbits) st.err[r] |= errbits;
+            // parity tap (UpdateRates, :516-546): the totals as the increments left them -- a fresh recompute from the final
+            // state (vgsim_rates) must give the same numbers
+            st.rate_tot[2 * (size_t)r] = Rt;
+            st.rate_tot[2 * (size_t)r + 1] = K > 1 ? fmax(ginf * mA - mB, 0.0) : 0.0;
         }
         __syncwarp();
     }
