@@ -235,6 +235,10 @@ int vgsim_set_tau_variant(vgsim_handle h, int variant);
  * 1 drifts + tau, 2 primary draws, 3 slow-path drain, 4 feasibility, 5 apply, 6 lockdown vote, 7 = #leaps)
  * summed over CTAs since the last reset.  out16[16]. */
 int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset);
+/* Same tap, the tail of a launch: out1024[2b] / [2b+1] = global-timer ns at which the first / the last warp of CTA b
+ * (b < 512) of the warp kernel ran out of replicates; slots 8-11 of vgsim_debug_tau_phases hold latest / sum / count /
+ * earliest over all warps. */
+int vgsim_debug_tau_cta_end(vgsim_handle h, uint64_t *out1024, int reset);
 
 /* Launch accounting: kernels launched by this handle since creation. */
 int64_t vgsim_launch_count(vgsim_handle h);

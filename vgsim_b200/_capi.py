@@ -80,6 +80,7 @@ def _load():
         "vgsim_launch_count": (c_int64, [P]),
         "vgsim_set_tau_variant": (c_int, [P, c_int]),
         "vgsim_debug_tau_phases": (c_int, [P, P, c_int]),
+        "vgsim_debug_tau_cta_end": (c_int, [P, P, c_int]),
         "vgsim_last_kernel_ms": (c_int, [P, ctypes.POINTER(c_float)]),
         "vgsim_last_kernel_id": (c_int64, [P]),
         "vgsim_kernel_ms": (c_int, [P, c_int64, ctypes.POINTER(c_float)]),
@@ -404,6 +405,11 @@ class Handle:
         out = np.zeros(16, np.uint64)
         _ck(lib.vgsim_debug_tau_phases(self._h, _p(out), 1 if reset else 0))
         return out
+
+    def tau_cta_end(self, reset=True):
+        out = np.zeros(1024, np.uint64)
+        _ck(lib.vgsim_debug_tau_cta_end(self._h, _p(out), 1 if reset else 0))
+        return out.reshape(512, 2)
 
     def set_tau_variant(self, variant):
         """0 = small mutation / out-migration groups drawn as one Poisson total + multinomial split (product path),

@@ -1005,6 +1005,13 @@ int vgsim_debug_tau_phases(vgsim_handle h, uint64_t *out16, int reset) {
     return 0;
 }
 
+int vgsim_debug_tau_cta_end(vgsim_handle h, uint64_t *out1024, int reset) {
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(tau_cta_end((unsigned long long *)out1024, reset));
+    return 0;
+}
+
 int vgsim_set_tau_variant(vgsim_handle h, int variant) {
     if (variant < 0 || variant > 63 || (variant & 12) == 12)
         return fail("tau variant must be 0..63 (bit 0: per-channel draws, bit 1: phase timing, bit 2: force the team kernel, bit 3: force the warp kernel, bit 4: free-running warps, bit 5: unsorted schedule)");

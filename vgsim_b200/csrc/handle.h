@@ -72,6 +72,7 @@ struct Handle {
 cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream, int num_sms, int variant, int uniform_pp,
                        int *order_buf);
 cudaError_t tau_phase_cycles(unsigned long long *out16, int reset);
+cudaError_t tau_cta_end(unsigned long long *out1024, int reset);
 cudaError_t launch_propensities(const DevState &st, int r, double *out, double *dI, double *dS, double *tau,
                                 cudaStream_t stream);
 cudaError_t launch_archive_count(const DevState &st, int *cnt, int *need, cudaStream_t stream);

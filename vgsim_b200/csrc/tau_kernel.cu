@@ -612,6 +612,7 @@ __device__ __forceinline__ void lockdown_pass(const DevState &st, int r, const D
 // Phase timing tap (variant bit 1): thread 0 of every CTA accumulates the cycles between consecutive barrier exits
 // of the leap loop, i.e. the critical path of each phase, into this buffer (read by vgsim_debug_tau_phases).
 __device__ unsigned long long g_tau_phase_cycles[16];
+__device__ unsigned long long g_tau_cta_end[1024];  // timing tap: [2b] when CTA b's first warp ran out of work, [2b+1] its last (global timer, ns)
 #define TAU_MARK(k)                                   \
     if (prof && tid == 0) {                           \
         const long long now_ = clock64();             \
@@ -1340,10 +1341,21 @@ cudaError_t launch_tau(const DevState &st, const SimArgs &a, cudaStream_t stream
     return launch_tau_cfg<1>(st, a, stream, num_sms, variant, cap);
 }
 
+cudaError_t tau_cta_end(unsigned long long *out1024, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out1024, g_tau_cta_end, 1024 * sizeof(unsigned long long));
+    if (e == cudaSuccess && reset) {
+        static unsigned long long z[1024];
+        for (int i = 0; i < 1024; i++) z[i] = (i & 1) ? 0ull : ~0ull;
+        e = cudaMemcpyToSymbol(g_tau_cta_end, z, sizeof(z));
+    }
+    return e;
+}
+
 cudaError_t tau_phase_cycles(unsigned long long *out16, int reset) {
     cudaError_t e = cudaMemcpyFromSymbol(out16, g_tau_phase_cycles, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess && reset) {
         unsigned long long z[16] = {0};
+        z[11] = ~0ull;  // slot 11 is a minimum
         e = cudaMemcpyToSymbol(g_tau_phase_cycles, z, sizeof(z));
     }
     return e;

@@ -1477,6 +1477,18 @@ __global__ void __launch_bounds__(VGSIM_TW_MAXWARPS * 32, 1)
     }
     if (prof && lane == 0)
         for (int k = 0; k < 8; k++) atomicAdd(&g_tau_phase_cycles[k], pc[k]);
+    if (prof && lane == 0) {  // timing tap: when this warp ran out of work (ns on the global timer) -- the spread over the CTAs
+        unsigned long long now;  // is the tail of the launch (slots 8: latest, 9: sum, 10: warps, 11: earliest)
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        atomicMax(&g_tau_phase_cycles[8], now);
+        atomicAdd(&g_tau_phase_cycles[9], now & 0xffffffffffull);
+        atomicAdd(&g_tau_phase_cycles[10], 1ull);
+        atomicMin(&g_tau_phase_cycles[11], now);
+        if (blockIdx.x < 512) {
+            atomicMin(&g_tau_cta_end[2 * blockIdx.x], now);
+            atomicMax(&g_tau_cta_end[2 * blockIdx.x + 1], now);
+        }
+    }
     // ---- lockstep tail: this warp is out of replicates; keep answering the generation barriers until every
     // warp is.  A warp announces itself after the last barrier of its last generation and before the first
     // barrier of the next; the counter is read between the first and the second barrier of a generation, where
