@@ -573,6 +573,68 @@ class BirthDeathModel:
         self._require_tree()
         return self._handle.get_migrations(replicate)
 
+    def export_ts_tables(self, replicate=0):
+        """The rows the reference's export_ts (src/_BirthDeath.pyx:1909-1946) hands to a tskit.TableCollection, as numpy
+        columns in the order it adds them (before `tc.sort()`): works without tskit, `export_ts` feeds them to it.
+        Times are tskit times: `times[0] - t` (time before the node 0, the reference's convention)."""
+        self._require_tree()
+        tree, pop, times = self._handle.get_tree(replicate)
+        n_nodes = len(tree)
+        L = float(self._genome_length)
+        t0 = times[0] if n_nodes else 0.0
+        child = np.arange(max(n_nodes - 1, 0), dtype=np.int64)               # rows 0 .. 2n-3: every node but the last
+        is_parent = np.zeros(n_nodes, bool)
+        is_parent[tree[child]] = True                                        # child_or_parent[self.tree[i]] = 0
+        node, AS, DS, site, mt = self._handle.get_mutations(replicate)
+        gnode, gt, gold, gnew = self._handle.get_migrations(replicate)
+        pos = self.sitesPosition.astype(np.float64)
+        pos = np.where(pos == 0, pos + 1, np.where(pos == L, pos - 1, pos))  # sites must lie strictly inside (0, L)
+        allele = np.array(['A', 'T', 'C', 'G'])
+        return {
+            "sequence_length": L,
+            "populations": self.popNum,
+            "migrations": {"left": np.zeros(len(gnode)), "right": np.ones(len(gnode)), "node": gnode.astype(np.int64),
+                           "source": gold.astype(np.int64), "dest": gnew.astype(np.int64), "time": t0 - gt},
+            "edges": {"left": np.zeros(len(child)), "right": np.full(len(child), L), "parent": tree[child].astype(np.int64),
+                      "child": child},
+            "nodes": {"flags": (~is_parent).astype(np.uint32), "time": t0 - times, "population": pop.astype(np.int64)},
+            "sites": {"position": pos, "ancestral_state": np.full(self.sites, 'A')},
+            "mutations": {"site": site.astype(np.int64), "node": node.astype(np.int64), "derived_state": allele[DS],
+                          "time": t0 - mt},
+        }
+
+    def export_ts(self, replicate=0):
+        """tskit.TreeSequence of one replicate's genealogy (reference src/_BirthDeath.pyx:1909-1946).  tskit is an
+        optional dependency here: without it use export_ts_tables()."""
+        try:
+            import tskit
+        except ImportError as e:
+            raise ImportError("export_ts needs tskit; export_ts_tables() returns the same rows as numpy columns") from e
+        tb = self.export_ts_tables(replicate)
+        tc = tskit.TableCollection()
+        tc.sequence_length = tb["sequence_length"]
+        m = tb["migrations"]
+        for i in range(len(m["node"])):
+            tc.migrations.add_row(m["left"][i], m["right"][i], int(m["node"][i]), int(m["source"][i]), int(m["dest"][i]),
+                                  float(m["time"][i]))
+        for _ in range(tb["populations"]):
+            tc.populations.add_row(None)
+        e_ = tb["edges"]
+        for i in range(len(e_["child"])):
+            tc.edges.add_row(e_["left"][i], e_["right"][i], int(e_["parent"][i]), int(e_["child"][i]))
+        nd = tb["nodes"]
+        for i in range(len(nd["time"])):
+            tc.nodes.add_row(int(nd["flags"][i]), float(nd["time"][i]), int(nd["population"][i]))
+        st = tb["sites"]
+        for i in range(len(st["position"])):
+            tc.sites.add_row(float(st["position"][i]), str(st["ancestral_state"][i]))
+        mu = tb["mutations"]
+        for i in range(len(mu["node"])):
+            tc.mutations.add_row(site=int(mu["site"][i]), node=int(mu["node"][i]), derived_state=str(mu["derived_state"][i]),
+                                 time=float(mu["time"][i]))
+        tc.sort()
+        return tc.tree_sequence()
+
     def print_mutations(self, replicate=0):
         """Reference src/_BirthDeath.pyx:1176-1179: one tuple (nodeId, DS, AS, site, time) per line."""
         self._require_tree()

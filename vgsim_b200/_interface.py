@@ -319,12 +319,20 @@ class Simulator:
         print("Vladimir Shchur, Vadim Spirin, Dmitry Sirotkin, EvgeniBurovski, Nicola De Maio, Russell Corbett-Detig")
         print("medRxiv 2021.04.21.21255891; doi: https://doi.org/10.1101/2021.04.21.21255891")
 
-    # ------------------------------------------------------------------ out of scope (plotting, printing, tskit)
+    def export_ts(self, replicate=0):
+        """tskit tree sequence of the genealogy (src/_interface.py:593); needs tskit, see export_ts_tables."""
+        return self.simulation.export_ts(replicate)
+
+    def export_ts_tables(self, replicate=0):
+        """The table rows of export_ts as numpy columns (no tskit needed)."""
+        return self.simulation.export_ts_tables(replicate)
+
+    # ------------------------------------------------------------------ out of scope (SURVEY §2: plotting, printing)
     def _out_of_scope(self, *a, **k):
-        raise NotImplementedError("outside the hot-path scope of vgsim_b200 (plotting / pretty-printing / tskit)")
+        raise NotImplementedError("outside the hot-path scope of vgsim_b200 (plotting / pretty-printing)")
 
     add_plot_infectious = add_plot_susceptible = add_legend = add_title = plot = _out_of_scope
     print_basic_parameters = print_populations = print_immunity_model = print_all = _out_of_scope
-    export_ts = export_state = set_settings = set_state = debug = _out_of_scope
+    export_state = set_settings = set_state = debug = _out_of_scope
     # print_chain / print_tree / print_recomb delegate to engine methods that do not exist upstream either
     plot_infectious = print_chain = print_tree = print_recomb = _out_of_scope
