@@ -76,8 +76,9 @@ def test_tables_follow_the_reference_loops_cpu():
     assert tb["sites"]["position"].tolist() == [1.0, 999.0]      # 0 and genome_length are moved inside (0, L)
     assert tb["nodes"]["flags"].tolist() == [1, 1, 1, 0, 0]
     try:
-        import tskit  # noqa: F401
-    except ImportError:
+        import tskit
+        tskit.TableCollection       # (the out-of-tree reference build runs with a stand-in module of that name)
+    except (ImportError, AttributeError):
         with pytest.raises(ImportError, match="export_ts_tables"):
             e.export_ts()
     else:

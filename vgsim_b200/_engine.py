@@ -608,7 +608,8 @@ class BirthDeathModel:
         optional dependency here: without it use export_ts_tables()."""
         try:
             import tskit
-        except ImportError as e:
+            tskit.TableCollection
+        except (ImportError, AttributeError) as e:
             raise ImportError("export_ts needs tskit; export_ts_tables() returns the same rows as numpy columns") from e
         tb = self.export_ts_tables(replicate)
         tc = tskit.TableCollection()
