@@ -100,6 +100,7 @@ struct TauShared {
     // fp64 state (counts are exact in fp64; kept as doubles so the rate arithmetic needs no conversions)
     SArr<double> I, Sx;       // infectious [K][H], susceptible [K][S]
     SArr<double> dI, dS, Qm;  // drifts; Q[p,h] = sum_s Sx[p,s] sigma[s,h]
+    SArr<double> Mg;          // Mg[p,s] = sum_{t != p} eff[t,p] Sx[t,s]: what deme p's emigrants meet abroad, by group (mig_total)
     SArr<double> Bp, Rp;      // per (deme, group): infection pressure sum_h sigma b I, and return flow into the group
     SArr<double> red;
     SArr<unsigned long long> nbrmask;  // [H] (H <= 64) haplotypes one substitution away from h
@@ -150,7 +151,7 @@ __host__ __device__ inline TauShared tau_layout(const Dims &D, bool store_drift,
     if (s.has_effS) o += D.K * D.K * 8;
     dbl(s.I, KH); dbl(s.Sx, KS);
     dbl(s.dI, store_drift ? KH : 0); dbl(s.dS, store_drift ? KS : 0); dbl(s.Qm, KH);
-    dbl(s.Bp, KS); dbl(s.Rp, KS);
+    dbl(s.Bp, KS); dbl(s.Rp, KS); dbl(s.Mg, KS);
     dbl(s.red, 64);
     u64(s.nbrmask, s.use_masks ? D.H : 0); u64(s.rowmask, s.use_masks ? D.K : 0);
     i32(s.chkI, KH); i32(s.updI, KH); i32(s.act, KH);
@@ -374,6 +375,18 @@ __device__ __forceinline__ void q_pass(const Dims &D, const TauShared &s) {
         for (int sn = 0; sn < S; sn++) Q += s.Sx[p * S + sn] * s.sigT[sn * H + h];
         s.Qm[i] = Q;
     }
+}
+
+// Mg[p,s] = sum_{t != p} eff[t,p] Sx[t,s] (needs only Sx; runs beside q_pass).  Same loop order in the warp kernel.
+template <class SH>
+__device__ __forceinline__ void mig_pressure(int i, const Dims &D, const SH &s, const double *eff) {
+    const int K = D.K, S = D.S;
+    const int p = i / S, sn = i - p * S;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int tp = 0; tp < K; tp++)
+        if (tp != p) acc += eff[tp * K + p] * s.Sx[tp * S + sn];
+    s.Mg[i] = acc;
 }
 
 // Net drift of infectious cell i = (p,h): force of infection (own deme + migration from every deme holding h),
@@ -723,23 +736,16 @@ __device__ __forceinline__ DrawGeom draw_geom(const Dims &D) {
 #endif
 static_assert(TAU_THETA_MUT < 10.0 && TAU_THETA_MIG < 10.0, "aggregated totals are drawn by inversion (lambda < 10)");
 
-// total out-migration propensity of cell (p,h): sum over targets and groups of the channel propensities,
-// factorised through Q[tp,h] = sum_s Sx[tp,s] sigma[s,h]
+// total out-migration propensity of cell (p,h): the sum over targets t and groups s of the channel propensities
+// I b[h] m[p,p] eff[t,p] Sx[t,s] sigma[s,h], with the sum over targets taken once per leap and (deme, group):
+// sum_s sigma[s,h] Mg[p,s] -- S multiply-adds per cell instead of (K-1) S (the targets' Q[t,h] = sum_s Sx[t,s] sigma[s,h]
+// were 7 % of a dense leap's instructions in the warp kernel, whose Q table no longer fits when most haplotypes are present)
 template <class SH>
 __device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims &D, const SH &s, const double *eff) {
+    (void)eff;
     double acc = 0.0;
-    if constexpr (SH::has_qin) {  // warp kernel: the per-leap Q table, row stride and column hoisted out of the loop
-        const int stride = s.cnt[4];
-        if (stride > 0) {
-            const double *tab = s.qtab.ptr() + s.hidx[h];
 #pragma unroll 1
-            for (int tp = 0; tp < D.K; tp++)
-                if (tp != p) acc += eff[tp * D.K + p] * tab[tp * stride];
-            return Ii * s.b[h] * s.mdiag[p] * acc;
-        }
-    }
-    for (int tp = 0; tp < D.K; tp++)
-        if (tp != p) acc += eff[tp * D.K + p] * s.Qm[tp * D.H + h];
+    for (int sn = 0; sn < D.S; sn++) acc += s.sigT[sn * D.H + h] * s.Mg[p * D.S + sn];
     return Ii * s.b[h] * s.mdiag[p] * acc;
 }
 
@@ -948,6 +954,7 @@ __global__ void __launch_bounds__(TAU_TEAM * TEAMS, 1) tau_kernel(const __grid_c
                     if (!lists_ready) write_lists(D, s);
                     lists_ready = true;
                     q_pass(D, s);
+                    for (int i = threadIdx.x; i < D.K * D.S; i += blockDim.x) mig_pressure(i, D, s, eff);
                     align_teams();  // generation barrier 2 of 5
                     TAU_MARK(0)
                     // ---- 1-2. drifts and tau (the barriers also order the zero-fill before the scatter below)
@@ -1233,6 +1240,7 @@ __global__ void __launch_bounds__(256) propensity_kernel(const __grid_constant__
     load_replicate(st, r, D, s, pp, eff_g);
     const double *eff = s.has_effS ? (const double *)s.effS.ptr() : eff_g;
     q_pass(D, s);
+    for (int i = threadIdx.x; i < D.K * D.S; i += blockDim.x) mig_pressure(i, D, s, eff);
     team_sync();
     double tau = drifts_and_tau(D, s, eff, 0);
     for (int c = threadIdx.x; c < D.P; c += blockDim.x) {

@@ -191,7 +191,7 @@ struct WS {
     WArr<double> qmax;  // [0]: largest mutation channel rate of the parameter point (bounds the inflow into empty cells)
     WGq q;
     WArr<int> g;
-    WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp;
+    WArr<double> cd, c, maxEBM, effS, Sx, Bp, Rp, Mg;
     WIval I;
     WQval Qm;
     WArr<int> Iraw, chkI, updI, dSx, lock, tot, dstart, colcnt, colmask, hlist, qhi, qoc, sqp, cnt;
@@ -222,6 +222,7 @@ inline WS make_ws(const WarpLayout &L, const Dims &D) {
     s.g.off = pb + L.p_g; s.g.scale = ps;
     s.cd = Wd(L.w_cd); s.c = Wd(L.w_c); s.maxEBM = Wd(L.w_maxEBM); s.effS = Wd(L.w_eff);
     s.Sx = Wd(L.w_Sx); s.Bp = Wd(L.w_Bp); s.Rp = Wd(L.w_Rp);
+    s.Mg = s.Rp;  // the return-flow sums are dead once the susceptible drifts are done: Mg takes their place until the next leap
     s.Iraw = Wi(L.w_I); s.I.raw = s.Iraw;
     s.chkI = Wi(L.w_chk); s.updI = Wi(L.w_upd); s.act.off = wb + L.w_act; s.act.scale = ws; s.dSx = Wi(L.w_dSx); s.lock = Wi(L.w_lock);
     s.tot = Wi(L.w_tot); s.dstart = Wi(L.w_dstart); s.colcnt = Wi(L.w_colcnt); s.colmask = Wi(L.w_colmask);
@@ -622,6 +623,10 @@ __device__ __forceinline__ double w_drifts_and_tau(const Dims &D, const WSQ &s, 
     // ---- B2. susceptible drifts
 #pragma unroll 1
     for (int i = lane; i < KS; i += 32) candidate(drift_S_cell(i, D, s, eff), s.Sx[i]);
+    // ---- C. Mg[p,s] for the out-migration totals of the draws (overwrites Rp, which nobody reads any more)
+    __syncwarp();
+#pragma unroll 1
+    for (int i = lane; i < KS; i += 32) mig_pressure(i, D, s, eff);
     return warp_min_d(tmin);
 }
 
