@@ -148,3 +148,21 @@ def test_incremental_totals_equal_fresh_recompute(name, N):
         assert abs(s[r, 23] - fresh[1]) <= 1e-9 * max(fresh[0], fresh[1]), (r, s[r, 23], fresh[1])
         checked += 1
     assert checked >= R // 2
+
+
+def test_contact_density_property_follows_lockdowns():
+    """The reference's CheckLockdown overwrites contactDensity (src/_BirthDeath.pyx:698-710), so the `contact_density`
+    property shows the lockdown value afterwards; a later simulate call must not put the pre-lockdown value back."""
+    e = make_engine("example", 1234)
+    before = e.contact_density.copy()
+    e.SimulatePopulation(10 ** 7, 10 ** 9, 90.0, 200)
+    h = e._handle
+    _, _, cd, lock = h.get_state(full=True)
+    assert lock[0].sum() > 0, "the example model locks demes down by t = 90"
+    assert np.array_equal(e.contact_density, cd[0]) and not np.array_equal(e.contact_density, before)
+    locked = lock[0] == 1
+    assert np.allclose(e.contact_density[locked], e.contactDensityAfterLockdown[locked])
+    e.SimulatePopulation(1000, 10 ** 9, -1, 200)      # continues from the live densities
+    _, _, cd2, lock2 = h.get_state(full=True)
+    same = lock2[0] == lock[0]
+    assert np.array_equal(cd2[0][same], cd[0][same])

@@ -400,9 +400,11 @@ class BirthDeathModel:
         return h
 
     def _refresh_host_state(self):
-        Sx, I = self._handle.get_state()
+        Sx, I, cd, _ = self._handle.get_state(full=True)
         self._susceptible[...] = Sx[0]
         self._infectious[...] = I[0]
+        # CheckLockdown rewrites contactDensity in place (src/_BirthDeath.pyx:698-710): the property shows the live value
+        self.contactDensity[...] = cd[0]
         c = self._handle.get_counters()
         self._counters = c
 
