@@ -749,6 +749,45 @@ __device__ __forceinline__ double mig_total(int p, int h, double Ii, const Dims 
     return Ii * s.b[h] * s.mdiag[p] * acc;
 }
 
+// One event of an aggregated out-migration total of cell (p,h): its local channel, or -1 when every weight is zero.
+// Shared by both kernels (same arithmetic, same pick for the same uniform).
+template <class SH>
+__device__ __forceinline__ int split_migration(int p, int h, double u, const Dims &D, const SH &s, const double *eff) {
+    const int K = D.K, H = D.H, S = D.S;
+    double tot = 0.0;
+#pragma unroll 1
+    for (int sn = 0; sn < S; sn++) tot += s.sigT[sn * H + h] * s.Mg[p * S + sn];
+    const double x = u * tot;
+    double acc = 0.0, before = 0.0;
+    int ssel = -1;
+#pragma unroll 1
+    for (int sn = 0; sn < S; sn++) {
+        const double wt = s.sigT[sn * H + h] * s.Mg[p * S + sn];
+        if (wt > 0.0) {
+            ssel = sn;
+            before = acc;
+            acc += wt;
+            if (x < acc) break;
+        }
+    }
+    if (ssel < 0) return -1;
+    const double sg = s.sigT[ssel * H + h], x2 = x - before;  // x2 in [0, sigma[ssel,h] * Mg[p,ssel])
+    double acc2 = 0.0;
+    int tsel = -1;
+#pragma unroll 1
+    for (int tp = 0; tp < K; tp++) {
+        if (tp == p) continue;
+        const double pr = eff[tp * K + p] * s.Sx[tp * S + ssel] * sg;
+        if (pr > 0.0) {
+            tsel = tp;
+            acc2 += pr;
+            if (x2 < acc2) break;
+        }
+    }
+    if (tsel < 0) return -1;
+    return D.E + (tsel - (tsel > p ? 1 : 0)) * S + ssel;
+}
+
 // One primary draw: nothing to do for lam == 0 (numpy's random_poisson(0) consumes no randomness either); a
 // count that the top 32 bits of the uniform already prove to be 0 is settled here; everything else goes to
 // the slow-path queue (inversion entries from the bottom, PTRS entries from the top) or, for group totals
@@ -794,36 +833,10 @@ __device__ __forceinline__ int split_total_impl(int n, int p, int h, int code, i
                     if (x < acc) break;
                 }
             }
-        } else {  // out-migration: first the target deme by eff[tp,p] Q[tp,h], then the group
-            const double common = Ii * s.b[h] * s.mdiag[p];
-            double tot = 0.0;
-            for (int tp = 0; tp < K; tp++)
-                if (tp != p) tot += eff[tp * K + p] * s.Qm[tp * H + h];
-            double x = u * tot, acc = 0.0, before = 0.0;
-            int tsel = -1;
-            for (int tp = 0; tp < K; tp++) {
-                if (tp == p) continue;
-                double wt = eff[tp * K + p] * s.Qm[tp * H + h];
-                if (wt > 0.0) {
-                    tsel = tp;
-                    before = acc;
-                    acc += wt;
-                    if (x < acc) break;
-                }
-            }
-            if (tsel >= 0) {
-                double x2 = (x - before) * common, acc2 = 0.0;
-                int ssel = -1;
-                for (int sn = 0; sn < S; sn++) {
-                    double pr = eff[tsel * K + p] * s.Sx[tsel * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
-                    if (pr > 0.0) {
-                        ssel = sn;
-                        acc2 += pr;
-                        if (x2 < acc2) break;
-                    }
-                }
-                if (ssel >= 0) l = D.E + (tsel - (tsel > p ? 1 : 0)) * S + ssel;
-            }
+        } else {  // out-migration: the channel (target t, group s) has weight eff[t,p] Sx[t,s] sigma[s,h] (the cell's common
+                  // factor cancels).  First the group by sigma[s,h] Mg[p,s] (Mg = the sum over targets, once per leap), then
+                  // the target inside the group with what is left of the uniform: S + K - 1 terms, no Q[t,h] needed.
+            l = split_migration(p, h, u, D, s, eff);
         }
         if (l >= 0) {
             Channel ch;

@@ -754,40 +754,7 @@ __device__ __forceinline__ int tw_split_event(int owner, int kind, int e, const 
             }
         }
     } else {
-        const double common = Ii * s.b[h] * s.mdiag[p];
-        double tot = 0.0;
-#pragma unroll 1
-        for (int tp = 0; tp < K; tp++)
-            if (tp != p) tot += eff[tp * K + p] * s.Qm[tp * H + h];
-        const double x = u * tot;
-        double acc = 0.0, before = 0.0;
-        int tsel = -1;
-#pragma unroll 1
-        for (int tp = 0; tp < K; tp++) {
-            if (tp == p) continue;
-            const double wt = eff[tp * K + p] * s.Qm[tp * H + h];
-            if (wt > 0.0) {
-                tsel = tp;
-                before = acc;
-                acc += wt;
-                if (x < acc) break;
-            }
-        }
-        if (tsel >= 0) {
-            const double x2 = (x - before) * common;
-            double acc2 = 0.0;
-            int ssel = -1;
-#pragma unroll 1
-            for (int sn = 0; sn < S; sn++) {
-                const double pr = eff[tsel * K + p] * s.Sx[tsel * S + sn] * Ii * s.b[h] * s.sigT[sn * H + h] * s.mdiag[p];
-                if (pr > 0.0) {
-                    ssel = sn;
-                    acc2 += pr;
-                    if (x2 < acc2) break;
-                }
-            }
-            if (ssel >= 0) l = D.E + (tsel - (tsel > p ? 1 : 0)) * S + ssel;
-        }
+        l = split_migration(p, h, u, D, s, eff);
     }
     return l;
 }
