@@ -46,6 +46,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+WARM_CAP = 600000   # log capacity of the reference's direct warm-up (the longest T3 epidemics have ~3e5 events by t = 60)
 T_WARM = 60.0
 SEED0 = 1000
 WORKLOAD = "T3 tau-leap: 3 sites (64 haplotypes) x 10 demes x 3 susceptibility groups, 1e6/deme"
@@ -102,6 +103,7 @@ def cpu_worker(seed, reps, leaps, scenario):
     n_leaps = 0
     t_direct = 0.0
     n_direct_ev = 0
+    t_loop0 = time.perf_counter()
     for r in range(reps):
         if use_ref:
             def fresh():
@@ -112,7 +114,7 @@ def cpu_worker(seed, reps, leaps, scenario):
                 # pass 1 learns the warm-up's row count; pass 2 repeats it with iterations == that count so the
                 # tau call's log allocation is exactly `leaps` rows (avoids reference quirk Q3)
                 m = fresh()
-                m.SimulatePopulation(2000000, 10 ** 9, T_WARM, 200)
+                m.SimulatePopulation(WARM_CAP, 10 ** 9, T_WARM, 200)
                 import tempfile
                 with tempfile.TemporaryDirectory() as d:
                     m.export_chain_events(os.path.join(d, "c"))
@@ -159,7 +161,8 @@ def cpu_worker(seed, reps, leaps, scenario):
         t_alloc = (time.perf_counter() - t0) / 3 * reps
     print(json.dumps({"events": int(events), "leaps": int(n_leaps), "seconds": t_tau, "P": P,
                       "kind": "reference" if use_ref else "port", "direct_events": int(n_direct_ev),
-                      "direct_seconds": t_direct, "alloc_seconds": t_alloc}))
+                      "direct_seconds": t_direct, "alloc_seconds": t_alloc,
+                      "wall_seconds": time.perf_counter() - t_loop0}))
     sys.stdout.flush()
     # the reference's destructor can abort at interpreter teardown (free(): invalid pointer): run the registered exit
     # hooks (the driver's record of loaded .so files among them) explicitly, then leave without teardown
@@ -206,18 +209,30 @@ def run_cpu_sample(scenario, leaps, reps_per_worker, seed_base):
                 direct_events_per_s=drate, events_per_s_excl_alloc=rate_xa)
 
 
-def calibrate_cpu_reps(scenario, leaps, target_seconds):
-    """One replicate on one core to size the sample (reference T3: ~2 ms per leap on one core)."""
-    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(SEED0), "1", str(leaps), scenario]
+def calibrate_cpu_reps(scenario, leaps, target_seconds, wall_budget=None):
+    """Two replicates on one core to size the sample (reference T3: ~2 ms per leap on one core).  `target_seconds` bounds
+    the TIMED tau seconds per worker, `wall_budget` (optional) everything a worker does for one sample -- the untimed
+    direct warm-up of every replicate included -- plus the start-up of the worker process itself."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(SEED0), "2", str(leaps), scenario]
+    t0 = time.perf_counter()
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    wall = time.perf_counter() - t0
     o = [json.loads(l) for l in out.splitlines() if l.startswith("{")][0]
-    return max(1, int(round(target_seconds / max(o["seconds"], 1e-3))))
+    reps = max(1, int(round(target_seconds / max(o["seconds"] / 2, 1e-3))))
+    if wall_budget is not None:
+        per_rep = max(o.get("wall_seconds", o["seconds"]) / 2, 1e-3)
+        startup = max(wall - o.get("wall_seconds", o["seconds"]), 0.0)
+        reps = max(1, min(reps, int((wall_budget - startup) / per_rep)))
+    return reps
 
 
 def reference_arm(args, rank):
     if rank != 0:
         return
-    reps = calibrate_cpu_reps(args.scenario, args.leaps, args.cpu_seconds)
+    # Every step is a bounded sample of the workload, sized so that the whole --steps K --warmup W run ends within a few
+    # minutes on the box's host cores (VGSIM_REF_BUDGET_S, default 150 s of wall clock for the K + W samples together).
+    budget = float(os.environ.get("VGSIM_REF_BUDGET_S", "150"))
+    reps = calibrate_cpu_reps(args.scenario, args.leaps, args.cpu_seconds, budget / max(args.steps + args.warmup, 1))
     for _ in range(args.warmup):
         run_cpu_sample(args.scenario, args.leaps, 1, SEED0 + 500000)
     t_events = 0
