@@ -221,7 +221,7 @@ int vgsim_epidemic_curves(vgsim_handle h, int rep_first, int rep_count, int step
 
 /* Parity tap.  Variant 0 (default, product): per infectious cell the kernel draws ONE Poisson for the total of
  * its mutation channels and ONE for the total of its out-migration channels whenever that total's lambda is
- * <= 0.25, and splits a non-zero total multinomially over the group's channels (independent Poissons
+ * <= 0.25 (mutation) / 0.5 (out-migration), and splits a non-zero total multinomially over the group's channels (independent Poissons
  * conditioned on their sum are multinomial, so the joint distribution is unchanged).  Variant 1 draws every
  * channel separately, exactly like the reference's GenerateEvents_tau (src/_BirthDeath.pyx:2454-2532);
  * tests compare both with theory and with each other.

@@ -66,8 +66,9 @@ inline WarpLayout warp_layout(const Dims &D, bool par_shared, int pp0, int max_b
     L.use_masks = (H <= 64 && K <= 32) ? 1 : 0;
     L.has_eff = tau_eff_in_smem(D) ? 1 : 0;
 #ifndef VGSIM_TW_QCAP
-#define VGSIM_TW_QCAP 96    // >= 64: half a round (two words per lane) must fit an empty queue.  96 leaves the per-leap Q
-                            // table room for ~17 present haplotypes at the T3 shape (4.58 -> 4.44 ms at t = 60 against 128)
+#define VGSIM_TW_QCAP 112   // >= 64: half a round (two words per lane) must fit an empty queue.  Round 2, final kernel
+                            // (ms at t = 60 / 90 / 120): 96 entries 4.39 / 12.64 / 26.34, 112 entries 4.36 / 12.32 / 25.95 -- the
+                            // out-migration totals no longer read the per-leap Q table, so the queue gets the room
 #endif
     L.qcap = VGSIM_TW_QCAP;
     L.xcap = 64;
